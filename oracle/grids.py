@@ -183,7 +183,7 @@ class Grid:
     def _inverse_from_A(self, A: np.ndarray, patch_splines, tile: "Grid", physical: np.ndarray):
         """A: patch spectral [S_patch, V] (self is the PATCH) -> tile.physical[:, :, :]."""
         t = tile
-        off = t.params.patchOffsetL
+        off = t.params.patchOffsetL - self.params.patchOffsetL
         rows = slice(off, off + t.rDim)
         for v in range(self.V):
             Av = A[:, v].reshape(self.b_zDim, self.ncolp, self.b_rDim)[:, :t.ncolp, :]

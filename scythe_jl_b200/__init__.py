@@ -1,0 +1,10 @@
+"""scythe_jl_b200 -- B200 (sm_100a) implementation of the Scythe.jl semi-spectral transform and
+time-step hot path behind the reference's API names.  See DESIGN.md / INTEGRATION.md.
+
+Importing the package does not load the CUDA library; the first grid/model creation does, and it
+fails loudly if ``libscythe_b200.so`` has not been built (there is no CPU fallback).
+"""
+from .api import (Chebyshev, CubicBSpline, DomainError, Grid, GridParameters, Model, ModelParameters,  # noqa: F401
+                  ReferenceState, ScytheError, UnsupportedError, calcTileSizes, checkCFL, createGrid,
+                  getGridpoints, gridTransform, integrate_model, num_columns, read_physical_grid,
+                  spectralTransform, splineTransform, tileTransform, tile_grid_params, write_grid)

@@ -1,0 +1,553 @@
+"""Host-side mirror of the Scythe.jl / Springsteel.jl API for the semi-spectral hot path.
+
+Julia is not installed in this image, so the host side above the C ABI is written in Python
+with the reference's names, argument meaning and error behaviour (the ``!`` of the mutating
+Julia functions is dropped):
+
+==============================  ===========================================================
+reference (Julia)               here
+==============================  ===========================================================
+``GridParameters(; ...)``        :class:`GridParameters`          src/spectralGrid.jl:20-45
+``CubicBSpline.R0 ...``          :class:`CubicBSpline` constants  models/cha_bell2024/*.jl
+``createGrid(gp)``               :func:`createGrid`               src/semiimplicit.jl:130
+``spectralTransform!(grid)``     :func:`spectralTransform`        src/semiimplicit.jl:135,734
+``gridTransform!(grid)``         :func:`gridTransform`            src/semiimplicit.jl:136
+``splineTransform!(...)``        :func:`splineTransform`          src/semiimplicit.jl:237,285
+``tileTransform!(...)``          :func:`tileTransform`            src/semiimplicit.jl:241,305
+``calcTileSizes(patch, n)``      :func:`calcTileSizes`            src/semiimplicit.jl:141
+``getGridpoints(grid)``          :func:`getGridpoints`            src/semiimplicit.jl:59
+``num_columns(grid)``            :func:`num_columns`              src/semiimplicit.jl:308
+``ModelParameters(; ...)``       :class:`ModelParameters`         src/Scythe.jl:8-21
+``integrate_model(model)``       :func:`integrate_model`          src/Scythe.jl:37-62
+``initialize_model/run_model``   :class:`Model`                   src/semiimplicit.jl:126-299
+==============================  ===========================================================
+
+Arrays are NumPy float64 in Fortran (column-major) order so that ``grid.physical[i, v, d]``
+and ``grid.spectral[s, v]`` index exactly like the Julia arrays (0-based).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field, replace
+
+import numpy as np
+
+from . import _lib
+from ._lib import DomainError, ScytheError, UnsupportedError  # noqa: F401  (re-exported)
+
+
+class CubicBSpline:
+    """Radial boundary-condition descriptors, same dictionaries as Springsteel's CubicBSpline."""
+    R0 = {"R0": 0}
+    R1T0 = {"α1": -4.0, "β1": -1.0}
+    R1T1 = {"α1": 0.0, "β1": 1.0}
+    R1T2 = {"α1": 2.0, "β1": -1.0}
+    R2T10 = {"α2": 1.0, "β2": -0.5}
+    R2T20 = {"α2": -1.0, "β2": 0.0}
+    R3 = {"R3": 0}
+    PERIODIC = {"PERIODIC": 0}
+    mubar = 3
+    _names = ("R0", "R1T0", "R1T1", "R1T2", "R2T10", "R2T20", "R3", "PERIODIC")
+
+    @classmethod
+    def code(cls, bc: dict) -> int:
+        for n in cls._names:
+            if getattr(cls, n) == bc:
+                return _lib.SPLINE_BC[n]
+        raise ValueError(f"unknown CubicBSpline boundary condition {bc!r}")
+
+
+class Chebyshev:
+    """Vertical boundary-condition descriptors (Springsteel's Chebyshev module)."""
+    R0 = {"R0": 0}
+    R1T0 = {"α0": 0.0}
+    R1T1 = {"α1": 0.0}
+    R1T2 = {"α2": 0.0}
+    _names = ("R0", "R1T0", "R1T1", "R1T2")
+
+    @classmethod
+    def code(cls, bc: dict) -> int:
+        for n in cls._names:
+            if getattr(cls, n) == bc:
+                return _lib.CHEB_BC[n]
+        raise ValueError(f"unknown Chebyshev boundary condition {bc!r}")
+
+
+@dataclass
+class GridParameters:
+    """src/spectralGrid.jl:20-45; derived fields are properties."""
+    geometry: str = "R"
+    xmin: float = 0.0
+    xmax: float = 0.0
+    num_cells: int = 0
+    l_q: float = 2.0
+    BCL: dict = field(default_factory=lambda: dict(CubicBSpline.R0))
+    BCR: dict = field(default_factory=lambda: dict(CubicBSpline.R0))
+    zmin: float = 0.0
+    zmax: float = 0.0
+    zDim: int = 0
+    b_zDim: int = -1
+    BCB: dict = field(default_factory=lambda: dict(Chebyshev.R0))
+    BCT: dict = field(default_factory=lambda: dict(Chebyshev.R0))
+    vars: dict = field(default_factory=lambda: {"u": 1})
+    spectralIndexL: int = 1
+    tile_num: int = 0
+
+    def __post_init__(self):
+        if self.b_zDim < 0:
+            self.b_zDim = min(self.zDim, (2 * self.zDim - 1) // 3 + 1) if self.zDim > 0 else 0
+
+    @property
+    def rDim(self):
+        return self.num_cells * CubicBSpline.mubar
+
+    @property
+    def b_rDim(self):
+        return self.num_cells + 3
+
+    @property
+    def spectralIndexR(self):
+        return self.spectralIndexL + self.b_rDim - 1
+
+    @property
+    def patchOffsetL(self):
+        return (self.spectralIndexL - 1) * 3
+
+    @property
+    def patchOffsetR(self):
+        return self.patchOffsetL + self.rDim
+
+    def var_names(self):
+        return [k for k, _ in sorted(self.vars.items(), key=lambda kv: kv[1])]
+
+    def _bc(self, which, name):
+        d = getattr(self, which)
+        return d[name] if (name in d and isinstance(d[name], dict)) else d
+
+
+def _c_grid_params(gp: GridParameters):
+    """GridParameters -> (sb_grid_params, keep-alive objects)."""
+    if gp.geometry == "Z":
+        raise DomainError(_lib.SB_EDOMAIN, "Z column model not implemented yet")
+    if gp.geometry not in _lib.GEOM:
+        raise DomainError(_lib.SB_EDOMAIN, "Unknown geometry")
+    names = gp.var_names()
+    V = len(names)
+    arr = lambda codes: (C.c_int32 * V)(*codes)  # noqa: E731
+    bcl = arr([CubicBSpline.code(gp._bc("BCL", n)) for n in names])
+    bcr = arr([CubicBSpline.code(gp._bc("BCR", n)) for n in names])
+    bcb = arr([Chebyshev.code(gp._bc("BCB", n)) for n in names])
+    bct = arr([Chebyshev.code(gp._bc("BCT", n)) for n in names])
+    p = _lib.sb_grid_params(
+        geometry=_lib.GEOM[gp.geometry], nvars=V, xmin=gp.xmin, xmax=gp.xmax, num_cells=gp.num_cells, l_q=gp.l_q,
+        zmin=gp.zmin, zmax=gp.zmax, zDim=gp.zDim, b_zDim=gp.b_zDim if gp.b_zDim > 0 else 0,
+        spectralIndexL=gp.spectralIndexL, tile_num=gp.tile_num,
+        BCL=C.cast(bcl, _lib.c_i32p), BCR=C.cast(bcr, _lib.c_i32p), BCB=C.cast(bcb, _lib.c_i32p),
+        BCT=C.cast(bct, _lib.c_i32p))
+    return p, (bcl, bcr, bcb, bct)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_f64p)
+
+
+class Grid:
+    """A spectral grid (patch or tile) whose transforms run on the GPU.
+
+    ``physical`` [N,V,D] and ``spectral`` [S,V] are host mirrors (what Julia code indexes);
+    the transform functions copy the slots they consume to the device, run the kernels and
+    copy the result back -- the reference's host-array semantics.  ``resident=True`` skips the
+    copies for callers that drive the device buffers themselves (:class:`Model`, bench).
+    """
+
+    def __init__(self, gp: GridParameters, device: int = 0, lib: _lib.Library | None = None, handle=None):
+        self.lib = lib or _lib.load()
+        self.params = gp
+        self._own = handle is None
+        if handle is None:
+            cp, keep = _c_grid_params(gp)
+            h = _lib.grid_t()
+            self.lib.check(self.lib.sb_grid_create(C.byref(cp), device, None, C.byref(h)))
+            handle = h
+        self.handle = handle
+        info = _lib.sb_grid_info()
+        self.lib.check(self.lib.sb_grid_get_info(self.handle, C.byref(info)))
+        self.info = info
+        for n, _ in info._fields_:
+            setattr(self, n, int(getattr(info, n)))
+        self.lDim_h = self.lDim
+        self._physical = None
+        self._spectral = None
+        self.resident = False
+
+    # host mirrors, allocated on first touch
+    @property
+    def physical(self) -> np.ndarray:
+        if self._physical is None:
+            self._physical = np.zeros((self.N, self.V, self.D), order="F")
+        return self._physical
+
+    @property
+    def spectral(self) -> np.ndarray:
+        if self._spectral is None:
+            self._spectral = np.zeros((self.S, self.V), order="F")
+        return self._spectral
+
+    def close(self):
+        if self._own and self.handle is not None:
+            self.lib.sb_grid_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # explicit device <-> host movement
+    def upload_physical(self, slot0=0, nslots=1):
+        a = np.asfortranarray(self.physical[:, :, slot0:slot0 + nslots])
+        self.lib.check(self.lib.sb_grid_set_physical(self.handle, _ptr(a), slot0, nslots))
+
+    def download_physical(self, slot0=0, nslots=None):
+        nslots = self.D - slot0 if nslots is None else nslots
+        a = np.empty((self.N, self.V, nslots), order="F")
+        self.lib.check(self.lib.sb_grid_get_physical(self.handle, _ptr(a), slot0, nslots))
+        self.physical[:, :, slot0:slot0 + nslots] = a
+        return self.physical
+
+    def upload_spectral(self, which=0, array=None):
+        a = np.asfortranarray(self.spectral if array is None else array)
+        self.lib.check(self.lib.sb_grid_set_spectral(self.handle, which, _ptr(a)))
+
+    def download_spectral(self, which=0, out=None):
+        a = self.spectral if out is None else out
+        assert a.flags.f_contiguous
+        self.lib.check(self.lib.sb_grid_get_spectral(self.handle, which, _ptr(a)))
+        return a
+
+    def sync(self):
+        self.lib.check(self.lib.sb_grid_sync(self.handle))
+
+
+def createGrid(gp: GridParameters, device: int = 0, lib=None) -> Grid:
+    return Grid(gp, device=device, lib=lib)
+
+
+def getGridpoints(grid: Grid) -> np.ndarray:
+    out = np.empty((grid.N, grid.ndims), order="F")
+    grid.lib.check(grid.lib.sb_grid_get_gridpoints(grid.handle, _ptr(out), out.size))
+    return out[:, 0].copy() if grid.ndims == 1 else out
+
+
+def num_columns(grid: Grid) -> int:
+    return grid.num_columns
+
+
+def spectralTransform(grid: Grid):
+    """physical[:, :, 0] -> spectral (B coefficients)."""
+    if not grid.resident:
+        grid.upload_physical(0, 1)
+    grid.lib.check(grid.lib.sb_spectral_transform(grid.handle))
+    if not grid.resident:
+        grid.download_spectral(0)
+    return grid.spectral
+
+
+def gridTransform(grid: Grid):
+    """spectral (B) -> A -> physical[:, :, 0:D]; ``spectral`` keeps B."""
+    if not grid.resident:
+        grid.upload_spectral(0)
+    grid.lib.check(grid.lib.sb_grid_transform(grid.handle))
+    if not grid.resident:
+        grid.download_physical(0)
+    return grid.physical
+
+
+def splineTransform(patch: Grid, patchSpectral: np.ndarray | None, sharedSpectral: np.ndarray | None):
+    """B (sharedSpectral, patch-sized) -> A (patchSpectral).  Arrays may be None when resident."""
+    if sharedSpectral is not None:
+        patch.upload_spectral(0, sharedSpectral)
+    patch.lib.check(patch.lib.sb_spline_transform(patch.handle, patch.handle))
+    if patchSpectral is not None:
+        patch.download_spectral(1, patchSpectral)
+    return patchSpectral
+
+
+def tileTransform(patch: Grid, patchSpectral: np.ndarray | None, tile: Grid):
+    """patch A -> tile.physical at the tile's own points."""
+    if patchSpectral is not None:
+        patch.upload_spectral(1, patchSpectral)
+    patch.lib.check(patch.lib.sb_tile_transform(patch.handle, tile.handle))
+    if not tile.resident:
+        tile.download_physical(0)
+    return tile.physical
+
+
+def calcTileSizes(patch, num_tiles: int, lib=None) -> np.ndarray:
+    gp = patch.params if isinstance(patch, Grid) else patch
+    lib = lib or (patch.lib if isinstance(patch, Grid) else _lib.load())
+    cp, keep = _c_grid_params(gp)
+    out = np.zeros((5, num_tiles), order="F")
+    lib.check(lib.sb_calc_tile_sizes(C.byref(cp), num_tiles, _ptr(out)))
+    return out
+
+
+def tile_grid_params(gp: GridParameters, tile_params: np.ndarray, t: int) -> GridParameters:
+    """GridParameters of tile t (0-based), as at src/semiimplicit.jl:155-169."""
+    names = gp.var_names()
+    return replace(gp, xmin=float(tile_params[0, t]), xmax=float(tile_params[1, t]), num_cells=int(tile_params[2, t]),
+                   BCL={k: dict(CubicBSpline.R0) for k in names}, BCR={k: dict(CubicBSpline.R0) for k in names},
+                   spectralIndexL=int(tile_params[3, t]), tile_num=t + 2)
+
+
+def checkCFL(grid: Grid):
+    var = C.c_int32(-1)
+    idx = C.c_int64(-1)
+    rc = grid.lib.sb_check_cfl(grid.handle, C.byref(var), C.byref(idx))
+    if rc == _lib.SB_ENAN:
+        names = grid.params.var_names()
+        raise ScytheError(rc, f"NaN found in variable {names[var.value]} at index{idx.value + 1} ! "
+                              "CFL condition likely violated")
+    grid.lib.check(rc)
+
+
+# ---------------------------------------------------------------------------------- model
+@dataclass
+class ModelParameters:
+    """src/Scythe.jl:8-21."""
+    ts: float = 0.0
+    integration_time: float = 1.0
+    output_interval: float = 1.0
+    equation_set: str = "LinearAdvection1D"
+    initial_conditions: str = "ic.csv"
+    output_dir: str = "./output/"
+    ref_state_file: str = ""
+    grid_params: GridParameters = None
+    physical_params: dict = field(default_factory=dict)
+    options: dict = field(default_factory=lambda: {"semiimplicit": False, "exact_reference_state": False})
+
+
+@dataclass
+class ReferenceState:
+    """src/reference_state.jl:4-10; arrays are [zDim, 3] (value, d/dz, d2/dz2)."""
+    sbar: np.ndarray
+    xibar: np.ndarray
+    mubar: np.ndarray
+    mu_lbar: np.ndarray | None = None
+    Pxi_bar: float = 0.0
+
+
+class Model:
+    """initialize_model + run_model for the tiles this process owns (one tile per reference worker).
+
+    ``num_tiles`` is the total tile count (the reference's number of workers); this process owns
+    ``tile_count`` consecutive tiles starting at ``tile_first`` (all of them by default = several
+    tiles emulated on one device).  With ``torch.distributed`` initialised and ``distributed=True``
+    each rank owns ``num_tiles / world_size`` tiles and the shared spectral sum is an all-reduce.
+    """
+
+    def __init__(self, model: ModelParameters, num_tiles: int = 1, tile_first: int = 0, tile_count: int | None = None,
+                 device: int = 0, ref_state: ReferenceState | None = None, lib=None, distributed: bool = False,
+                 exchange: str | None = None):
+        self.lib = lib or _lib.load()
+        self.model = model
+        self.num_tiles = num_tiles
+        self.dist = None
+        self.rank, self.world = 0, 1
+        if distributed:
+            import torch.distributed as dist
+            self.dist = dist
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+            if num_tiles % self.world:
+                raise ValueError("num_tiles must be a multiple of the world size")
+            per = num_tiles // self.world
+            tile_first, tile_count = self.rank * per, per
+        tile_count = num_tiles - tile_first if tile_count is None else tile_count
+        self.tile_first, self.tile_count = tile_first, tile_count
+        gp = model.grid_params
+        cgp, keep = _c_grid_params(gp)
+        names = gp.var_names()
+        cnames = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        pk = list(model.physical_params.keys())
+        pnames = (C.c_char_p * max(len(pk), 1))(*[str(k).lstrip(":").encode() for k in pk])
+        pvals = (C.c_double * max(len(pk), 1))(*[float(model.physical_params[k]) for k in pk])
+        semi = bool(model.options.get("semiimplicit", model.options.get(":semiimplicit", False)))
+        mp = _lib.sb_model_params(ts=model.ts, integration_time=model.integration_time,
+                                  output_interval=model.output_interval, equation_set=model.equation_set.encode(),
+                                  grid=C.pointer(cgp), var_names=cnames, n_physical_params=len(pk), param_names=pnames,
+                                  param_values=pvals, semiimplicit=int(semi))
+        if ref_state is not None:
+            self._ref = [np.asfortranarray(np.asarray(a, dtype=np.float64)) for a in
+                         (ref_state.sbar, ref_state.xibar, ref_state.mubar)]
+            mp.ref_sbar, mp.ref_xibar, mp.ref_mubar = (_ptr(a) for a in self._ref)
+            mp.Pxi_bar = float(ref_state.Pxi_bar)
+        h = _lib.model_t()
+        self.lib.check(self.lib.sb_model_create(C.byref(mp), num_tiles, tile_first, tile_count, device, None, C.byref(h)))
+        self.handle = h
+        ph = _lib.grid_t()
+        self.lib.check(self.lib.sb_model_patch(h, C.byref(ph)))
+        self.patch = Grid(gp, lib=self.lib, handle=ph)
+        self.patch.resident = True
+        self.tile_params = calcTileSizes(gp, num_tiles, lib=self.lib)
+        self.tiles = []
+        for i in range(tile_count):
+            th = _lib.grid_t()
+            self.lib.check(self.lib.sb_model_tile(h, i, C.byref(th)))
+            g = Grid(tile_grid_params(gp, self.tile_params, tile_first + i), lib=self.lib, handle=th)
+            g.resident = True
+            self.tiles.append(g)
+        self.t = 0
+        self.exchange = exchange or os.environ.get("SB_EXCHANGE", "torch")
+        self._shared_tensor = None
+        if self.dist is not None and self.world > 1 and self.exchange == "native":
+            self._init_native_comm()
+
+    # -- multi-process plumbing -------------------------------------------------------
+    def _init_native_comm(self):
+        import torch
+        uid = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            self.lib.check(self.lib.sb_comm_unique_id(uid))
+        t = torch.tensor(list(uid), dtype=torch.uint8)
+        backend = self.dist.get_backend()
+        if backend == "nccl":
+            t = t.cuda()
+        self.dist.broadcast(t, 0)
+        uid = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self.lib.check(self.lib.sb_model_comm_init(self.handle, uid, self.rank, self.world))
+
+    def _shared_as_tensor(self):
+        """torch view of the device-resident shared B buffer (zero copy)."""
+        if self._shared_tensor is None:
+            import torch
+            ptr, n = C.c_void_p(), C.c_int64()
+            self.lib.check(self.lib.sb_grid_device_ptr(self.patch.handle, 1, C.byref(ptr), C.byref(n)))
+            if self.dist.get_backend() == "nccl":
+                class _Wrap:
+                    __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f8", "data": (ptr.value, False),
+                                                "version": 2}
+                self._shared_tensor = torch.as_tensor(_Wrap(), device=f"cuda:{torch.cuda.current_device()}")
+            else:  # CPU emulation build under gloo: the "device" buffer is host memory
+                buf = (C.c_double * n.value).from_address(ptr.value)
+                self._shared_tensor = torch.from_numpy(np.ctypeslib.as_array(buf))
+        return self._shared_tensor
+
+    # -- reference driver ---------------------------------------------------------------
+    def initialize(self, ic: np.ndarray):
+        """initialize_model: ic is patch.physical[:, :, 0] as [N_patch, V]."""
+        ic = np.asfortranarray(np.asarray(ic, dtype=np.float64).reshape(self.patch.N, self.patch.V, order="F"))
+        self.lib.check(self.lib.sb_model_initialize(self.handle, _ptr(ic)))
+        self.t = 0
+
+    def step(self):
+        self.t += 1
+        if self.dist is None or self.world == 1:
+            self.lib.check(self.lib.sb_model_step(self.handle, self.t))
+            return
+        self.lib.check(self.lib.sb_model_advance_tiles(self.handle, self.t))
+        if self.exchange == "native":
+            self.lib.check(self.lib.sb_model_exchange(self.handle))
+        else:
+            self.dist.all_reduce(self._shared_as_tensor())
+        self.lib.check(self.lib.sb_model_spline_transform(self.handle))
+
+    def run(self, nsteps: int):
+        if self.dist is None or self.world == 1:
+            self.lib.check(self.lib.sb_model_run(self.handle, self.t + 1, nsteps))
+            self.t += nsteps
+        else:
+            for _ in range(nsteps):
+                self.step()
+
+    def output(self, to_host: bool = True) -> np.ndarray | None:
+        """patch.spectral <- A; tileTransform!(patch); checkCFL  (src/semiimplicit.jl:289-291)."""
+        if to_host:
+            out = np.empty((self.patch.N, self.patch.V, self.patch.D), order="F")
+            rc = self.lib.sb_model_output(self.handle, _ptr(out))
+        else:
+            out, rc = None, self.lib.sb_model_output(self.handle, None)
+        if rc == _lib.SB_ENAN:
+            raise ScytheError(rc, (self.lib.sb_last_error() or b"").decode())
+        self.lib.check(rc)
+        return out
+
+    def state(self, tile: int, which: str) -> np.ndarray:
+        idx = {"var_np1": 0, "expdot_n": 1, "expdot_nm1": 2, "expdot_nm2": 3,
+               "impdot_n": 4, "impdot_nm1": 5, "impdot_nm2": 6}[which]
+        g = self.tiles[tile]
+        out = np.empty((g.N, g.V), order="F")
+        self.lib.check(self.lib.sb_model_get_state(self.handle, tile, idx, _ptr(out)))
+        return out
+
+    def sync(self):
+        self.lib.check(self.lib.sb_model_sync(self.handle))
+
+    def launch_count(self) -> int:
+        return int(self.lib.sb_model_launch_count(self.handle))
+
+    def close(self):
+        if self.handle is not None:
+            for g in self.tiles + [self.patch]:
+                g.handle = None
+            self.lib.sb_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------- CSV + driver
+def read_physical_grid(path: str, grid: Grid):
+    """Fill grid.physical[:, v, 0] from a CSV with coordinate columns then one column per variable."""
+    with open(path) as f:
+        header = f.readline().strip().split(",")
+    data = np.loadtxt(path, delimiter=",", skiprows=1, ndmin=2)
+    for name, v in grid.params.vars.items():
+        grid.physical[:, v - 1, 0] = data[:, header.index(name)]
+
+
+def write_grid(grid: Grid, output_dir: str, tag: str, physical: np.ndarray | None = None):
+    physical = grid.physical if physical is None else physical
+    pts = getGridpoints(grid)
+    pts = pts.reshape(grid.N, -1)
+    coord = ["r", "l", "z"] if grid.params.geometry == "RLZ" else (["r", "z"] if grid.params.geometry == "RZ" else ["r", "l"])
+    names = grid.params.var_names()
+    cols = [pts[:, i] for i in range(pts.shape[1])] + [physical[:, i, 0] for i in range(len(names))]
+    os.makedirs(output_dir, exist_ok=True)
+    np.savetxt(os.path.join(output_dir, f"physical_out_{tag}.csv"), np.stack(cols, axis=1), delimiter=",",
+               header=",".join(coord[:pts.shape[1]] + names), comments="", fmt="%.17g")
+
+
+def integrate_model(model: ModelParameters, num_tiles: int = 1, ic: np.ndarray | None = None,
+                    ref_state: ReferenceState | None = None, write: bool = False, device: int = 0, lib=None):
+    """src/Scythe.jl:37-62 + model_loop (src/semiimplicit.jl:258-299).  Returns the final patch.physical."""
+    if num_tiles < 1:
+        raise ScytheError(_lib.SB_EINVAL, "Need to add at least 1 worker process")
+    m = Model(model, num_tiles=num_tiles, device=device, ref_state=ref_state, lib=lib)
+    if ic is None:
+        read_physical_grid(model.initial_conditions, m.patch)
+        ic = m.patch.physical[:, :, 0]
+    m.initialize(ic)
+    num_ts = int(round(model.integration_time / model.ts))
+    output_int = max(int(round(model.output_interval / model.ts)), 1)
+    if write:
+        write_grid(m.patch, model.output_dir, "0.0", m.output())
+    t = 0
+    while t < num_ts:
+        n = min(output_int - (t % output_int), num_ts - t)
+        m.run(n)
+        t += n
+        if t % output_int == 0:
+            out = m.output(to_host=write)
+            if write:
+                write_grid(m.patch, model.output_dir, str(round(t * model.ts, 2)), out)
+    out = m.output()
+    if write:
+        write_grid(m.patch, model.output_dir, str(round(model.integration_time, 2)), out)
+    m.close()
+    return out

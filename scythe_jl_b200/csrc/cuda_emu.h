@@ -1,0 +1,143 @@
+// cuda_emu.h -- TEST-ONLY host emulation of the small CUDA subset the kernels use.
+//
+// There is no GPU in the build container, so the CPU test-suite compiles the *same*
+// kernel sources with g++ (-DSB_EMU) against this shim to check indexing and maths
+// against the oracle before spending GPU time.  The emulated library is built as
+// tests/_emu/libscythe_b200_emu.so and is loaded ONLY by tests; the product loader
+// (scythe_jl_b200/_lib.py) never looks for it and fails loudly without the sm_100a build.
+//
+// Model: one OS thread per CUDA thread of a block, blocks executed one after another,
+// __syncthreads() = std::barrier, __shared__ = function-level static (safe because only
+// one block is live at a time), warp shuffles through a per-warp exchange buffer.
+#pragma once
+#ifdef SB_EMU
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+#define __constant__ static
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct uint3 { unsigned x, y, z; };
+struct double2 { double x, y; };
+struct alignas(16) double4 { double x, y, z, w; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+
+namespace sbemu {
+extern thread_local uint3 t_threadIdx, t_blockIdx;
+extern thread_local dim3 t_blockDim, t_gridDim;
+extern thread_local int t_lin;            // linear thread id in block
+extern std::barrier<>* g_block_barrier;
+extern std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
+extern double g_warp_buf[64][32];
+extern unsigned char* g_dyn_smem;
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+}  // namespace sbemu
+
+#define threadIdx (sbemu::t_threadIdx)
+#define blockIdx (sbemu::t_blockIdx)
+#define blockDim (sbemu::t_blockDim)
+#define gridDim (sbemu::t_gridDim)
+
+static inline void __syncthreads() { sbemu::g_block_barrier->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { sbemu::g_warp_barriers[sbemu::t_lin / 32]->arrive_and_wait(); }
+static inline double __shfl_sync(unsigned, double v, int src, int = 32) {
+  int w = sbemu::t_lin / 32, l = sbemu::t_lin % 32;
+  sbemu::g_warp_buf[w][l] = v;
+  sbemu::g_warp_barriers[w]->arrive_and_wait();
+  double r = sbemu::g_warp_buf[w][src & 31];
+  sbemu::g_warp_barriers[w]->arrive_and_wait();
+  return r;
+}
+static inline double __shfl_xor_sync(unsigned m, double v, int lanemask, int = 32) {
+  return __shfl_sync(m, v, (sbemu::t_lin % 32) ^ lanemask);
+}
+static inline double __shfl_down_sync(unsigned m, double v, unsigned d, int = 32) {
+  int l = sbemu::t_lin % 32;
+  return __shfl_sync(m, v, (l + (int)d < 32) ? l + (int)d : l);
+}
+static inline double __shfl_up_sync(unsigned m, double v, unsigned d, int = 32) {
+  int l = sbemu::t_lin % 32;
+  return __shfl_sync(m, v, (l - (int)d >= 0) ? l - (int)d : l);
+}
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline void sincospi(double x, double* s, double* c) {
+  *s = std::sin(M_PI * x);
+  *c = std::cos(M_PI * x);
+}
+static inline double atomicAdd(double* p, double v) {  // blocks run serially, threads concurrently
+  static std::atomic_flag lock = ATOMIC_FLAG_INIT;
+  while (lock.test_and_set(std::memory_order_acquire)) {}
+  double o = *p;
+  *p = o + v;
+  lock.clear(std::memory_order_release);
+  return o;
+}
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+using std::fma;
+using std::fabs;
+using std::sqrt;
+
+// ---- tiny runtime shim ------------------------------------------------------------
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef struct sbemu_event* cudaEvent_t;
+struct sbemu_event { double t; };
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaPeekAtLastError() { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)1 << 40; return 0; }
+cudaError_t cudaEventCreate(cudaEvent_t* e);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
+cudaError_t cudaEventSynchronize(cudaEvent_t e);
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
+
+#define SB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(sbemu::g_dyn_smem)
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  sbemu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+
+#else  // ---------------------------------------------------------------- real CUDA
+#include <cuda_runtime.h>
+#define SB_DYN_SMEM(type, name)                                   \
+  extern __shared__ __align__(16) unsigned char _sb_dyn_smem[];   \
+  type* name = reinterpret_cast<type*>(_sb_dyn_smem)
+#define SB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif

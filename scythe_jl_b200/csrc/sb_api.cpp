@@ -1,0 +1,1040 @@
+// sb_api.cpp -- Grid / Model host objects and the extern "C" ABI declared in include/scythe_b200.h.
+//
+// All state is device-resident for the whole integration (physical slots, spectral B/A, AB3
+// history); the host only enqueues kernels and (multi-GPU) one NCCL all-reduce per step.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/scythe_b200.h"
+#include "sb_internal.hpp"
+
+using namespace sb;
+
+namespace sb { int sb_rows_per_cta(int L); }
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct DomainErr : std::runtime_error { using std::runtime_error::runtime_error; };
+struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
+struct NanFound : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CU(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return SB_OK;
+  } catch (const DomainErr& e) { return fail(SB_EDOMAIN, e.what());
+  } catch (const Unsupported& e) { return fail(SB_EUNSUPPORTED, e.what());
+  } catch (const NanFound& e) { return fail(SB_ENAN, e.what());
+  } catch (const CudaError& e) { return fail(SB_ECUDA, e.what());
+  } catch (const std::invalid_argument& e) { return fail(SB_EINVAL, e.what());
+  } catch (const std::exception& e) { return fail(SB_ECUDA, e.what()); }
+}
+
+template <class T>
+static T* dev_upload(const std::vector<T>& h) {
+  T* d = nullptr;
+  CU(cudaMalloc((void**)&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) CU(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+static double* dev_zeros(long long n, cudaStream_t s) {
+  double* d = nullptr;
+  CU(cudaMalloc((void**)&d, (size_t)std::max<long long>(n, 1) * sizeof(double)));
+  CU(cudaMemsetAsync(d, 0, (size_t)std::max<long long>(n, 1) * sizeof(double), s));
+  return d;
+}
+
+// ====================================================================================== grid
+struct sb_grid {
+  sb_grid_params gp{};
+  std::vector<int32_t> bcl, bcr, bcb, bct;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevGrid dg{};
+  std::vector<int> ring_n, ring_ri, h2r;
+  std::vector<long long> hoff, woff;
+  std::vector<double> rad;
+  ChebTables cheb;
+  std::vector<SplineFactor> factors;
+  std::vector<DevSplineFactor> hfactors;
+  std::vector<void*> owned;   // device allocations freed at destroy
+  double* physical = nullptr;
+  double* spectralB = nullptr;
+  double* spectralA = nullptr;
+  double* scratch = nullptr;
+  long long scratch_doubles = 0;
+  int vchunk = 1;
+  ZTile* d_ztiles = nullptr;
+  int nztiles = 0;
+  std::vector<FftClass> classes;
+  std::vector<std::vector<LWork>> fwork, iwork;
+  std::vector<const LWork*> d_fwork, d_iwork;
+  std::vector<const double*> d_tw;
+  RingPlan* d_plans = nullptr;
+  double* d_blob = nullptr;
+  double* d_fwdT = nullptr;
+  double* d_invM = nullptr;
+  long long launches = 0;
+  long long* d_nan = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int ndims = 1;
+
+  LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
+  template <class T> T* up(const std::vector<T>& h) { T* d = dev_upload(h); owned.push_back(d); return d; }
+  long long slot_stride() const { return dg.N * dg.V; }
+
+  void ensure_physical() {
+    if (!physical) physical = dev_zeros(dg.N * dg.V * dg.D, stream);
+  }
+  void release_physical() {
+    if (physical) { CU(cudaStreamSynchronize(stream)); cudaFree(physical); physical = nullptr; }
+  }
+  // per-variable scratch need (doubles)
+  long long fwd_need() const {
+    long long sl = (long long)dg.bz * dg.W;
+    long long sz = (dg.has_l && dg.has_z) ? (long long)dg.bz * dg.hpoints : 0;
+    return (dg.has_l || dg.has_z) ? sl + sz : 0;
+  }
+  long long inv_need() const {
+    long long sl = 3LL * dg.bz * dg.W;
+    long long sz = (dg.has_l && dg.has_z) ? 5LL * dg.bz * dg.hpoints : 0;
+    return (dg.has_l || dg.has_z) ? sl + sz : 0;
+  }
+  void ensure_scratch() {
+    if (scratch) return;
+    long long per_v = std::max(fwd_need(), inv_need());
+    const char* env = std::getenv("SB_VCHUNK");
+    vchunk = dg.V;
+    if (env && std::atoi(env) > 0) vchunk = std::min(dg.V, std::atoi(env));
+    else if (per_v * dg.V * 8 > (4LL << 30)) vchunk = 1;
+    scratch_doubles = std::max<long long>(per_v * vchunk, 1);
+    CU(cudaMalloc((void**)&scratch, (size_t)scratch_doubles * sizeof(double)));
+  }
+};
+
+static void build_grid(sb_grid* G) {
+  const sb_grid_params& gp = G->gp;
+  DevGrid& d = G->dg;
+  if (gp.geometry < SB_GEOM_R || gp.geometry > SB_GEOM_RLZ) throw DomainErr("Unknown geometry");
+  if (gp.num_cells < 1 || !(gp.xmax > gp.xmin)) throw std::invalid_argument("num_cells >= 1 and xmax > xmin required");
+  if (gp.nvars < 1) throw std::invalid_argument("nvars >= 1 required");
+  d.has_l = (gp.geometry == SB_GEOM_RL || gp.geometry == SB_GEOM_RLZ);
+  d.has_z = (gp.geometry == SB_GEOM_RZ || gp.geometry == SB_GEOM_RLZ);
+  d.V = gp.nvars;
+  d.D = 3 + (d.has_l ? 2 : 0) + (d.has_z ? 2 : 0);
+  d.num_cells = (int)gp.num_cells;
+  d.rDim = 3 * d.num_cells;
+  d.b_rDim = d.num_cells + 3;
+  if (d.has_z) {
+    if (gp.zDim < 4 || !(gp.zmax > gp.zmin)) throw std::invalid_argument("zDim >= 4 and zmax > zmin required");
+    d.zDim = (int)gp.zDim;
+    long long def = std::min<long long>(gp.zDim, (2 * gp.zDim - 1) / 3 + 1);
+    d.bz = (int)(gp.b_zDim > 0 ? gp.b_zDim : def);
+    if (d.bz > d.zDim) throw std::invalid_argument("b_zDim > zDim");
+  } else {
+    d.zDim = 1;
+    d.bz = 1;
+  }
+  d.bzp = (d.bz + 3) & ~3;
+  const long long sIL = gp.spectralIndexL > 0 ? gp.spectralIndexL : 1;
+  d.coefOffset = (int)(sIL - 1);
+  d.patchOffsetL = d.coefOffset * 3;
+  d.kDim = d.has_l ? d.rDim + d.patchOffsetL : 0;
+  d.ncolp = 1 + 2 * d.kDim;
+  const double DX = (gp.xmax - gp.xmin) / gp.num_cells;
+  spline_weights(DX, d.phi, d.wq);
+  spline_mish_points(gp.xmin, DX, d.num_cells, G->rad);
+  G->ring_n.resize(d.rDim);
+  G->ring_ri.resize(d.rDim);
+  G->hoff.assign(d.rDim + 1, 0);
+  G->woff.assign(d.rDim + 1, 0);
+  for (int r = 0; r < d.rDim; ++r) {
+    int ri = r + 1 + d.patchOffsetL;
+    G->ring_ri[r] = ri;
+    G->ring_n[r] = d.has_l ? 4 + 4 * ri : 1;
+    G->hoff[r + 1] = G->hoff[r] + G->ring_n[r];
+    G->woff[r + 1] = G->woff[r] + (d.has_l ? 1 + 2 * ri : 1);
+  }
+  d.hpoints = G->hoff[d.rDim];
+  d.W = G->woff[d.rDim];
+  d.N = d.hpoints * d.zDim;
+  d.S = (long long)d.bz * d.b_rDim * d.ncolp;
+  G->ndims = 1 + (d.has_l ? 1 : 0) + (d.has_z ? 1 : 0);
+  G->h2r.resize((size_t)d.hpoints);
+  for (int r = 0; r < d.rDim; ++r)
+    for (long long h = G->hoff[r]; h < G->hoff[r + 1]; ++h) G->h2r[(size_t)h] = r;
+
+  CU(cudaSetDevice(G->device));
+  d.ring_n = G->up(G->ring_n);
+  d.ring_ri = G->up(G->ring_ri);
+  d.ring_hoff = G->up(G->hoff);
+  d.ring_woff = G->up(G->woff);
+  d.rad = G->up(G->rad);
+  d.h2r = G->up(G->h2r);
+
+  // splines: one factor per (BCL,BCR) pair
+  std::map<std::pair<int, int>, int> cache;
+  G->factors.clear();
+  std::vector<int> fidx(d.V);
+  for (int v = 0; v < d.V; ++v) {
+    auto key = std::make_pair((int)G->bcl[v], (int)G->bcr[v]);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      if (key.first < 0 || key.first > 7 || key.second < 0 || key.second > 7) throw std::invalid_argument("bad spline BC code");
+      if ((key.first == SB_BC_PERIODIC) != (key.second == SB_BC_PERIODIC)) throw std::invalid_argument("PERIODIC must be set on both ends");
+      if (key.first == SB_BC_PERIODIC && d.b_rDim > 4096) throw Unsupported("PERIODIC splines are limited to 4093 cells");
+      G->factors.push_back(make_spline_factor(d.num_cells, DX, gp.l_q > 0 ? gp.l_q : 2.0, key.first, key.second));
+      it = cache.emplace(key, (int)G->factors.size() - 1).first;
+    }
+    fidx[v] = it->second;
+  }
+  std::vector<DevSplineFactor> df(G->factors.size());
+  for (size_t i = 0; i < G->factors.size(); ++i) {
+    const SplineFactor& f = G->factors[i];
+    DevSplineFactor& o = df[i];
+    o.M = f.M; o.rL = f.rL; o.rR = f.rR; o.nfree = f.nfree; o.periodic = f.periodic ? 1 : 0;
+    o.foldL[0] = f.foldL[0]; o.foldL[1] = f.foldL[1]; o.foldR[0] = f.foldR[0]; o.foldR[1] = f.foldR[1];
+    o.chol = f.chol.empty() ? nullptr : G->up(f.chol);
+    o.dense = f.dense.empty() ? nullptr : G->up(f.dense);
+  }
+  G->hfactors.resize(d.V);
+  for (int v = 0; v < d.V; ++v) G->hfactors[v] = df[fidx[v]];
+
+  // Chebyshev tables
+  if (d.has_z) {
+    G->cheb = make_cheb_tables(d.zDim, d.bz, gp.zmin, gp.zmax);
+    d.zlev = G->up(G->cheb.z);
+    std::vector<double> fwdT((size_t)d.zDim * d.bzp, 0.0);
+    for (int zb = 0; zb < d.bz; ++zb)
+      for (int z = 0; z < d.zDim; ++z) fwdT[(size_t)z * d.bzp + zb] = G->cheb.fwd[(size_t)zb * d.zDim + z];
+    G->d_fwdT = G->up(fwdT);
+    const int zp = (d.zDim + 3) & ~3, nz = d.zDim, bz = d.bz;
+    std::vector<double> invM((size_t)d.V * 3 * bz * zp, 0.0);
+    for (int v = 0; v < d.V; ++v) {
+      int b = G->bcb.empty() ? 0 : G->bcb[v], t = G->bct.empty() ? 0 : G->bct[v];
+      if (b < 0 || b > 3 || t < 0 || t > 3) throw std::invalid_argument("bad Chebyshev BC code");
+      std::vector<double> IG = cheb_bc_matrix(G->cheb, b, t);
+      const std::vector<double>* T[3] = {&G->cheb.T0, &G->cheb.T1, &G->cheb.T2};
+      for (int k = 0; k < 3; ++k)
+        for (int z = 0; z < nz; ++z)
+          for (int zb = 0; zb < bz; ++zb) {
+            long double s = 0;
+            for (int q = 0; q < bz; ++q) s += (long double)(*T[k])[(size_t)z * nz + q] * IG[(size_t)q * bz + zb];
+            invM[(((size_t)v * 3 + k) * bz + zb) * zp + z] = (double)s;
+          }
+    }
+    G->d_invM = G->up(invM);
+    // z tiles
+    std::vector<ZTile> zt;
+    if (d.has_l) {
+      for (int r = 0; r < d.rDim; ++r)
+        for (int j0 = 0; j0 < G->ring_n[r]; j0 += 32) {
+          ZTile t{};
+          t.hcol0 = (int)(G->hoff[r] + j0);
+          t.ncols = std::min(32, G->ring_n[r] - j0);
+          t.out_base = (long long)d.bz * G->hoff[r] + j0;
+          t.out_stride = G->ring_n[r];
+          zt.push_back(t);
+        }
+    } else {
+      for (int j0 = 0; j0 < d.rDim; j0 += 32) {
+        ZTile t{};
+        t.hcol0 = j0;
+        t.ncols = std::min(32, d.rDim - j0);
+        t.out_base = j0;
+        t.out_stride = d.rDim;
+        zt.push_back(t);
+      }
+    }
+    if ((long long)d.hpoints > 0x7fffffffLL) throw Unsupported("more than 2^31 horizontal points per tile");
+    G->nztiles = (int)zt.size();
+    G->d_ztiles = G->up(zt);
+  }
+  // ring FFT plans
+  if (d.has_l) {
+    std::vector<RingPlan> plans;
+    std::vector<double> blob;
+    build_ring_plans(G->ring_ri, G->classes, plans, blob);
+    G->d_plans = G->up(plans);
+    G->d_blob = G->up(blob);
+    G->fwork.assign(G->classes.size(), {});
+    G->iwork.assign(G->classes.size(), {});
+    for (int r = d.rDim - 1; r >= 0; --r) {
+      int nr = sb_rows_per_cta(plans[r].L);
+      for (int row0 = 0; row0 < d.bz; row0 += nr) G->fwork[plans[r].cls].push_back(LWork{r, row0, std::min(nr, d.bz - row0), 0});
+      for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork[plans[r].cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
+    }
+    for (size_t c = 0; c < G->classes.size(); ++c) {
+      G->d_fwork.push_back(G->up(G->fwork[c]));
+      G->d_iwork.push_back(G->up(G->iwork[c]));
+      G->d_tw.push_back(G->up(G->classes[c].tw));
+    }
+  }
+  G->spectralB = dev_zeros(d.S * d.V, G->stream);
+  G->spectralA = dev_zeros(d.S * d.V, G->stream);
+  CU(cudaMalloc((void**)&G->d_nan, sizeof(long long)));
+  CU(cudaEventCreate(&G->ev0));
+  CU(cudaEventCreate(&G->ev1));
+}
+
+// forward transform of `in` ([V][N] var-major) into G->spectralB (K1)
+static void grid_forward(sb_grid* G, const double* in, double* mirror) {
+  DevGrid& d = G->dg;
+  LaunchCtx c = G->ctx();
+  if (!d.has_l && !d.has_z) {
+    if (mirror && mirror != in) launch_copy(c, mirror, in, d.N * d.V);
+    launch_fwd_r(c, d, d.V, in, d.N, G->spectralB, d.S);
+    return;
+  }
+  G->ensure_scratch();
+  const long long slN = (long long)d.bz * d.W, szN = (long long)d.bz * d.hpoints;
+  for (int v0 = 0; v0 < d.V; v0 += G->vchunk) {
+    const int nv = std::min(G->vchunk, d.V - v0);
+    double* SL = G->scratch;
+    double* SZ = G->scratch + slN * G->vchunk;
+    const double* inv = in + (long long)v0 * d.N;
+    double* mir = mirror ? mirror + (long long)v0 * d.N : nullptr;
+    if (d.has_l && d.has_z) {
+      launch_fwd_z(c, d, G->d_ztiles, G->nztiles, nv, inv, d.N, mir, d.N, SZ, szN, G->d_fwdT);
+      launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_plans, G->d_blob, nv, SZ, szN,
+                   1, nullptr, 0, SL, slN);
+    } else if (d.has_l) {
+      launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_plans, G->d_blob, nv, inv, d.N,
+                   0, mir, d.N, SL, slN);
+    } else {
+      launch_fwd_z(c, d, G->d_ztiles, G->nztiles, nv, inv, d.N, mir, d.N, SL, slN, G->d_fwdT);
+    }
+    launch_fwd_r(c, d, nv, SL, slN, G->spectralB + (long long)v0 * d.S, d.S);
+  }
+}
+
+// inverse transform: patch A -> tile physical (K3)
+static void grid_inverse(sb_grid* P, sb_grid* T) {
+  DevGrid& t = T->dg;
+  DevGrid& p = P->dg;
+  if (t.has_l != p.has_l || t.has_z != p.has_z || t.V != p.V || t.bz != p.bz || t.zDim != p.zDim)
+    throw std::invalid_argument("tile and patch are incompatible");
+  if (t.coefOffset < p.coefOffset || t.coefOffset + t.b_rDim > p.coefOffset + p.b_rDim)
+    throw std::invalid_argument("tile is not inside the patch");
+  T->ensure_physical();
+  LaunchCtx c = T->ctx();
+  if (!t.has_l && !t.has_z) {
+    launch_inv_r(c, t, p, t.V, P->spectralA, p.S, T->physical, 0, 0, 1, 0);
+    return;
+  }
+  T->ensure_scratch();
+  const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
+  for (int v0 = 0; v0 < t.V; v0 += T->vchunk) {
+    const int nv = std::min(T->vchunk, t.V - v0);
+    double* SL = T->scratch;                          // [3][vchunk][slN]
+    double* SZ = T->scratch + 3 * slN * T->vchunk;    // [5][vchunk][szN]
+    const long long sl_fs = slN * T->vchunk, sz_fs = szN * T->vchunk;
+    launch_inv_r(c, t, p, nv, P->spectralA + (long long)v0 * p.S, p.S, SL, sl_fs, slN, 0, v0);
+    if (t.has_l && t.has_z) {
+      launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
+                   slN, SZ, sz_fs, szN, 0, v0);
+      launch_inv_z(c, t, T->d_ztiles, T->nztiles, nv, v0, 5, SZ, sz_fs, szN, T->physical, T->d_invM);
+    } else if (t.has_l) {
+      launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
+                   slN, T->physical, 0, 0, 1, v0);
+    } else {
+      launch_inv_z(c, t, T->d_ztiles, T->nztiles, nv, v0, 3, SL, sl_fs, slN, T->physical, T->d_invM);
+    }
+  }
+}
+
+static void grid_spline(sb_grid* P, const double* B) {
+  launch_spline_solve(P->ctx(), P->dg, nullptr, P->hfactors, B, P->spectralA);
+}
+
+static void fill_gridpoints(sb_grid* G, double* out) {
+  const DevGrid& d = G->dg;
+  const long long N = d.N;
+  const double twopi = 6.283185307179586476925286766559;
+  for (int r = 0; r < d.rDim; ++r) {
+    const int n = G->ring_n[r], ri = G->ring_ri[r];
+    const double dl = twopi / n, ymin = 0.5 * dl * (ri - 1);
+    for (int j = 0; j < n; ++j) {
+      const long long h = G->hoff[r] + j;
+      for (int z = 0; z < d.zDim; ++z) {
+        const long long i = h * d.zDim + z;
+        int col = 0;
+        out[i + N * col++] = G->rad[r];
+        if (d.has_l) out[i + N * col++] = ymin + dl * j;
+        if (d.has_z) out[i + N * col++] = G->cheb.z[z];
+      }
+    }
+  }
+}
+
+static void copy_params(sb_grid* G, const sb_grid_params* gp) {
+  G->gp = *gp;
+  auto cp = [&](const int32_t* src, std::vector<int32_t>& dst) {
+    dst.assign(gp->nvars, 0);
+    if (src) std::copy(src, src + gp->nvars, dst.begin());
+  };
+  cp(gp->BCL, G->bcl); cp(gp->BCR, G->bcr); cp(gp->BCB, G->bcb); cp(gp->BCT, G->bct);
+  G->gp.BCL = G->bcl.data(); G->gp.BCR = G->bcr.data(); G->gp.BCB = G->bcb.data(); G->gp.BCT = G->bct.data();
+}
+
+static void require_device() {
+#ifndef SB_EMU
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw CudaError("no CUDA device: libscythe_b200 has no CPU fallback (" + std::string(cudaGetErrorString(e)) + ")");
+#endif
+}
+
+static sb_grid* grid_new(const sb_grid_params* gp, int device, void* stream) {
+  if (!gp) throw std::invalid_argument("grid params is NULL");
+  if (gp->nvars < 1) throw std::invalid_argument("nvars >= 1 required");
+  require_device();
+  std::unique_ptr<sb_grid> G(new sb_grid());
+  copy_params(G.get(), gp);
+  G->device = device;
+  G->stream = (cudaStream_t)stream;
+  build_grid(G.get());
+  return G.release();
+}
+
+static void grid_free(sb_grid* G) {
+  if (!G) return;
+  cudaSetDevice(G->device);
+  cudaStreamSynchronize(G->stream);
+  for (void* p : G->owned) cudaFree(p);
+  cudaFree(G->physical); cudaFree(G->spectralB); cudaFree(G->spectralA); cudaFree(G->scratch); cudaFree(G->d_nan);
+  if (G->ev0) cudaEventDestroy(G->ev0);
+  if (G->ev1) cudaEventDestroy(G->ev1);
+  delete G;
+}
+
+// calcTileSizes: equal-gridpoint cuts on cell boundaries, >= 3 cells per tile
+static void calc_tile_sizes(const sb_grid_params* gp, int ntiles, double* out) {
+  if (!gp || !out) throw std::invalid_argument("NULL argument");
+  const long long nc = gp->num_cells;
+  if (ntiles < 1 || nc < 3LL * ntiles) throw DomainErr("Too many tiles for this grid (need at least 3 cells per tile)");
+  const bool has_l = (gp->geometry == SB_GEOM_RL || gp->geometry == SB_GEOM_RLZ);
+  const bool has_z = (gp->geometry == SB_GEOM_RZ || gp->geometry == SB_GEOM_RLZ);
+  const long long zDim = has_z ? gp->zDim : 1;
+  const long long sIL = gp->spectralIndexL > 0 ? gp->spectralIndexL : 1;
+  const long long off = (sIL - 1) * 3;
+  std::vector<long long> cum(nc + 1, 0);
+  for (long long c = 0; c < nc; ++c) {
+    long long pts = 0;
+    for (int mu = 0; mu < 3; ++mu) {
+      long long ri = 3 * c + mu + 1 + off;
+      pts += has_l ? 4 + 4 * ri : 1;
+    }
+    cum[c + 1] = cum[c] + pts * zDim;
+  }
+  const double total = (double)cum[nc];
+  const double DX = (gp->xmax - gp->xmin) / nc;
+  long long start = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int remaining = ntiles - t - 1;
+    long long end;
+    if (remaining == 0) {
+      end = nc;
+    } else {
+      const double target = total * (t + 1) / ntiles;
+      end = std::lower_bound(cum.begin(), cum.end(), target, [](long long a, double b) { return (double)a < b; }) - cum.begin();
+      if (end > 0 && std::fabs((double)cum[end - 1] - target) <= std::fabs((double)cum[std::min(end, nc)] - target)) end -= 1;
+      end = std::max(end, start + 3);
+      end = std::min(end, nc - 3LL * remaining);
+    }
+    out[5 * t + 0] = gp->xmin + start * DX;
+    out[5 * t + 1] = gp->xmin + end * DX;
+    out[5 * t + 2] = (double)(end - start);
+    out[5 * t + 3] = (double)(sIL + start);
+    out[5 * t + 4] = (double)(cum[end] - cum[start]);
+    start = end;
+  }
+}
+
+static void check_cfl(sb_grid* G, int32_t* var, int64_t* index) {
+  if (!G->physical) throw std::invalid_argument("grid has no physical array");
+  long long init = 0x7fffffffffffffffLL;
+  CU(cudaMemcpyAsync(G->d_nan, &init, sizeof(init), cudaMemcpyHostToDevice, G->stream));
+  launch_nan_scan(G->ctx(), G->physical, G->dg.N, G->dg.V, G->d_nan);
+  long long res = 0;
+  CU(cudaMemcpyAsync(&res, G->d_nan, sizeof(res), cudaMemcpyDeviceToHost, G->stream));
+  CU(cudaStreamSynchronize(G->stream));
+  if (res != init) {
+    int v = (int)(res / G->dg.N);
+    long long i = res - (long long)v * G->dg.N;
+    if (var) *var = v;
+    if (index) *index = i;
+    throw NanFound("NaN found in variable " + std::to_string(v) + " at index" + std::to_string(i + 1) +
+                   " ! CFL condition likely violated");
+  }
+}
+
+// ====================================================================================== NCCL (dlopen)
+struct Uid { char internal[128]; };  // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, void*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+static void nccl_load() {
+  if (g_nccl.lib) return;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) throw std::runtime_error(std::string("cannot load NCCL: ") + dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Uid, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, void*))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) throw std::runtime_error("NCCL symbols missing");
+}
+struct CommError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define NC(call)                                                                         \
+  do {                                                                                   \
+    int r_ = (call);                                                                     \
+    if (r_ != 0) throw CommError(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
+  } while (0)
+
+// ====================================================================================== model
+struct TileState {
+  sb_grid* grid = nullptr;
+  double* var_np1 = nullptr;
+  double* expd[3] = {nullptr, nullptr, nullptr};  // n, nm1, nm2 (rotating)
+  double* impd[3] = {nullptr, nullptr, nullptr};
+};
+
+struct sb_model {
+  sb_grid_params gp{};
+  std::vector<int32_t> bcl, bcr, bcb, bct;
+  std::vector<std::string> var_names;
+  std::map<std::string, double> params;
+  double ts = 0, integration_time = 0, output_interval = 0;
+  int eq = -1;
+  int semiimplicit = 0;
+  EqParams ep{};
+  int ntiles = 1, tile_first = 0, tile_count = 1;
+  std::vector<double> tile_params;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  sb_grid* patch = nullptr;
+  std::vector<TileState> tiles;
+  std::vector<void*> owned;
+  double* d_colops = nullptr;
+  double* d_refstate = nullptr;
+  double* d_sicols = nullptr;
+  std::vector<double> ref_host;  // [3][3][zDim]
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+  long long extra_launches = 0;
+};
+
+static int var_index(const sb_model* M, const char* name) {
+  for (size_t i = 0; i < M->var_names.size(); ++i)
+    if (M->var_names[i] == name) return (int)i;
+  return -1;
+}
+static double param_or(const sb_model* M, const char* k, double dflt) {
+  auto it = M->params.find(k);
+  return it == M->params.end() ? dflt : it->second;
+}
+static double param_req(const sb_model* M, const char* k) {
+  auto it = M->params.find(k);
+  if (it == M->params.end()) throw std::invalid_argument(std::string("physical_params is missing :") + k);
+  return it->second;
+}
+
+static void model_check_equation_set(sb_model* M) {
+  const int geom = M->gp.geometry, V = M->gp.nvars;
+  auto need = [&](int g, int nv, std::initializer_list<const char*> ps) {
+    if (geom != g) throw std::invalid_argument("equation set does not match the grid geometry");
+    if (V < nv) throw std::invalid_argument("equation set needs more variables than the grid has");
+    for (const char* p : ps) param_req(M, p);
+  };
+  switch (M->eq) {
+    case EQ_LinearAdvection1D: need(SB_GEOM_R, 1, {"c_0", "K"}); break;
+    case EQ_LinearAdvectionRZ: need(SB_GEOM_RZ, 4, {"K"}); break;
+    case EQ_LinearAdvectionRL: need(SB_GEOM_RL, 3, {"K"}); break;
+    case EQ_LinearAdvectionRLZ: need(SB_GEOM_RLZ, 3, {"K"}); break;
+    case EQ_LinearShallowWater1D: need(SB_GEOM_R, 2, {"g", "K", "H"}); break;
+    case EQ_LinearShallowWaterRL: need(SB_GEOM_RL, 3, {"g", "K", "H"}); break;
+    case EQ_Oneway_ShallowWater_Slab: need(SB_GEOM_RL, 6, {"g", "K", "Cd", "Hfree", "Hb", "f"}); break;
+    case EQ_Twoway_ShallowWater_Slab: need(SB_GEOM_RL, 6, {"g", "K", "Cd", "Hfree", "Hb", "f", "S1"}); break;
+    case EQ_Oneway_ShallowWater_HeightResolvedBL: need(SB_GEOM_RLZ, 6, {"g", "Kh", "Cd", "Hfree", "f", "Um", "Vm"}); break;
+    case EQ_Euler_test: need(SB_GEOM_RZ, 5, {"K"}); break;
+    default: throw Unsupported("equation set is not built as a CUDA kernel (no CPU fallback)");
+  }
+  EqParams& e = M->ep;
+  e.ts = M->ts;
+  e.c_0 = param_or(M, "c_0", 0); e.K = param_or(M, "K", 0); e.g = param_or(M, "g", 0); e.Cd = param_or(M, "Cd", 0);
+  e.Hfree = param_or(M, "Hfree", 0); e.Hb = param_or(M, "Hb", 1); e.f = param_or(M, "f", 0); e.S1 = param_or(M, "S1", 0);
+  e.H = param_or(M, "H", 0); e.Kh = param_or(M, "Kh", 0); e.Um = param_or(M, "Um", 0); e.Vm = param_or(M, "Vm", 0);
+  e.iw = var_index(M, "w"); e.ixi = var_index(M, "xi"); e.ih = var_index(M, "h");
+  if (M->eq == EQ_Oneway_ShallowWater_HeightResolvedBL && e.ih < 0) throw std::invalid_argument("variable \"h\" not found");
+  if (M->eq == EQ_Euler_test) {
+    if (M->ref_host.empty()) throw std::invalid_argument("Euler_test needs a reference state");
+    if (M->semiimplicit && (e.iw != 4 || e.ixi != 1)) throw std::invalid_argument("Euler_test expects vars s,xi,mu,u,w = 1..5");
+  }
+}
+
+// composite column operators (all stored transposed: Mt[k][z'][z] = M[z][z'])
+static void build_column_ops(sb_model* M) {
+  sb_grid* P = M->patch;
+  const DevGrid& d = P->dg;
+  if (!d.has_z) return;
+  const int nz = d.zDim, bz = d.bz;
+  const ChebTables& ct = P->cheb;
+  auto composite = [&](const std::vector<double>& T, const std::vector<double>& IG, std::vector<double>& out) {
+    // out[z][z'] = sum_{q,zb} T[z][q] IG[q][zb] fwd[zb][z']
+    std::vector<double> TI((size_t)nz * bz);
+    for (int z = 0; z < nz; ++z)
+      for (int zb = 0; zb < bz; ++zb) {
+        long double s = 0;
+        for (int q = 0; q < bz; ++q) s += (long double)T[(size_t)z * nz + q] * IG[(size_t)q * bz + zb];
+        TI[(size_t)z * bz + zb] = (double)s;
+      }
+    out.assign((size_t)nz * nz, 0.0);
+    matmul(TI.data(), ct.fwd.data(), out.data(), nz, bz, nz);
+  };
+  auto transpose_into = [&](const std::vector<double>& A, double* dst) {
+    for (int z = 0; z < nz; ++z)
+      for (int k = 0; k < nz; ++k) dst[(size_t)k * nz + z] = A[(size_t)z * nz + k];
+  };
+  const size_t nn = (size_t)nz * nz;
+  if (M->eq == EQ_Oneway_ShallowWater_HeightResolvedBL) {
+    const int ih = M->ep.ih;
+    std::vector<double> IG = cheb_bc_matrix(ct, P->bcb[ih], P->bct[ih]);
+    std::vector<double> ops(3 * nn), tmp;
+    composite(ct.T0, IG, tmp); transpose_into(tmp, ops.data());
+    composite(ct.T1, IG, tmp); transpose_into(tmp, ops.data() + nn);
+    composite(ct.Tint, IG, tmp); transpose_into(tmp, ops.data() + 2 * nn);
+    M->d_colops = dev_upload(ops); M->owned.push_back(M->d_colops);
+  }
+  if (M->eq == EQ_Euler_test) {
+    M->d_refstate = dev_upload(M->ref_host); M->owned.push_back(M->d_refstate);
+    if (M->semiimplicit) {
+      const int ixi = M->ep.ixi;
+      std::vector<double> IG = cheb_bc_matrix(ct, P->bcb[ixi], P->bct[ixi]);
+      std::vector<double> ops(6 * nn), F, Dz;
+      composite(ct.T0, IG, F); transpose_into(F, ops.data());
+      composite(ct.T1, IG, Dz); transpose_into(Dz, ops.data() + nn);
+      // Helmholtz (src/semiimplicit.jl:768-781): rows 0,1 = tau^2 Pxi dct[0,:], dct[nz-1,:]; rows 2.. = (tau^2 Pxi dct2 - dct)[1..nz-2]
+      for (int k = 0; k < 2; ++k) {
+        const double tau = (k == 0 ? 0.5 : 1.25) * M->ts;
+        const double c = tau * tau * M->ep.Pxi_bar;
+        std::vector<double> H(nn);
+        for (int j = 0; j < nz; ++j) {
+          H[j] = c * ct.T0[j];
+          H[(size_t)nz + j] = c * ct.T0[(size_t)(nz - 1) * nz + j];
+        }
+        for (int i = 2; i < nz; ++i)
+          for (int j = 0; j < nz; ++j) H[(size_t)i * nz + j] = c * ct.T2[(size_t)(i - 1) * nz + j] - ct.T0[(size_t)(i - 1) * nz + j];
+        if (!invert(H, nz)) throw std::runtime_error("Helmholtz matrix is singular");
+        // HS = H^-1 Shift : column j of HS = column j+1 of H^-1 for j = 1..nz-2 (g_new[i] = g_old[i-1], i>=2), else 0
+        std::vector<double> HS(nn, 0.0);
+        for (int i = 0; i < nz; ++i)
+          for (int j = 1; j <= nz - 2; ++j) HS[(size_t)i * nz + j] = H[(size_t)i * nz + j + 1];
+        std::vector<double> W(nn), X(nn);
+        matmul(ct.T0.data(), HS.data(), W.data(), nz, nz, nz);
+        matmul(ct.T1.data(), HS.data(), X.data(), nz, nz, nz);
+        transpose_into(W, ops.data() + (2 + 2 * k) * nn);
+        transpose_into(X, ops.data() + (3 + 2 * k) * nn);
+      }
+      M->d_sicols = dev_upload(ops); M->owned.push_back(M->d_sicols);
+    }
+  }
+}
+
+static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first, int tile_count, int device, void* stream) {
+  if (!mp || !mp->grid || !mp->equation_set) throw std::invalid_argument("NULL model parameter");
+  if (!(mp->ts > 0)) throw std::invalid_argument("ts must be positive");
+  if (ntiles < 1 || tile_first < 0 || tile_count < 1 || tile_first + tile_count > ntiles)
+    throw std::invalid_argument("bad tile range");
+  require_device();
+  std::unique_ptr<sb_model> M(new sb_model());
+  M->gp = *mp->grid;
+  const int V = mp->grid->nvars;
+  auto cp = [&](const int32_t* src, std::vector<int32_t>& dst) { dst.assign(V, 0); if (src) std::copy(src, src + V, dst.begin()); };
+  cp(mp->grid->BCL, M->bcl); cp(mp->grid->BCR, M->bcr); cp(mp->grid->BCB, M->bcb); cp(mp->grid->BCT, M->bct);
+  M->gp.BCL = M->bcl.data(); M->gp.BCR = M->bcr.data(); M->gp.BCB = M->bcb.data(); M->gp.BCT = M->bct.data();
+  for (int v = 0; v < V; ++v) M->var_names.push_back(mp->var_names && mp->var_names[v] ? mp->var_names[v] : ("v" + std::to_string(v)));
+  for (int i = 0; i < mp->n_physical_params; ++i) M->params[mp->param_names[i]] = mp->param_values[i];
+  M->ts = mp->ts; M->integration_time = mp->integration_time; M->output_interval = mp->output_interval;
+  M->semiimplicit = mp->semiimplicit;
+  M->eq = equation_set_from_name(mp->equation_set);
+  if (M->eq < 0) throw Unsupported(std::string("equation set \"") + mp->equation_set + "\" is not built as a CUDA kernel (no CPU fallback)");
+  const bool has_z = (M->gp.geometry == SB_GEOM_RZ || M->gp.geometry == SB_GEOM_RLZ);
+  if (mp->ref_sbar && mp->ref_xibar && mp->ref_mubar && has_z) {
+    const size_t n3 = (size_t)3 * M->gp.zDim;
+    M->ref_host.resize(3 * n3);
+    std::copy(mp->ref_sbar, mp->ref_sbar + n3, M->ref_host.begin());
+    std::copy(mp->ref_xibar, mp->ref_xibar + n3, M->ref_host.begin() + n3);
+    std::copy(mp->ref_mubar, mp->ref_mubar + n3, M->ref_host.begin() + 2 * n3);
+  }
+  M->ep.Pxi_bar = mp->Pxi_bar;
+  model_check_equation_set(M.get());
+  M->ntiles = ntiles; M->tile_first = tile_first; M->tile_count = tile_count;
+  M->device = device; M->stream = (cudaStream_t)stream;
+  M->tile_params.resize((size_t)5 * ntiles);
+  calc_tile_sizes(&M->gp, ntiles, M->tile_params.data());
+  M->patch = grid_new(&M->gp, device, stream);
+  std::vector<int32_t> r0(V, SB_BC_R0);
+  for (int t = tile_first; t < tile_first + tile_count; ++t) {
+    sb_grid_params tp = M->gp;
+    tp.xmin = M->tile_params[5 * t + 0];
+    tp.xmax = M->tile_params[5 * t + 1];
+    tp.num_cells = (int64_t)M->tile_params[5 * t + 2];
+    tp.spectralIndexL = (int64_t)M->tile_params[5 * t + 3];
+    tp.tile_num = t + 2;
+    tp.BCL = r0.data();  // tiles carry no radial BCs (src/semiimplicit.jl:163-164)
+    tp.BCR = r0.data();
+    TileState ts;
+    ts.grid = grid_new(&tp, device, stream);
+    ts.grid->ensure_physical();
+    const long long n = ts.grid->dg.N * V;
+    ts.var_np1 = dev_zeros(n, M->stream);
+    for (int k = 0; k < 3; ++k) ts.expd[k] = dev_zeros(n, M->stream);
+    if (M->semiimplicit)
+      for (int k = 0; k < 3; ++k) ts.impd[k] = dev_zeros(n, M->stream);
+    M->tiles.push_back(ts);
+  }
+  build_column_ops(M.get());
+  return M.release();
+}
+
+static void model_free(sb_model* M) {
+  if (!M) return;
+  if (M->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(M->comm);
+  for (auto& t : M->tiles) {
+    grid_free(t.grid);
+    cudaFree(t.var_np1);
+    for (int k = 0; k < 3; ++k) { cudaFree(t.expd[k]); cudaFree(t.impd[k]); }
+  }
+  grid_free(M->patch);
+  for (void* p : M->owned) cudaFree(p);
+  delete M;
+}
+
+static void model_initialize(sb_model* M, const double* ic_host) {
+  sb_grid* P = M->patch;
+  P->ensure_physical();
+  if (ic_host) CU(cudaMemcpyAsync(P->physical, ic_host, (size_t)P->dg.N * P->dg.V * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+  grid_forward(P, P->physical, nullptr);      // spectralTransform!(patch)   :135
+  grid_spline(P, P->spectralB);               // gridTransform!(patch)       :136  (A-solve ...
+  grid_inverse(P, P);                         //                                   ... + evaluate)
+  CU(cudaStreamSynchronize(P->stream));
+  if ((size_t)P->dg.N * P->dg.V * P->dg.D * sizeof(double) > ((size_t)4 << 30)) P->release_physical();
+}
+
+static void model_advance_tiles(sb_model* M, int64_t t) {
+  sb_grid* P = M->patch;
+  CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
+  sb_grid* prev = nullptr;
+  for (auto& T : M->tiles) {
+    sb_grid* G = T.grid;
+    grid_inverse(P, G);                                     // tileTransform!  :305
+    ModelArrays a{};
+    a.phys = G->physical; a.var_np1 = T.var_np1;
+    a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
+    a.imp_n = T.impd[0]; a.imp_nm1 = T.impd[1]; a.imp_nm2 = T.impd[2];
+    a.colops = M->d_colops; a.refstate = M->d_refstate; a.sicols = M->d_sicols;
+    launch_equation_set(G->ctx(), M->eq, G->dg, M->ep, a, (int)std::min<int64_t>(t, 3));  // :308-314
+    // history rotation (:685-695): nm2 <- nm1 <- n ; the old nm2 buffer becomes next step's n
+    std::rotate(T.expd, T.expd + 2, T.expd + 3);
+    if (M->semiimplicit) std::rotate(T.impd, T.impd + 2, T.impd + 3);
+    grid_forward(G, T.var_np1, G->physical);                // calcTendency    :728-735
+    launch_assemble(G->ctx(), P->dg, G->dg, G->spectralB, prev ? &prev->dg : nullptr, prev ? prev->spectralB : nullptr, 0,
+                    P->spectralB);                         // :320-329
+    prev = G;
+  }
+}
+
+static void model_exchange(sb_model* M) {
+  if (M->nranks <= 1) return;
+  sb_grid* P = M->patch;
+  NC(g_nccl.AllReduce(P->spectralB, P->spectralB, (size_t)P->dg.S * P->dg.V, /*ncclFloat64*/ 8, /*ncclSum*/ 0, M->comm,
+                      (void*)P->stream));
+  ++M->extra_launches;
+}
+
+static void model_step(sb_model* M, int64_t t) {
+  model_advance_tiles(M, t);
+  model_exchange(M);
+  grid_spline(M->patch, M->patch->spectralB);  // splineTransform! :285
+}
+
+// ====================================================================================== C ABI
+extern "C" {
+
+const char* sb_last_error(void) { return g_err.c_str(); }
+const char* sb_version(void) {
+#ifdef SB_EMU
+  return "scythe_b200 0.1 (cpu-emulation test build)";
+#else
+  return "scythe_b200 0.1 (sm_100a)";
+#endif
+}
+int sb_device_count(void) {
+#ifdef SB_EMU
+  return 1;
+#else
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+#endif
+}
+
+int sb_grid_create(const sb_grid_params* gp, int device, void* stream, sb_grid_t* out) {
+  return guarded([&] { if (!out) throw std::invalid_argument("out is NULL"); *out = grid_new(gp, device, stream); });
+}
+int sb_grid_destroy(sb_grid_t g) { return guarded([&] { grid_free(g); }); }
+int sb_grid_get_info(sb_grid_t g, sb_grid_info* o) {
+  return guarded([&] {
+    if (!g || !o) throw std::invalid_argument("NULL argument");
+    const DevGrid& d = g->dg;
+    o->N = d.N; o->V = d.V; o->D = d.D; o->S = d.S; o->rDim = d.rDim; o->b_rDim = d.b_rDim;
+    o->zDim = d.has_z ? d.zDim : 0; o->b_zDim = d.has_z ? d.bz : 0; o->kDim = d.kDim;
+    o->lDim = d.has_l ? d.hpoints : 0; o->num_columns = d.has_z ? d.hpoints : 0;
+    o->patchOffsetL = d.patchOffsetL; o->ndims = g->ndims;
+  });
+}
+int sb_grid_get_gridpoints(sb_grid_t g, double* out, int64_t n) {
+  return guarded([&] {
+    if (!g || !out) throw std::invalid_argument("NULL argument");
+    if (n < g->dg.N * g->ndims) throw std::invalid_argument("gridpoints buffer too small");
+    fill_gridpoints(g, out);
+  });
+}
+static void check_slots(sb_grid_t g, const void* host, int slot0, int nslots) {
+  if (!g || !host) throw std::invalid_argument("NULL argument");
+  if (slot0 < 0 || nslots < 1 || slot0 + nslots > g->dg.D) throw std::invalid_argument("slot range outside 0..D-1");
+}
+int sb_grid_set_physical(sb_grid_t g, const double* host, int32_t slot0, int32_t nslots) {
+  return guarded([&] {
+    check_slots(g, host, slot0, nslots);
+    g->ensure_physical();
+    CU(cudaMemcpyAsync(g->physical + g->slot_stride() * slot0, host, (size_t)g->slot_stride() * nslots * sizeof(double),
+                       cudaMemcpyHostToDevice, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+  });
+}
+int sb_grid_get_physical(sb_grid_t g, double* host, int32_t slot0, int32_t nslots) {
+  return guarded([&] {
+    check_slots(g, host, slot0, nslots);
+    g->ensure_physical();
+    CU(cudaMemcpyAsync(host, g->physical + g->slot_stride() * slot0, (size_t)g->slot_stride() * nslots * sizeof(double),
+                       cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+  });
+}
+int sb_grid_set_spectral(sb_grid_t g, int32_t which, const double* host) {
+  return guarded([&] {
+    if (!g || !host || which < 0 || which > 1) throw std::invalid_argument("bad argument");
+    CU(cudaMemcpyAsync(which ? g->spectralA : g->spectralB, host, (size_t)g->dg.S * g->dg.V * sizeof(double),
+                       cudaMemcpyHostToDevice, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+  });
+}
+int sb_grid_get_spectral(sb_grid_t g, int32_t which, double* host) {
+  return guarded([&] {
+    if (!g || !host || which < 0 || which > 1) throw std::invalid_argument("bad argument");
+    CU(cudaMemcpyAsync(host, which ? g->spectralA : g->spectralB, (size_t)g->dg.S * g->dg.V * sizeof(double),
+                       cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+  });
+}
+int sb_spectral_transform(sb_grid_t g) {
+  return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); g->ensure_physical(); grid_forward(g, g->physical, nullptr); });
+}
+int sb_grid_transform(sb_grid_t g) {
+  return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); grid_spline(g, g->spectralB); grid_inverse(g, g); });
+}
+int sb_spline_transform(sb_grid_t patch, sb_grid_t shared) {
+  return guarded([&] {
+    if (!patch) throw std::invalid_argument("NULL grid");
+    sb_grid* s = shared ? shared : patch;
+    if (s->dg.S != patch->dg.S || s->dg.V != patch->dg.V) throw std::invalid_argument("shared spectral array has the wrong size");
+    grid_spline(patch, s->spectralB);
+  });
+}
+int sb_tile_transform(sb_grid_t patch, sb_grid_t tile) {
+  return guarded([&] { if (!patch || !tile) throw std::invalid_argument("NULL grid"); grid_inverse(patch, tile); });
+}
+int sb_calc_tile_sizes(const sb_grid_params* patch, int32_t ntiles, double* out) {
+  return guarded([&] { calc_tile_sizes(patch, ntiles, out); });
+}
+int sb_shared_clear(sb_grid_t patch) {
+  return guarded([&] {
+    if (!patch) throw std::invalid_argument("NULL grid");
+    CU(cudaMemsetAsync(patch->spectralB, 0, (size_t)patch->dg.S * patch->dg.V * sizeof(double), patch->stream));
+  });
+}
+int sb_shared_assemble(sb_grid_t patch, sb_grid_t tile, sb_grid_t prev, int32_t last) {
+  return guarded([&] {
+    if (!patch || !tile) throw std::invalid_argument("NULL grid");
+    launch_assemble(tile->ctx(), patch->dg, tile->dg, tile->spectralB, prev ? &prev->dg : nullptr,
+                    prev ? prev->spectralB : nullptr, last, patch->spectralB);
+  });
+}
+int sb_check_cfl(sb_grid_t g, int32_t* var, int64_t* index) {
+  return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); check_cfl(g, var, index); });
+}
+int sb_grid_sync(sb_grid_t g) {
+  return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); CU(cudaStreamSynchronize(g->stream)); });
+}
+int sb_grid_device_ptr(sb_grid_t g, int32_t which, void** ptr, int64_t* n) {
+  return guarded([&] {
+    if (!g || !ptr) throw std::invalid_argument("NULL argument");
+    switch (which) {
+      case 0: g->ensure_physical(); *ptr = g->physical; if (n) *n = g->dg.N * g->dg.V * g->dg.D; break;
+      case 1: *ptr = g->spectralB; if (n) *n = g->dg.S * g->dg.V; break;
+      case 2: *ptr = g->spectralA; if (n) *n = g->dg.S * g->dg.V; break;
+      default: throw std::invalid_argument("which must be 0, 1 or 2");
+    }
+  });
+}
+
+int sb_model_create(const sb_model_params* mp, int32_t ntiles, int32_t tile_first, int32_t tile_count, int device,
+                    void* stream, sb_model_t* out) {
+  return guarded([&] { if (!out) throw std::invalid_argument("out is NULL"); *out = model_new(mp, ntiles, tile_first, tile_count, device, stream); });
+}
+int sb_model_destroy(sb_model_t m) { return guarded([&] { model_free(m); }); }
+int sb_model_initialize(sb_model_t m, const double* ic) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); model_initialize(m, ic); });
+}
+int sb_model_patch(sb_model_t m, sb_grid_t* out) {
+  return guarded([&] { if (!m || !out) throw std::invalid_argument("NULL argument"); *out = m->patch; });
+}
+int sb_model_tile(sb_model_t m, int32_t i, sb_grid_t* out) {
+  return guarded([&] {
+    if (!m || !out || i < 0 || i >= (int)m->tiles.size()) throw std::invalid_argument("bad tile index");
+    *out = m->tiles[i].grid;
+  });
+}
+int sb_model_advance_tiles(sb_model_t m, int64_t t) {
+  return guarded([&] { if (!m || t < 1) throw std::invalid_argument("bad argument"); model_advance_tiles(m, t); });
+}
+int sb_model_exchange(sb_model_t m) {
+  try {
+    if (!m) return fail(SB_EINVAL, "NULL model");
+    model_exchange(m);
+    return SB_OK;
+  } catch (const std::exception& e) { return fail(SB_ECOMM, e.what()); }
+}
+int sb_model_spline_transform(sb_model_t m) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); grid_spline(m->patch, m->patch->spectralB); });
+}
+int sb_model_step(sb_model_t m, int64_t t) {
+  try {
+    if (!m || t < 1) return fail(SB_EINVAL, "bad argument");
+    model_step(m, t);
+    return SB_OK;
+  } catch (const CommError& e) { return fail(SB_ECOMM, e.what());
+  } catch (const std::exception& e) { return fail(SB_ECUDA, e.what()); }
+}
+int sb_model_run(sb_model_t m, int64_t t0, int64_t nsteps) {
+  try {
+    if (!m || t0 < 1 || nsteps < 0) return fail(SB_EINVAL, "bad argument");
+    for (int64_t t = t0; t < t0 + nsteps; ++t) model_step(m, t);
+    return SB_OK;
+  } catch (const CommError& e) { return fail(SB_ECOMM, e.what());
+  } catch (const std::exception& e) { return fail(SB_ECUDA, e.what()); }
+}
+int sb_model_output(sb_model_t m, double* host) {
+  return guarded([&] {
+    if (!m) throw std::invalid_argument("NULL model");
+    sb_grid* P = m->patch;
+    grid_inverse(P, P);
+    check_cfl(P, nullptr, nullptr);
+    if (host) {
+      CU(cudaMemcpyAsync(host, P->physical, (size_t)P->dg.N * P->dg.V * P->dg.D * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+      CU(cudaStreamSynchronize(P->stream));
+    }
+  });
+}
+int sb_model_get_state(sb_model_t m, int32_t tile, int32_t which, double* host) {
+  return guarded([&] {
+    if (!m || !host || tile < 0 || tile >= (int)m->tiles.size() || which < 0 || which > 6) throw std::invalid_argument("bad argument");
+    TileState& T = m->tiles[tile];
+    const double* src = which == 0 ? T.var_np1 : (which <= 3 ? T.expd[which - 1] : T.impd[which - 4]);
+    // after a step the rotation has already happened: expd[0] is scratch for the next step, so
+    // "expdot_n" of the step just taken is expd[1] (== expdot_nm1, as the reference leaves it)
+    if (which == 1) src = T.expd[1];
+    if (which == 4) src = T.impd[1];
+    if (!src) throw std::invalid_argument("state array not allocated (semi-implicit off)");
+    CU(cudaMemcpyAsync(host, src, (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+  });
+}
+int sb_model_sync(sb_model_t m) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); CU(cudaStreamSynchronize(m->stream)); });
+}
+int64_t sb_model_launch_count(sb_model_t m) {
+  if (!m) return 0;
+  long long n = m->patch->launches + m->extra_launches;
+  for (auto& t : m->tiles) n += t.grid->launches;
+  return n;
+}
+
+int sb_comm_unique_id(void* out128) {
+  try {
+    if (!out128) return fail(SB_EINVAL, "NULL argument");
+    nccl_load();
+    NC(g_nccl.GetUniqueId(out128));
+    return SB_OK;
+  } catch (const std::exception& e) { return fail(SB_ECOMM, e.what()); }
+}
+int sb_model_comm_init(sb_model_t m, const void* id128, int32_t rank, int32_t nranks) {
+  try {
+    if (!m || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(SB_EINVAL, "bad argument");
+    nccl_load();
+    Uid id;
+    std::memcpy(&id, id128, sizeof(id));
+    cudaSetDevice(m->device);
+    NC(g_nccl.CommInitRank(&m->comm, nranks, id, rank));
+    m->rank = rank;
+    m->nranks = nranks;
+    return SB_OK;
+  } catch (const std::exception& e) { return fail(SB_ECOMM, e.what()); }
+}
+
+int sb_timer_start(sb_grid_t g) {
+  return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); CU(cudaEventRecord(g->ev0, g->stream)); });
+}
+int sb_timer_stop(sb_grid_t g, float* ms) {
+  return guarded([&] {
+    if (!g || !ms) throw std::invalid_argument("NULL argument");
+    CU(cudaEventRecord(g->ev1, g->stream));
+    CU(cudaEventSynchronize(g->ev1));
+    CU(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+  });
+}
+
+}  // extern "C"

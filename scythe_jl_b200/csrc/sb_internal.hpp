@@ -1,0 +1,147 @@
+// sb_internal.hpp -- structures shared between host table generation, kernels and the C ABI.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "cuda_emu.h"
+
+namespace sb {
+
+// ---------------------------------------------------------------- host-side tables
+struct SplineFactor {        // Gamma (P+Q) Gamma^T = L L^T for one (BCL,BCR) pair
+  int M = 0;                 // b_rDim
+  int rL = 0, rR = 0;        // BC ranks folded on the left / right
+  int nfree = 0;
+  bool periodic = false;
+  double foldL[2] = {0, 0};  // rank1: (alpha1,beta1); rank2: (alpha2,beta2)
+  double foldR[2] = {0, 0};
+  std::vector<double> chol;  // [nfree][4]: {1/L_ii, L_{i,i-1}, L_{i,i-2}, L_{i,i-3}}
+  std::vector<double> dense; // periodic only: [M][M] row-major  T = Gamma^T G^-1 Gamma
+};
+SplineFactor make_spline_factor(int num_cells, double DX, double l_q, int bcl, int bcr);
+// basis weights at the 3 mish points of ANY cell: phi[d][mu][j] (d-th derivative of node
+// (cell-1+j) at mish point mu), wq[mu] quadrature weights (incl. DX)
+void spline_weights(double DX, double phi[3][3][4], double wq[3]);
+void spline_mish_points(double xmin, double DX, int num_cells, std::vector<double>& r);
+
+struct ChebTables {
+  int nz = 0, bz = 0;
+  std::vector<double> z;      // [nz] mish points
+  std::vector<double> fwd;    // [bz][nz]   b = fwd u            (CB)
+  std::vector<double> T0, T1, T2, Tint;  // [nz][nz]: value / d/dz / d2/dz2 / integral-from-bottom of mode k at z_j
+};
+ChebTables make_cheb_tables(int nz, int bz, double zmin, double zmax);
+// (I + Gamma) [bz][bz] for one (BCB,BCT) pair (CA)
+std::vector<double> cheb_bc_matrix(const ChebTables& t, int bcb, int bct);
+// dense helpers (row-major)
+void matmul(const double* A, const double* B, double* C, int n, int k, int m);  // C[n][m] = A[n][k] B[k][m]
+bool lu_factor(std::vector<double>& A, std::vector<int>& piv, int n);
+void lu_solve(const std::vector<double>& LU, const std::vector<int>& piv, int n, double* b);
+bool invert(std::vector<double>& A, int n);
+
+struct FftClass {            // one power-of-two convolution length
+  int L = 0, log2L = 0;
+  std::vector<double> tw;    // [L] complex: exp(-2 pi i t / L)
+};
+struct RingPlan {            // Bluestein plan of one ring (sub-DFT length m = n/4)
+  int n = 0, m = 0, L = 0, cls = 0;
+  long long off = 0;         // offset (in doubles) of this ring's tables in the blob
+};
+// blob layout per ring: chirp[2m] | wk[2m] | ph[2m] | FHp[2L]  (interleaved re,im)
+void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& classes,
+                      std::vector<RingPlan>& plans, std::vector<double>& blob);
+// host reference of the device FFT (used to build FHp and by self-tests)
+void host_fft_dif(double* x, int L, const double* tw);   // natural -> digit-reversed
+void host_fft_dit(double* x, int L, const double* tw);   // digit-reversed -> natural, unnormalised inverse
+
+// ---------------------------------------------------------------- device descriptors
+struct DevGrid {
+  int has_l, has_z;
+  int V, D;
+  int num_cells, rDim, b_rDim, zDim, bz, bzp, kDim, ncolp;
+  int patchOffsetL;          // radial mish-point offset of this tile inside the patch
+  int coefOffset;            // spectralIndexL-1: coefficient offset inside the patch
+  long long hpoints, N, S, W;
+  const int* ring_n;           // [rDim]
+  const int* ring_ri;          // [rDim]
+  const long long* ring_hoff;  // [rDim+1] horizontal point prefix
+  const long long* ring_woff;  // [rDim+1] retained-coefficient prefix (1+2ri per ring, or 1)
+  const double* rad;           // [rDim]
+  const double* zlev;          // [zDim]
+  const int* h2r;              // [hpoints] ring of each horizontal point
+  double phi[3][3][4];
+  double wq[3];
+};
+
+struct ZTile { int hcol0; int ncols; long long out_base; int out_stride; int pad; };
+struct LWork { int r; int row0; int nrows; int pad; };
+
+// ---------------------------------------------------------------- kernel launchers (sb_transforms.cu)
+struct LaunchCtx { cudaStream_t stream; long long* launches; };
+
+void launch_fwd_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars,
+                  const double* in, long long in_vstride, double* mirror, long long mirror_vstride,
+                  double* out, long long out_vstride, const double* fwdT);
+void launch_inv_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
+                  int nfields, const double* in, long long in_fstride, long long in_vstride,
+                  double* phys, const double* invM /* [V][3][bz][zDim] */);
+void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
+                  const LWork* const* work, const std::vector<FftClass>& classes,
+                  const double* const* tw, const RingPlan* plans, const double* blob, int nvars,
+                  const double* in, long long in_vstride, int in_is_z, double* mirror, long long mirror_vstride,
+                  double* out, long long out_vstride);
+void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
+                  const LWork* const* work, const std::vector<FftClass>& classes,
+                  const double* const* tw, const RingPlan* plans, const double* blob, int nvars,
+                  const double* in, long long in_fstride, long long in_vstride,
+                  double* out, long long out_fstride, long long out_vstride, int out_is_phys, int var0);
+void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride,
+                  double* B, long long B_vstride);
+void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch, int nvars,
+                  const double* A, long long A_vstride, double* out, long long out_fstride,
+                  long long out_vstride, int out_is_phys, int var0);
+struct DevSplineFactor {
+  int M, rL, rR, nfree, periodic;
+  double foldL[2], foldR[2];
+  const double* chol;   // [nfree][4]
+  const double* dense;  // [M][M]
+};
+void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFactor* factors /*device [V]*/,
+                         const std::vector<DevSplineFactor>& hfactors, const double* B, double* A);
+void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* tileB,
+                     const DevGrid* prev, const double* prevB, int last, double* shared);
+void launch_copy(const LaunchCtx& c, double* dst, const double* src, long long n);
+void launch_nan_scan(const LaunchCtx& c, const double* phys, long long N, int V, long long* result);
+
+// ---------------------------------------------------------------- equation sets (sb_model.cu)
+enum EquationSet {
+  EQ_LinearAdvection1D = 0, EQ_LinearAdvectionRZ, EQ_LinearAdvectionRL, EQ_LinearAdvectionRLZ,
+  EQ_LinearShallowWater1D, EQ_LinearShallowWaterRL, EQ_Oneway_ShallowWater_Slab,
+  EQ_Twoway_ShallowWater_Slab, EQ_Oneway_ShallowWater_HeightResolvedBL, EQ_Euler_test, EQ_COUNT
+};
+int equation_set_from_name(const char* name);
+struct EqParams {
+  double ts;
+  double c_0, K, g, Cd, Hfree, Hb, f, S1, H, Kh, Um, Vm;
+  double Pxi_bar;
+  int iw, ixi, ih;     // column indices of "w", "xi", "h" (0-based, -1 when absent)
+};
+struct ModelArrays {
+  double* phys;        // [D][V][N]
+  double* var_np1;     // [V][N]
+  double* exp_n;       // [V][N]  (pointers rotate each step)
+  double* exp_nm1;
+  double* exp_nm2;
+  double* imp_n;       // semi-implicit only
+  double* imp_nm1;
+  double* imp_nm2;
+  const double* colops;   // [4][zDim][zDim]: CB->CA->{CI, CIx, CIInt} of "h", (spare)
+  const double* refstate; // [3 profiles][3][zDim] sbar, xibar, mubar (value, dz, dzz)
+  const double* helm;     // [2][zDim][zDim] inverse Helmholtz matrices (tau=0.5 ts, 1.25 ts)
+  const double* sicols;   // [2 vars (xi,w)][3][zDim][zDim] composite column operators for semi-implicit
+};
+void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p,
+                         const ModelArrays& a, int tstep);
+
+}  // namespace sb

@@ -1,0 +1,390 @@
+// sb_model.cu -- fused physical-space tendency + explicit AB3 time step (+ semi-implicit
+// adjustment) kernels: the reference's equation-set plugins as built-in CUDA kernels.
+//
+// Reference: /root/reference/src/testModels.jl:1-215, src/shallowWaterModels.jl:1-298,346-511,
+// explicit_timestep src/semiimplicit.jl:672-698, semiimplicit_adjustment :521-597.
+// One pass over the point reads the derivative slots it needs and the two history arrays and
+// writes var_np1 and expdot_n; the history rotation (:689-695) is a pointer rotation on the host.
+#include "sb_internal.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace sb {
+
+static const char* kEqNames[EQ_COUNT] = {
+    "LinearAdvection1D", "LinearAdvectionRZ", "LinearAdvectionRL", "LinearAdvectionRLZ",
+    "LinearShallowWater1D", "LinearShallowWaterRL", "Oneway_ShallowWater_Slab", "Twoway_ShallowWater_Slab",
+    "Oneway_ShallowWater_HeightResolvedBL", "Euler_test"};
+
+int equation_set_from_name(const char* name) {
+  for (int i = 0; i < EQ_COUNT; ++i)
+    if (std::strcmp(name, kEqNames[i]) == 0) return i;
+  return -1;
+}
+
+// explicit_timestep for one value (src/semiimplicit.jl:682-696)
+__device__ __forceinline__ double ab_step(int t, double ts, double u, double fn, double fnm1, double fnm2) {
+  if (t == 1) return u + (ts * fn);
+  if (t == 2) return u + (0.5 * ts) * ((3.0 * fn) - fnm1);
+  return u + ((ts / 12.0) * ((23.0 * fn) - (16.0 * fnm1) + (5.0 * fnm2)));
+}
+
+struct PointCtx {
+  const DevGrid& g;
+  const ModelArrays& a;
+  long long i;
+  __device__ __forceinline__ double P(int v, int d) const { return a.phys[((long long)d * g.V + v) * g.N + i]; }
+  __device__ __forceinline__ void setP(int v, int d, double x) const { a.phys[((long long)d * g.V + v) * g.N + i] = x; }
+  __device__ __forceinline__ void advance(int v, int t, double ts, double u, double fn) const {
+    const long long o = (long long)v * g.N + i;
+    double f1 = (t >= 2) ? a.exp_nm1[o] : 0.0;
+    double f2 = (t >= 3) ? a.exp_nm2[o] : 0.0;
+    a.exp_n[o] = fn;
+    a.var_np1[o] = ab_step(t, ts, u, fn, f1, f2);
+  }
+};
+
+__device__ __forceinline__ double point_radius(const DevGrid& g, long long i) {
+  long long h = g.has_z ? i / g.zDim : i;
+  return g.rad[g.h2r[h]];
+}
+
+// shallow-water / slab boundary layer tendencies shared by Oneway/Twoway (src/shallowWaterModels.jl:60-108,176-228)
+__device__ __forceinline__ void slab_tendencies(const PointCtx& c, const EqParams& p, double r, bool twoway, int t) {
+  const double g = p.g, K = p.K, Cd = p.Cd, Hfree = p.Hfree, Hb = p.Hb, f = p.f;
+  double h = c.P(0, 0), hr = c.P(0, 1), hl = c.P(0, 3);
+  double ug = c.P(1, 0), ugr = c.P(1, 1), ugl = c.P(1, 3);
+  double vg = c.P(2, 0), vgr = c.P(2, 1), vgl = c.P(2, 3);
+  double ub = c.P(3, 0), ubr = c.P(3, 1), ubrr = c.P(3, 2), ubl = c.P(3, 3), ubll = c.P(3, 4);
+  double vb = c.P(4, 0), vbr = c.P(4, 1), vbrr = c.P(4, 2), vbl = c.P(4, 3), vbll = c.P(4, 4);
+  double U = 0.78 * sqrt((ub * ub) + (vb * vb));
+  double w = -Hb * ((ub / r) + ubr + (vbl / r));
+  c.setP(5, 0, w);
+  double w_ = 0.5 * fabs(w) - w;
+  double e0 = ((-vg * hl / r) + (-ug * hr)) + (-(Hfree + h) * ((ug / r) + ugr + (vgl / r)));
+  if (twoway) e0 += -(Hfree + h) * w * p.S1;
+  double e1 = ((-vg * ugl / r) + (-ug * ugr)) + (-g * hr) + (vg * (f + (vg / r)));
+  double e2 = ((-vg * vgl / r) + (-ug * vgr)) + (-g * (hl / r)) + (-ug * (f + (vg / r)));
+  double e3 = ((-vb * ubl / r) + (-ub * ubr)) + (-g * hr) + (vb * (f + (vb / r))) + (-(Cd * U * ub / Hb)) +
+              (w_ * (ug - ub) / Hb) +
+              (K * ((ubr / r) + ubrr - (ub / (r * r)) + (ubll / (r * r)) - (2.0 * vbl / (r * r))));
+  double e4 = ((-vb * vbl / r) + (-ub * vbr)) + (-g * (hl / r)) + (-ub * (f + (vb / r))) + (-(Cd * U * vb / Hb)) +
+              (w_ * (vg - vb) / Hb) +
+              (K * ((vbr / r) + vbrr - (vb / (r * r)) + (vbll / (r * r)) + (2.0 * ubl / (r * r))));
+  c.advance(0, t, p.ts, h, e0);
+  c.advance(1, t, p.ts, ug, e1);
+  c.advance(2, t, p.ts, vg, e2);
+  c.advance(3, t, p.ts, ub, e3);
+  c.advance(4, t, p.ts, vb, e4);
+  c.advance(5, t, p.ts, w, 0.0);
+}
+
+template <int EQ>
+__global__ void __launch_bounds__(256) k_pointwise(DevGrid g, EqParams p, ModelArrays a, int t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.N) return;
+  PointCtx c{g, a, i};
+  const double ts = p.ts;
+  if (EQ == EQ_LinearAdvection1D) {  // src/testModels.jl:15
+    double e = -(p.c_0 * c.P(0, 1)) + (p.K * c.P(0, 2));
+    c.advance(0, t, ts, c.P(0, 0), e);
+  } else if (EQ == EQ_LinearShallowWater1D) {  // src/shallowWaterModels.jl:253-254
+    double e0 = -p.H * c.P(1, 1);
+    double e1 = (-p.g * c.P(0, 1)) + (p.K * c.P(1, 2));
+    c.advance(0, t, ts, c.P(0, 0), e0);
+    c.advance(1, t, ts, c.P(1, 0), e1);
+  } else if (EQ == EQ_LinearAdvectionRZ) {  // src/testModels.jl:40 (vars h=1,u=2,w=4)
+    double r = point_radius(g, i);
+    double hr = c.P(0, 1), hrr = c.P(0, 2), hz = c.P(0, 3), hzz = c.P(0, 4);
+    double u = c.P(1, 0), w = c.P(3, 0);
+    double e = (-u * hr) + (-w * hz) + (p.K * ((hr / r) + hrr + hzz));
+    c.advance(0, t, ts, c.P(0, 0), e);
+    for (int v = 1; v < g.V; ++v) c.advance(v, t, ts, c.P(v, 0), 0.0);
+  } else if (EQ == EQ_LinearAdvectionRL || EQ == EQ_LinearAdvectionRLZ) {  // src/testModels.jl:62-68, :93
+    double r = point_radius(g, i);
+    double hr = c.P(0, 1), hl = c.P(0, 3);
+    double u = c.P(1, 0), v = c.P(2, 0);
+    double e;
+    if (EQ == EQ_LinearAdvectionRL && !(p.K > 0.0)) {
+      e = (-u * hr) - (v * (hl / r));
+    } else {
+      double hrr = c.P(0, 2), hll = c.P(0, 4);
+      e = (-u * hr) - (v * (hl / r)) + (p.K * ((hr / r) + hrr + (hll / (r * r))));
+    }
+    c.advance(0, t, ts, c.P(0, 0), e);
+    c.advance(1, t, ts, u, 0.0);
+    c.advance(2, t, ts, v, 0.0);
+    for (int vv = 3; vv < g.V; ++vv) c.advance(vv, t, ts, c.P(vv, 0), 0.0);
+  } else if (EQ == EQ_LinearShallowWaterRL) {  // src/shallowWaterModels.jl:290-292
+    double r = point_radius(g, i);
+    double hr = c.P(0, 1), hl = c.P(0, 3);
+    double u = c.P(1, 0), ur = c.P(1, 1), urr = c.P(1, 2), ull = c.P(1, 4);
+    double v = c.P(2, 0), vr = c.P(2, 1), vrr = c.P(2, 2), vl = c.P(2, 3), vll = c.P(2, 4);
+    double e0 = -p.H * ((u / r) + ur + (vl / r));
+    double e1 = (-p.g * hr) + (p.K * ((ur / r) + urr + (ull / (r * r))));
+    double e2 = (-p.g * (hl / r)) + (p.K * ((vr / r) + vrr + (vll / (r * r))));
+    c.advance(0, t, ts, c.P(0, 0), e0);
+    c.advance(1, t, ts, u, e1);
+    c.advance(2, t, ts, v, e2);
+  } else if (EQ == EQ_Oneway_ShallowWater_Slab) {
+    slab_tendencies(c, p, point_radius(g, i), false, t);
+  } else if (EQ == EQ_Twoway_ShallowWater_Slab) {
+    slab_tendencies(c, p, point_radius(g, i), true, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// column kernels: one thread per level, blockDim = (zDim, columns per block)
+// colops (transposed, [k][z'][z]): 0 = CB->CA->CI, 1 = CB->CA->CIx, 2 = CB->CA->CIInt  (of variable "h")
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ double col_matvec(const double* __restrict__ Mt, const double* x, int nz, int z) {
+  double s = 0.0;
+  for (int k = 0; k < nz; ++k) s = fma(Mt[(size_t)k * nz + z], x[k], s);
+  return s;
+}
+
+// Oneway_ShallowWater_HeightResolvedBL, src/shallowWaterModels.jl:346-511
+__global__ void k_heightresolved_bl(DevGrid g, EqParams p, ModelArrays a, int t) {
+  SB_DYN_SMEM(double, sm);
+  const int nz = g.zDim, z = threadIdx.x, cl = threadIdx.y;
+  const long long col = (long long)blockIdx.x * blockDim.y + cl;
+  const bool live = col < g.hpoints;
+  double* s0 = sm + (size_t)cl * 4 * nz;  // per-column scratch: 4 vectors
+  double* s1 = s0 + nz;
+  double* s2 = s1 + nz;
+  double* s3 = s2 + nz;
+  const long long i = live ? col * nz + z : 0;
+  PointCtx c{g, a, i};
+  const int ring = live ? g.h2r[col] : 0;
+  const double r = g.rad[ring];
+  const double zz = g.zlev[z];
+  const double* Mint = a.colops + (size_t)2 * nz * nz;
+  const double* Mdz = a.colops + (size_t)1 * nz * nz;
+  double h = c.P(0, 0), hr = c.P(0, 1), hl = c.P(0, 3);
+  double ug = c.P(1, 0), ugr = c.P(1, 1), ugl = c.P(1, 3);
+  double vg = c.P(2, 0), vgr = c.P(2, 1), vgl = c.P(2, 3);
+  double ub = c.P(3, 0), ubr = c.P(3, 1), ubrr = c.P(3, 2), ubl = c.P(3, 3), ubll = c.P(3, 4), ubz = c.P(3, 5);
+  double vb = c.P(4, 0), vbr = c.P(4, 1), vbrr = c.P(4, 2), vbl = c.P(4, 3), vbll = c.P(4, 4), vbz = c.P(4, 5);
+  double S = sqrt((ubz * ubz) + (vbz * vbz));
+  double l = 1.0 / ((1.0 / (0.4 * zz)) + (1.0 / 80.0));
+  double Kv = (l * l) * S;
+  s0[z] = -((ub / r) + ubr + (vbl / r));
+  s1[z] = ub;
+  s2[z] = vb;
+  __syncthreads();
+  double wb = col_matvec(Mint, s0, nz, z);
+  // storm-motion surface wind rotated by the column's azimuth; 10 m wind = level 2
+  const int jring = (int)(col - g.ring_hoff[ring]);
+  const int n = g.ring_n[ring], ri = g.ring_ri[ring];
+  const double dl = 6.283185307179586476925286766559 / n;
+  const double lam = 0.5 * dl * (ri - 1) + dl * jring;
+  const double sfcu = (p.Um * cos(lam)) + (p.Vm * sin(lam));
+  const double sfcv = (p.Vm * cos(lam)) - (p.Um * sin(lam));
+  const double u10 = s1[1] + sfcu, v10 = s2[1] + sfcv;
+  const double U10 = sqrt(u10 * u10 + v10 * v10);
+  double Cd = p.Cd;
+  if (U10 < 5.2) Cd = 1.0e-3;
+  else if (U10 < 33.6) Cd = 4.4e-4 * sqrt(U10);
+  __syncthreads();
+  s0[z] = (z == 0) ? Cd * U10 * u10 : Kv * ubz;
+  s3[z] = (z == 0) ? Cd * U10 * v10 : Kv * vbz;
+  __syncthreads();
+  double vdu = col_matvec(Mdz, s0, nz, z);
+  double vdv = col_matvec(Mdz, s3, nz, z);
+  if (!live) return;
+  const double gg = p.g, Kh = p.Kh, Hfree = p.Hfree, f = p.f;
+  c.setP(5, 0, wb);
+  double e0 = ((-vg * hl / r) + (-ug * hr)) + (-(Hfree + h) * ((ug / r) + ugr + (vgl / r)));
+  double e1 = ((-vg * ugl / r) + (-ug * ugr)) + (-gg * hr) + (vg * (f + (vg / r)));
+  double e2 = ((-vg * vgl / r) + (-ug * vgr)) + (-gg * (hl / r)) + (-ug * (f + (vg / r)));
+  double hdu = Kh * ((ubr / r) + ubrr - (ub / (r * r)) + (ubll / (r * r)) - (2.0 * vbl / (r * r)));
+  double hdv = Kh * ((vbr / r) + vbrr - (vb / (r * r)) + (vbll / (r * r)) + (2.0 * ubl / (r * r)));
+  double e3 = ((-vb * ubl / r) + (-ub * ubr) + (-wb * ubz)) + (-gg * hr) + (vb * (f + (vb / r))) + vdu + hdu;
+  double e4 = ((-vb * vbl / r) + (-ub * vbr) + (-wb * vbz)) + (-gg * (hl / r)) + (-ub * (f + (vb / r))) + vdv + hdv;
+  c.advance(0, t, p.ts, h, e0);
+  c.advance(1, t, p.ts, ug, e1);
+  c.advance(2, t, p.ts, vg, e2);
+  c.advance(3, t, p.ts, ub, e3);
+  c.advance(4, t, p.ts, vb, e4);
+  c.advance(5, t, p.ts, wb, 0.0);
+}
+
+// ---- thermodynamic closure for Euler_test (src/thermodynamics.jl:2-17,31-32,67-80,184-269) ----
+#define TH_Rd 287.04
+#define TH_Rv 461.50
+#define TH_Cvd 716.96
+#define TH_Cvv 1410.0
+#define TH_Cl 4186.0
+#define TH_g 9.81
+#define TH_Lv0 2.501e6
+#define TH_T0 273.16
+#define TH_p0 1000.0
+#define TH_q0 1.0e-7
+
+struct Thermo { double rho_d0, rho_v0, Lv_T0; };
+static Thermo make_thermo() {
+  Thermo th;
+  th.rho_d0 = 100.0 * TH_p0 / (TH_T0 * TH_Rd);
+  double Tc = TH_T0 - 273.15;
+  double es = 6.112 * std::exp(17.67 * Tc / (Tc + 243.5));
+  th.rho_v0 = 100.0 * es / (TH_T0 * TH_Rv);
+  th.Lv_T0 = TH_Lv0 + (((TH_Cvv + TH_Rv) - TH_Cl) * (TH_T0 - TH_T0));
+  return th;
+}
+__device__ __forceinline__ double th_ahyp(double mu) {
+  return (mu < 0.0) ? 0.0 : sqrt(mu * mu + TH_q0 * TH_q0) + mu - TH_q0;
+}
+__device__ __forceinline__ double th_dmudq(double mu, double q_v) { return ((q_v + TH_q0) - mu) / (q_v + TH_q0); }
+__device__ __forceinline__ double th_P_s(double Tk, double rho_d, double q_v) {
+  return Tk * ((rho_d * TH_Rd) + (q_v * rho_d * TH_Rv)) / (TH_Cvd + (q_v * TH_Cvv));
+}
+__device__ __forceinline__ double th_pgrad(const Thermo& th, double Tk, double rho_d, double q_v, double s_x,
+                                           double xi_x, double qv_x) {
+  double Ps = th_P_s(Tk, rho_d, q_v);
+  double Pxi = (TH_Rd + (q_v * rho_d * TH_Rv)) * ((rho_d * Tk) + Ps);
+  double Pqv = 0.0;
+  if (q_v != 0.0) {
+    double rho_v = q_v * rho_d;
+    double qf = TH_Rv * (1 + log(rho_v / th.rho_v0)) - (TH_Cvv * log(Tk / TH_T0)) - th.Lv_T0 / TH_T0;
+    Pqv = (rho_d * TH_Rv * Tk) + qf * Ps;
+  }
+  return (Ps * s_x) + (Pxi * xi_x) + (Pqv * qv_x);
+}
+
+// Euler_test + semiimplicit_adjustment, src/testModels.jl:100-215, src/semiimplicit.jl:521-597
+// sicols (transposed [k][z'][z]): 0 = F (CB->CA->CI of xi), 1 = Dz (CB->CA->CIx of xi),
+//   2,3 = W,X for tau = 0.5 ts ; 4,5 = W,X for tau = 1.25 ts   (W = dct H^-1 Shift, X = dct1 H^-1 Shift)
+__global__ void k_euler_test(DevGrid g, EqParams p, ModelArrays a, Thermo th, int semi, int t) {
+  SB_DYN_SMEM(double, sm);
+  const int nz = g.zDim, z = threadIdx.x, cl = threadIdx.y;
+  const long long col = (long long)blockIdx.x * blockDim.y + cl;
+  const bool live = col < g.hpoints;
+  double* s0 = sm + (size_t)cl * 2 * nz;
+  double* s1 = s0 + nz;
+  const long long i = live ? col * nz + z : 0;
+  PointCtx c{g, a, i};
+  const double ts = p.ts, K = p.K;
+  const double* rs = a.refstate;  // [profile][deriv][z]
+  const double sbar = rs[z], sbar_z = rs[nz + z];
+  const double xibar = rs[3 * nz + z], xibar_z = rs[4 * nz + z];
+  const double mubar = rs[6 * nz + z], mubar_z = rs[7 * nz + z];
+  double s = c.P(0, 0), s_x = c.P(0, 1), s_xx = c.P(0, 2), s_z = c.P(0, 3), s_zz = c.P(0, 4);
+  double xi = c.P(1, 0), xi_x = c.P(1, 1), xi_z = c.P(1, 3);
+  double mu = c.P(2, 0), mu_x = c.P(2, 1), mu_xx = c.P(2, 2), mu_z = c.P(2, 3), mu_zz = c.P(2, 4);
+  double u = c.P(3, 0), u_x = c.P(3, 1), u_xx = c.P(3, 2), u_z = c.P(3, 3), u_zz = c.P(3, 4);
+  double w = c.P(4, 0), w_x = c.P(4, 1), w_xx = c.P(4, 2), w_z = c.P(4, 3), w_zz = c.P(4, 4);
+  // thermodynamic_tuple
+  double q_v = th_ahyp(mu + mubar);
+  double rho_d = th.rho_d0 * exp(xi + xibar);
+  double Cfac = TH_Cvd + (q_v * TH_Cvv);
+  double qfac = (q_v != 0.0) ? pow(rho_d * q_v / th.rho_v0, (q_v * TH_Rv) / Cfac) : 1.0;
+  double Tk = TH_T0 * exp(((s + sbar) - (q_v * th.Lv_T0 / TH_T0)) / Cfac) * pow(rho_d / th.rho_d0, TH_Rd / Cfac) * qfac;
+  double rho_t = rho_d * (1.0 + q_v);
+  double dm = th_dmudq(mu + mubar, q_v);
+  double qvp_x = mu_x / dm, qvp_z = mu_z / dm;
+  double rhobar = (th.rho_d0 * exp(xibar)) * (1.0 + th_ahyp(mubar));
+  double rho_p = rho_t - rhobar;
+  double e0 = ((-u * s_x) + (-w * (s_z + sbar_z))) + (K * (s_xx + s_zz));
+  double e1 = ((-u * xi_x) + (-w * (xi_z + xibar_z))) - u_x - w_z;
+  double e2 = ((-u * mu_x) + (-w * (mu_z + mubar_z))) + (K * (mu_xx + mu_zz));
+  double e3 = ((-u * u_x) + (-w * u_z)) + (-(th_pgrad(th, Tk, rho_d, q_v, s_x, xi_x, qvp_x) / rho_t)) + (K * (u_xx + u_zz));
+  double e4 = ((-u * w_x) + (-w * w_z)) +
+              (-(TH_g * rho_p / rho_t) - (th_pgrad(th, Tk, rho_d, q_v, s_z, xi_z, qvp_z) / rho_t)) + (K * (w_xx + w_zz));
+  const long long o1 = (long long)1 * g.N + i, o4 = (long long)4 * g.N + i;
+  const double imp1 = -w_z, imp4 = -(p.Pxi_bar * xi_z);
+  double f1, f2;
+  f1 = (t >= 2) ? a.exp_nm1[o1] : 0.0; f2 = (t >= 3) ? a.exp_nm2[o1] : 0.0;
+  double xi_np1 = ab_step(t, ts, xi, e1, f1, f2);
+  f1 = (t >= 2) ? a.exp_nm1[o4] : 0.0; f2 = (t >= 3) ? a.exp_nm2[o4] : 0.0;
+  double w_np1 = ab_step(t, ts, w, e4, f1, f2);
+  if (live) {
+    c.advance(0, t, ts, s, e0);
+    c.advance(2, t, ts, mu, e2);
+    c.advance(3, t, ts, u, e3);
+    a.exp_n[o1] = e1;
+    a.exp_n[o4] = e4;
+    if (a.imp_n) { a.imp_n[o1] = imp1; a.imp_n[o4] = imp4; }
+  }
+  if (!semi) {
+    if (live) { a.var_np1[o1] = xi_np1; a.var_np1[o4] = w_np1; }
+    return;
+  }
+  // ---- semi-implicit adjustment (xi uses impdot[:,xi] = "wdot", w uses impdot[:,w] = "xidot")
+  double wdot_n = imp1, xidot_n = imp4;
+  double wdot_nm1 = (t >= 2) ? a.imp_nm1[o1] : 0.0, wdot_nm2 = (t >= 3) ? a.imp_nm2[o1] : 0.0;
+  double xidot_nm1 = (t >= 2) ? a.imp_nm1[o4] : 0.0, xidot_nm2 = (t >= 3) ? a.imp_nm2[o4] : 0.0;
+  double tau, w_ns, xi_ns;
+  if (t == 1) {
+    tau = 0.5 * ts;
+    w_ns = w_np1 - (ts * xidot_n) + (ts * 0.5 * xidot_n);
+    xi_ns = xi_np1 - (ts * wdot_n) + (ts * 0.5 * wdot_n);
+  } else if (t == 2) {
+    tau = 1.25 * ts;
+    w_ns = w_np1 - (0.5 * ts) * ((3.0 * xidot_n) - xidot_nm1) - (ts * xidot_n) + (ts * 0.75 * xidot_nm1);
+    xi_ns = xi_np1 - (0.5 * ts) * ((3.0 * wdot_n) - wdot_nm1) - (ts * wdot_n) + (ts * 0.75 * wdot_nm1);
+  } else {
+    tau = 1.25 * ts;
+    w_ns = w_np1 - ((ts / 12.0) * ((23.0 * xidot_n) - (16.0 * xidot_nm1) + (5.0 * xidot_nm2))) - (ts * xidot_n) +
+           (ts * 0.75 * xidot_nm1);
+    xi_ns = xi_np1 - ((ts / 12.0) * ((23.0 * wdot_n) - (16.0 * wdot_nm1) + (5.0 * wdot_nm2))) - (ts * wdot_n) +
+            (ts * 0.75 * wdot_nm1);
+  }
+  const size_t nn = (size_t)nz * nz;
+  s0[z] = xi_ns;
+  __syncthreads();
+  double xi_f = col_matvec(a.sicols, s0, nz, z);
+  double xi_fz = col_matvec(a.sicols + nn, s0, nz, z);
+  s1[z] = tau * p.Pxi_bar * xi_fz - w_ns;   // g before the BC-row shift (folded into W, X)
+  __syncthreads();
+  const double* Wm = a.sicols + ((t == 1) ? 2 : 4) * nn;
+  const double* Xm = Wm + nn;
+  double w_new = col_matvec(Wm, s1, nz, z);
+  double xi_new = xi_f - tau * col_matvec(Xm, s1, nz, z);
+  if (live) {
+    a.var_np1[o4] = w_new;
+    a.var_np1[o1] = xi_new;
+  }
+}
+
+template <int EQ>
+static void launch_pw(const LaunchCtx& c, const DevGrid& g, const EqParams& p, const ModelArrays& a, int t) {
+  long long blocks = (g.N + 255) / 256;
+  SB_LAUNCH(k_pointwise<EQ>, dim3((unsigned)blocks), dim3(256), 0, c.stream, g, p, a, t);
+}
+
+void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p, const ModelArrays& a,
+                         int tstep) {
+  switch (eq) {
+    case EQ_LinearAdvection1D: launch_pw<EQ_LinearAdvection1D>(c, g, p, a, tstep); break;
+    case EQ_LinearAdvectionRZ: launch_pw<EQ_LinearAdvectionRZ>(c, g, p, a, tstep); break;
+    case EQ_LinearAdvectionRL: launch_pw<EQ_LinearAdvectionRL>(c, g, p, a, tstep); break;
+    case EQ_LinearAdvectionRLZ: launch_pw<EQ_LinearAdvectionRLZ>(c, g, p, a, tstep); break;
+    case EQ_LinearShallowWater1D: launch_pw<EQ_LinearShallowWater1D>(c, g, p, a, tstep); break;
+    case EQ_LinearShallowWaterRL: launch_pw<EQ_LinearShallowWaterRL>(c, g, p, a, tstep); break;
+    case EQ_Oneway_ShallowWater_Slab: launch_pw<EQ_Oneway_ShallowWater_Slab>(c, g, p, a, tstep); break;
+    case EQ_Twoway_ShallowWater_Slab: launch_pw<EQ_Twoway_ShallowWater_Slab>(c, g, p, a, tstep); break;
+    case EQ_Oneway_ShallowWater_HeightResolvedBL: {
+      int cpb = 128 / g.zDim; if (cpb < 1) cpb = 1;
+      long long blocks = (g.hpoints + cpb - 1) / cpb;
+      size_t smem = (size_t)cpb * 4 * g.zDim * sizeof(double);
+      SB_LAUNCH(k_heightresolved_bl, dim3((unsigned)blocks), dim3(g.zDim, cpb), smem, c.stream, g, p, a, tstep);
+      break;
+    }
+    case EQ_Euler_test: {
+      int cpb = 128 / g.zDim; if (cpb < 1) cpb = 1;
+      long long blocks = (g.hpoints + cpb - 1) / cpb;
+      size_t smem = (size_t)cpb * 2 * g.zDim * sizeof(double);
+      SB_LAUNCH(k_euler_test, dim3((unsigned)blocks), dim3(g.zDim, cpb), smem, c.stream, g, p, a, make_thermo(),
+                a.imp_n ? 1 : 0, tstep);
+      break;
+    }
+    default: throw std::runtime_error("equation set has no CUDA kernel");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("equation-set launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+}  // namespace sb
