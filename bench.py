@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- RLZ timesteps/sec (BASELINE.json metric) on the north-star configuration.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference on host cores
+
+Workload: RLZ, 334 radial cells (rings 8..4012 points), 64 levels (43 modes),
+N = 128,897,280 points, V = 3 (LinearAdvectionRLZ), synthetic vortex.  With N GPUs the radial
+domain is scaled (num_cells x sqrt(N)) so every GPU owns one C4-sized tile (weak scaling, C5) and
+`value` counts C4-equivalent tile-timesteps per second over all ranks.
+A "step" = one iteration of model_loop: K3 tileTransform! -> equation set + AB3 -> K1
+spectralTransform! -> shared-spectral sum (NCCL all-reduce when N>1) -> K2 splineTransform!.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "RLZ timesteps/sec"
+UNIT = "timesteps/s"
+C4_CELLS, ZDIM, NVARS = 334, 64, 3
+XMAX, ZMAX = 1.0e6, 2.0e4
+TS, KDIFF = 2.0, 500.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=0, help="override radial cells per GPU tile (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ synthetic initial state
+def tile_rings(xmin, DX, num_cells, patch_offset):
+    g = math.sqrt(3.0 / 5.0)
+    c = xmin + (np.arange(num_cells) + 0.5) * DX
+    r = (c[:, None] + 0.5 * DX * np.array([-g, 0.0, g])[None, :]).reshape(-1)
+    ri = np.arange(1, 3 * num_cells + 1) + patch_offset
+    return r, ri
+
+
+def synthetic_state(xmin, DX, num_cells, patch_offset, zDim, zmax, out=None):
+    """Rankine-like vortex + wavenumber-2 asymmetry, exp(-z/H) decay; h Gaussian.  Deterministic.
+    Returns [N, 3] Fortran-ordered (h, u, v), N = sum_r (4+4 ri) * zDim with z fastest."""
+    r, ri = tile_rings(xmin, DX, num_cells, patch_offset)
+    n = 4 + 4 * ri
+    rr = np.repeat(r, n)
+    lam = np.concatenate([0.5 * (2 * np.pi / k) * (i - 1) + (2 * np.pi / k) * np.arange(k) for k, i in zip(n, ri)])
+    z = 0.5 * zmax * (1.0 - np.cos(np.pi * np.arange(zDim) / (zDim - 1)))
+    Rmax, Vmax = 5.0e4, 50.0
+    vbar = np.where(rr < Rmax, Vmax * rr / Rmax, Vmax * Rmax / rr)
+    hh = 100.0 * np.exp(-(rr / 2.0e5) ** 2) * (1.0 + 0.1 * np.cos(2.0 * lam))
+    uu = -0.05 * vbar * (1.0 + 0.2 * np.sin(lam))
+    vv = vbar * (1.0 + 0.1 * np.cos(2.0 * lam))
+    zh = 1.0 + 0.3 * np.cos(np.pi * z / zmax)
+    zw = np.exp(-z / 8.0e3)
+    N = rr.size * zDim
+    if out is None:
+        out = np.empty((N, 3), order="F")
+    out[:, 0] = (hh[:, None] * zh[None, :]).reshape(-1)
+    out[:, 1] = (uu[:, None] * zw[None, :]).reshape(-1)
+    out[:, 2] = (vv[:, None] * zw[None, :]).reshape(-1)
+    return out
+
+
+def dims(num_cells, patch_offset=0, zDim=ZDIM):
+    ri = np.arange(1, 3 * num_cells + 1) + patch_offset
+    hp = int((4 + 4 * ri).sum())
+    W = int((1 + 2 * ri).sum())
+    bz = min(zDim, (2 * zDim - 1) // 3 + 1)
+    kDim = 3 * num_cells + patch_offset
+    S = bz * (num_cells + 3) * (1 + 2 * kDim)
+    return dict(N=hp * zDim, hp=hp, W=W, bz=bz, S=S, D=7)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/sb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle = the reference restated)
+def cpu_baseline(steps=2, warmup=1, cells=24, workers=None):
+    """Oracle ModelRun on a bounded sample of the same workload, all host threads, scaled by points."""
+    from oracle import grids as G
+    from oracle import model as M
+    workers = workers or os.cpu_count() or 1
+    gp = G.GridParameters(geometry="RLZ", xmin=0.0, xmax=XMAX * cells / C4_CELLS, num_cells=cells, zmin=0.0, zmax=ZMAX,
+                          zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
+    mp = M.ModelParameters(ts=TS, integration_time=TS * (steps + warmup), equation_set="LinearAdvectionRLZ",
+                           grid_params=gp, physical_params={"K": KDIFF})
+    ic = synthetic_state(0.0, XMAX / C4_CELLS, cells, 0, ZDIM, ZMAX)
+    run = M.ModelRun(mp, 1, ic, workers=workers)
+    run.run(warmup)
+    t0 = time.perf_counter()
+    run.run(steps)
+    dt = (time.perf_counter() - t0) / steps
+    n_s, n_full = dims(cells)["N"], dims(C4_CELLS)["N"]
+    value = (1.0 / dt) * n_s / n_full
+    sample = (f"oracle (NumPy/SciPy pocketfft restatement) ModelRun, RLZ {cells} cells x {ZDIM} levels x {NVARS} vars = "
+              f"{n_s} points, {steps} timed steps ({dt * 1e3:.0f} ms/step), scaled by points to the "
+              f"{n_full}-point C4 grid")
+    return {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, dt = cpu_baseline(steps=max(args.steps, 1), warmup=min(max(args.warmup, 1), 2))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"] * 1.0, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, C4_CELLS), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(ngpus, cells_per_tile):
+    total_cells = int(round(cells_per_tile * math.sqrt(ngpus)))
+    return {"workload": "C4 RLZ LinearAdvectionRLZ" if ngpus == 1 else "C5 RLZ radius-scaled, one C4-sized tile per GPU",
+            "geometry": "RLZ", "num_cells": total_cells, "zDim": ZDIM, "b_zDim": 43, "vars": NVARS,
+            "equation_set": "LinearAdvectionRLZ", "tiles": ngpus, "ts": TS,
+            "l2": "working set >> 126 MB L2 (physical 21.7 GB/GPU); no flush needed",
+            "units": "C4-equivalent (128.9 M-point) tile-timesteps, summed over ranks"}
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+
+    import scythe_jl_b200 as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ntiles = world
+    cells_tile = args.cells or C4_CELLS
+    total_cells = int(round(cells_tile * math.sqrt(ntiles)))
+    DX = XMAX / C4_CELLS
+    gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * total_cells, num_cells=total_cells, zmin=0.0, zmax=ZMAX,
+                          zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
+    mp = S.ModelParameters(ts=TS, integration_time=TS * 1000, equation_set="LinearAdvectionRLZ", grid_params=gp,
+                           physical_params={"K": KDIFF})
+    m = S.Model(mp, num_tiles=ntiles, device=local_rank, distributed=distributed)
+    tp = m.tile_params
+    tcells, tsil = int(tp[2, m.tile_first]), int(tp[3, m.tile_first])
+    ic = synthetic_state(tp[0, m.tile_first], DX, tcells, (tsil - 1) * 3, ZDIM, ZMAX)
+    m.initialize_tiles([ic])
+    m.sync()
+    tile = m.tiles[0]
+    d = dict(N=tile.N, S=tile.S, D=tile.D)
+    lib = m.lib
+    import ctypes as C
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        lib.check(lib.sb_timer_start(m.patch.handle))
+        for _ in range(n):
+            fn()
+        ms = C.c_float()
+        lib.check(lib.sb_timer_stop(m.patch.handle, C.byref(ms)))
+        barrier()
+        t = torch.tensor([ms.value], device="cuda")
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up, then K timed steps with per-kernel event profiling on
+    for _ in range(args.warmup):
+        m.step()
+    l0 = m.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    m.profile(True)
+    total_ms = timed(m.step, args.steps)
+    m.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = m.profile_report()
+    launches = m.launch_count() - l0
+    ms_step = total_ms / args.steps
+    value = ntiles * 1e3 / ms_step
+
+    # transforms/sec (the second half of the BASELINE metric): K1 alone and K2+K3 alone on the tile
+    def k1():
+        lib.check(lib.sb_spectral_transform(tile.handle))
+
+    def k23():
+        lib.check(lib.sb_spline_transform(m.patch.handle, m.patch.handle))
+        lib.check(lib.sb_tile_transform(m.patch.handle, tile.handle))
+    k1(); k23()
+    k1_ms = timed(k1, 3) / 3
+    lib.check(lib.sb_model_spline_transform(m.handle))
+    k23_ms = timed(k23, 3) / 3
+
+    # end to end through the public API with HOST buffers: pinned state in -> one model_loop cycle -> state out
+    e2e = None
+    if not args.no_e2e and not distributed:
+        hin = torch.empty((NVARS, tile.N), dtype=torch.float64, pin_memory=True)
+        hout = torch.empty((NVARS, tile.N), dtype=torch.float64, pin_memory=True)
+        a_in, a_out = hin.numpy().T, hout.numpy().T      # [N, V] Fortran views
+        m.get_state_into(0, a_in)
+
+        def e2e_step():
+            m.set_state(0, a_in)
+            m.cycle()
+            m.get_state_into(0, a_out)
+        e2e_step()
+        e_ms = timed(e2e_step, max(2, min(args.steps, 3))) / max(2, min(args.steps, 3))
+        e2e = {"value": 1e3 / e_ms, "unit": UNIT, "h2d_bytes_per_step": int(a_in.nbytes), "d2h_bytes_per_step": int(a_out.nbytes),
+               "what": "Model.set_state(host pinned [N,V]) -> Model.cycle() -> get_state(host pinned [N,V])"}
+    elif distributed:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "what": "end-to-end host-buffer stepping is measured at N=1 only"}
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: K3 (tileTransform!) dominates; algorithmic bytes per SURVEY 8(d)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    N, Sg, D, V = d["N"], d["S"], d["D"], NVARS
+    Sp = m.patch.S
+    groups = {
+        "K3 tileTransform! (inv_r+inv_l+inv_z)": (["inv_r", "inv_l", "inv_z"], 8.0 * V * (Sg + N * D)),
+        "K1 spectralTransform! (fwd_z+fwd_l+fwd_r)": (["fwd_z", "fwd_l", "fwd_r"], 8.0 * V * (N + Sg)),
+        "K2 splineTransform! (spline_solve)": (["spline_solve"], 8.0 * V * 2 * Sp),
+        "K4 equation set + AB3 (LinearAdvectionRLZ)": (["equation_set"], 8.0 * N * (5 + 2 + 6 + 6)),
+    }
+    detail = {}
+    for name, (ks, nbytes) in groups.items():
+        ms = sum(prof.get(k, {"ms": 0.0})["ms"] for k in ks) / args.steps
+        detail[name] = {"ms_per_step": ms, "algorithmic_GB": nbytes / 1e9,
+                        "achieved_GBps": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else None,
+                        "frac": ((nbytes / 1e9) / (ms / 1e3) / peak) if ms > 0 else None}
+    kern_ms = {k: v["ms"] / args.steps for k, v in prof.items()}
+    top = max(detail, key=lambda k: detail[k]["ms_per_step"])
+    roof = {"bound": "hbm", "kernel": top, "achieved": detail[top]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+            "frac": detail[top]["frac"], "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": detail[top]["algorithmic_GB"] * 1e9,
+            "share_of_step": detail[top]["ms_per_step"] / ms_step}
+    step_bytes = 8.0 * V * (2 * N * D + 6 * N + 4 * Sg)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world, cells_tile), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roof, "roofline_detail": detail, "kernel_ms_per_step": kern_ms,
+            "timestep_algorithmic_GB": step_bytes / 1e9,
+            "timestep_frac_of_hbm_roofline": (step_bytes / 1e9) / (ms_step / 1e3) / peak,
+            "transforms_per_s": {"spectralTransform_K1": 1e3 / k1_ms, "gridTransform_K2K3": 1e3 / k23_ms,
+                                 "K1_ms": k1_ms, "K2K3_ms": k23_ms, "vars": V}}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"], _ = cpu_baseline()
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N=1 only"}
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

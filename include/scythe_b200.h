@@ -175,6 +175,24 @@ int sb_model_output(sb_model_t m, double* host_physical);
 /* ModelTile state arrays of local tile i <-> host [N_tile,V]:
  * which = 0 var_np1, 1 expdot_n, 2 expdot_nm1, 3 expdot_nm2, 4 impdot_n, 5 impdot_nm1, 6 impdot_nm2 */
 int sb_model_get_state(sb_model_t m, int32_t tile, int32_t which, double* host);
+/* var_np1 of local tile i <- host [N_tile,V] (which must be 0).  Restart / host-driven stepping:
+ * the reference restarts from an output file the same way (physical_out_*.csv as the next
+ * initial_conditions, notebooks/Cha_Bell_WCD2024_initialization.ipynb:196). */
+int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* host);
+/* calcTendency for every local tile (src/semiimplicit.jl:728-735: physical[:,:,1] <- var_np1,
+ * spectralTransform!) followed by the own-block / halo assembly into the shared B buffer (:320-329).
+ * With sb_model_set_state + sb_model_exchange + sb_model_spline_transform this is the tile-parallel
+ * form of initialize_model's spectralTransform!(patch) (:135): the forward transform is additive
+ * across tiles, so no rank ever needs the whole patch in physical space. */
+int sb_model_tendency(sb_model_t m);
+/* one full iteration of model_loop entered at calcTendency (src/semiimplicit.jl:317-329, 279-285,
+ * then :305-314 of the next iteration): var_np1 -> K1 -> shared sum -> K2 -> K3 -> equation set ->
+ * var_np1.  Same work as sb_model_step; used for host-buffer (end-to-end) stepping. */
+int sb_model_cycle(sb_model_t m, int64_t t);
+/* per-kernel CUDA-event timing on the model's stream: enable/disable, then read
+ * "name launches total_ms\n" lines (clears the records). */
+int sb_model_profile(sb_model_t m, int32_t on);
+int sb_model_profile_report(sb_model_t m, char* buf, int64_t buflen);
 int sb_model_sync(sb_model_t m);
 /* number of kernels this model launched since creation (bench.py's gpu_launches) */
 int64_t sb_model_launch_count(sb_model_t m);

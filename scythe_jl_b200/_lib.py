@@ -80,6 +80,11 @@ PROTOTYPES = {
     "sb_model_run": (C.c_int, [model_t, C.c_int64, C.c_int64]),
     "sb_model_output": (C.c_int, [model_t, c_f64p]),
     "sb_model_get_state": (C.c_int, [model_t, C.c_int32, C.c_int32, c_f64p]),
+    "sb_model_set_state": (C.c_int, [model_t, C.c_int32, C.c_int32, c_f64p]),
+    "sb_model_tendency": (C.c_int, [model_t]),
+    "sb_model_cycle": (C.c_int, [model_t, C.c_int64]),
+    "sb_model_profile": (C.c_int, [model_t, C.c_int32]),
+    "sb_model_profile_report": (C.c_int, [model_t, C.c_char_p, C.c_int64]),
     "sb_model_sync": (C.c_int, [model_t]),
     "sb_model_launch_count": (C.c_int64, [model_t]),
     "sb_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -447,10 +447,7 @@ class Model:
             self.lib.check(self.lib.sb_model_step(self.handle, self.t))
             return
         self.lib.check(self.lib.sb_model_advance_tiles(self.handle, self.t))
-        if self.exchange == "native":
-            self.lib.check(self.lib.sb_model_exchange(self.handle))
-        else:
-            self.dist.all_reduce(self._shared_as_tensor())
+        self._exchange()
         self.lib.check(self.lib.sb_model_spline_transform(self.handle))
 
     def run(self, nsteps: int):
@@ -479,6 +476,59 @@ class Model:
         g = self.tiles[tile]
         out = np.empty((g.N, g.V), order="F")
         self.lib.check(self.lib.sb_model_get_state(self.handle, tile, idx, _ptr(out)))
+        return out
+
+    def set_state(self, tile: int, var_np1: np.ndarray):
+        """var_np1 of local tile <- host [N_tile, V] (restart / host-driven stepping)."""
+        g = self.tiles[tile]
+        a = var_np1 if (var_np1.flags.f_contiguous and var_np1.dtype == np.float64) else np.asfortranarray(var_np1, dtype=np.float64)
+        assert a.size == g.N * g.V
+        self.lib.check(self.lib.sb_model_set_state(self.handle, tile, 0, _ptr(a)))
+
+    def get_state_into(self, tile: int, out: np.ndarray):
+        self.lib.check(self.lib.sb_model_get_state(self.handle, tile, 0, _ptr(out)))
+
+    def _exchange(self):
+        if self.dist is None or self.world == 1:
+            return
+        if self.exchange == "native":
+            self.lib.check(self.lib.sb_model_exchange(self.handle))
+        else:
+            self.dist.all_reduce(self._shared_as_tensor())
+
+    def cycle(self):
+        """One model_loop iteration entered at calcTendency (see sb_model_cycle)."""
+        self.t += 1
+        if self.dist is None or self.world == 1 or self.exchange == "native":
+            self.lib.check(self.lib.sb_model_cycle(self.handle, self.t))
+            return
+        self.lib.check(self.lib.sb_model_tendency(self.handle))
+        self._exchange()
+        self.lib.check(self.lib.sb_model_spline_transform(self.handle))
+        raise NotImplementedError("physics half after a torch exchange: use step()")
+
+    def initialize_tiles(self, tile_ics):
+        """Tile-parallel initialize_model: each local tile gets its own slice of the initial state
+        ([N_tile, V]); K1 per tile, shared sum (all-reduce across ranks), K2.  Equivalent to
+        spectralTransform!(patch) because the forward transform is additive across tiles."""
+        assert len(tile_ics) == len(self.tiles)
+        for i, ic in enumerate(tile_ics):
+            self.set_state(i, ic)
+        self.lib.check(self.lib.sb_model_tendency(self.handle))
+        self._exchange()
+        self.lib.check(self.lib.sb_model_spline_transform(self.handle))
+        self.t = 0
+
+    def profile(self, on: bool):
+        self.lib.check(self.lib.sb_model_profile(self.handle, int(on)))
+
+    def profile_report(self) -> dict:
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.check(self.lib.sb_model_profile_report(self.handle, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = {"launches": int(n), "ms": float(ms)}
         return out
 
     def sync(self):

@@ -97,7 +97,8 @@ struct sb_grid {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int ndims = 1;
 
-  LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
+  Profiler prof;
+  LaunchCtx ctx() { return LaunchCtx{stream, &launches, &prof}; }
   template <class T> T* up(const std::vector<T>& h) { T* d = dev_upload(h); owned.push_back(d); return d; }
   long long slot_stride() const { return dg.N * dg.V; }
 
@@ -753,10 +754,9 @@ static void model_initialize(sb_model* M, const double* ic_host) {
   if ((size_t)P->dg.N * P->dg.V * P->dg.D * sizeof(double) > ((size_t)4 << 30)) P->release_physical();
 }
 
-static void model_advance_tiles(sb_model* M, int64_t t) {
+// first half of advanceTimestep: tileTransform! + equation set + explicit/semi-implicit step
+static void tiles_physics(sb_model* M, int64_t t) {
   sb_grid* P = M->patch;
-  CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
-  sb_grid* prev = nullptr;
   for (auto& T : M->tiles) {
     sb_grid* G = T.grid;
     grid_inverse(P, G);                                     // tileTransform!  :305
@@ -769,11 +769,26 @@ static void model_advance_tiles(sb_model* M, int64_t t) {
     // history rotation (:685-695): nm2 <- nm1 <- n ; the old nm2 buffer becomes next step's n
     std::rotate(T.expd, T.expd + 2, T.expd + 3);
     if (M->semiimplicit) std::rotate(T.impd, T.impd + 2, T.impd + 3);
+  }
+}
+
+// second half: calcTendency (K1) + own block / halo into the shared B buffer
+static void tiles_tendency(sb_model* M) {
+  sb_grid* P = M->patch;
+  CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
+  sb_grid* prev = nullptr;
+  for (auto& T : M->tiles) {
+    sb_grid* G = T.grid;
     grid_forward(G, T.var_np1, G->physical);                // calcTendency    :728-735
     launch_assemble(G->ctx(), P->dg, G->dg, G->spectralB, prev ? &prev->dg : nullptr, prev ? prev->spectralB : nullptr, 0,
                     P->spectralB);                         // :320-329
     prev = G;
   }
+}
+
+static void model_advance_tiles(sb_model* M, int64_t t) {
+  tiles_physics(M, t);
+  tiles_tendency(M);
 }
 
 static void model_exchange(sb_model* M) {
@@ -991,6 +1006,60 @@ int sb_model_get_state(sb_model_t m, int32_t tile, int32_t which, double* host) 
     if (!src) throw std::invalid_argument("state array not allocated (semi-implicit off)");
     CU(cudaMemcpyAsync(host, src, (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
+  });
+}
+int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* host) {
+  return guarded([&] {
+    if (!m || !host || tile < 0 || tile >= (int)m->tiles.size() || which != 0) throw std::invalid_argument("bad argument");
+    TileState& T = m->tiles[tile];
+    CU(cudaMemcpyAsync(T.var_np1, host, (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  });
+}
+int sb_model_tendency(sb_model_t m) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); tiles_tendency(m); });
+}
+int sb_model_cycle(sb_model_t m, int64_t t) {
+  try {
+    if (!m || t < 1) return fail(SB_EINVAL, "bad argument");
+    tiles_tendency(m);
+    model_exchange(m);
+    grid_spline(m->patch, m->patch->spectralB);
+    tiles_physics(m, t);
+    return SB_OK;
+  } catch (const CommError& e) { return fail(SB_ECOMM, e.what());
+  } catch (const std::exception& e) { return fail(SB_ECUDA, e.what()); }
+}
+int sb_model_profile(sb_model_t m, int32_t on) {
+  return guarded([&] {
+    if (!m) throw std::invalid_argument("NULL model");
+    m->patch->prof.on = on != 0;
+    for (auto& t : m->tiles) t.grid->prof.on = on != 0;
+  });
+}
+int sb_model_profile_report(sb_model_t m, char* buf, int64_t buflen) {
+  return guarded([&] {
+    if (!m || !buf || buflen < 2) throw std::invalid_argument("bad argument");
+    CU(cudaStreamSynchronize(m->stream));
+    std::map<std::string, std::pair<long long, double>> acc;
+    auto drain = [&](sb_grid* g) {
+      for (auto& r : g->prof.recs) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = acc[r.name];
+        e.first += 1;
+        e.second += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+      }
+      g->prof.recs.clear();
+    };
+    drain(m->patch);
+    for (auto& t : m->tiles) drain(t.grid);
+    std::string s;
+    for (auto& kv : acc) s += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+    if ((int64_t)s.size() + 1 > buflen) s.resize((size_t)buflen - 1);
+    std::memcpy(buf, s.c_str(), s.size() + 1);
   });
 }
 int sb_model_sync(sb_model_t m) {

@@ -78,7 +78,27 @@ struct ZTile { int hcol0; int ncols; long long out_base; int out_stride; int pad
 struct LWork { int r; int row0; int nrows; int pad; };
 
 // ---------------------------------------------------------------- kernel launchers (sb_transforms.cu)
-struct LaunchCtx { cudaStream_t stream; long long* launches; };
+// per-launch CUDA-event timing on the launching stream (bench.py's live roofline numbers)
+struct Profiler {
+  bool on = false;
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+};
+struct LaunchCtx { cudaStream_t stream; long long* launches; Profiler* prof; };
+struct ProfScope {
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  ProfScope(const LaunchCtx& c, const char* name) : s(c.stream) {
+    if (c.prof && c.prof->on) {
+      cudaEvent_t a;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+      c.prof->recs.push_back(Profiler::Rec{name, a, b});
+    }
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, s); }
+};
 
 void launch_fwd_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars,
                   const double* in, long long in_vstride, double* mirror, long long mirror_vstride,

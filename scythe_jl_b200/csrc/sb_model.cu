@@ -356,6 +356,7 @@ static void launch_pw(const LaunchCtx& c, const DevGrid& g, const EqParams& p, c
 
 void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p, const ModelArrays& a,
                          int tstep) {
+  ProfScope prof_scope_(c, "equation_set");
   switch (eq) {
     case EQ_LinearAdvection1D: launch_pw<EQ_LinearAdvection1D>(c, g, p, a, tstep); break;
     case EQ_LinearAdvectionRZ: launch_pw<EQ_LinearAdvectionRZ>(c, g, p, a, tstep); break;

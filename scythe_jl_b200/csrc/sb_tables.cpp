@@ -204,10 +204,11 @@ bool lu_factor(std::vector<double>& A, std::vector<int>& piv, int n) {
 }
 
 void lu_solve(const std::vector<double>& LU, const std::vector<int>& piv, int n, double* b) {
-  for (int c = 0; c < n; ++c) {
+  // full rows (incl. the L part) were swapped during factorisation: permute b first, then solve
+  for (int c = 0; c < n; ++c)
     if (piv[c] != c) std::swap(b[c], b[piv[c]]);
+  for (int c = 0; c < n; ++c)
     for (int r = c + 1; r < n; ++r) b[r] -= LU[(size_t)r * n + c] * b[c];
-  }
   for (int r = n - 1; r >= 0; --r) {
     double s = b[r];
     for (int k = r + 1; k < n; ++k) s -= LU[(size_t)r * n + k] * b[k];

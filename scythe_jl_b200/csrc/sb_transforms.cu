@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(512) k_fwd_z(DevGrid g, const ZTile* __restric
 void launch_fwd_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars,
                   const double* in, long long in_vstride, double* mirror, long long mirror_vstride,
                   double* out, long long out_vstride, const double* fwdT) {
+  ProfScope prof_scope_(c, "fwd_z");
   int ngroups = g.bzp / 4;
   int nwarps = ngroups < 16 ? ngroups : 16;
   if (nwarps < 1) nwarps = 1;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(512) k_inv_z(DevGrid g, const ZTile* __restric
 void launch_inv_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
                   int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
                   const double* invM) {
+  ProfScope prof_scope_(c, "inv_z");
   int zp = (g.zDim + 3) & ~3;
   int ngroups = zp / 4;
   int nwarps = ngroups < 16 ? ngroups : 16;
@@ -368,6 +370,7 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   const LWork* const* work, const std::vector<FftClass>& classes, const double* const* tw,
                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vstride,
                   int /*in_is_z*/, double* mirror, long long mirror_vstride, double* out, long long out_vstride) {
+  ProfScope prof_scope_(c, "fwd_l");
   for (size_t ci = 0; ci < classes.size(); ++ci) {
     int nwork = (int)hostwork[ci].size();
     if (!nwork) continue;
@@ -472,6 +475,7 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fstride,
                   long long in_vstride, double* out, long long out_fstride, long long out_vstride,
                   int out_is_phys, int var0) {
+  ProfScope prof_scope_(c, "inv_l");
   for (size_t ci = 0; ci < classes.size(); ++ci) {
     int nwork = (int)hostwork[ci].size();
     if (!nwork) continue;
@@ -539,6 +543,7 @@ __global__ void __launch_bounds__(RQ) k_fwd_r(DevGrid g, const double* __restric
 
 void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride, double* B,
                   long long B_vstride) {
+  ProfScope prof_scope_(c, "fwd_r");
   dim3 grid((g.ncolp + RQ - 1) / RQ, g.bz, nvars);
   SB_LAUNCH(k_fwd_r, grid, dim3(RQ), 0, c.stream, g, in, in_vstride, B, B_vstride);
   SB_CHECK_LAUNCH();
@@ -601,6 +606,7 @@ __global__ void __launch_bounds__(RQ) k_inv_r(DevGrid t, DevGrid p, const double
 void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch, int nvars, const double* A,
                   long long A_vstride, double* out, long long out_fstride, long long out_vstride, int out_is_phys,
                   int var0) {
+  ProfScope prof_scope_(c, "inv_r");
   dim3 grid((tile.ncolp + RQ - 1) / RQ, tile.bz, nvars);
   SB_LAUNCH(k_inv_r, grid, dim3(RQ), 0, c.stream, tile, patch, A, A_vstride, out, out_fstride, out_vstride,
             out_is_phys, var0);
@@ -685,6 +691,7 @@ __global__ void k_spline_dense(DevSplineFactor f, int ncols, const double* __res
 
 void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFactor* /*dfactors*/,
                          const std::vector<DevSplineFactor>& hf, const double* B, double* A) {
+  ProfScope prof_scope_(c, "spline_solve");
   const int ncols = g.bz * g.ncolp;
   for (int v = 0; v < g.V; ++v) {
     const DevSplineFactor& f = hf[v];
@@ -729,6 +736,7 @@ __global__ void k_assemble(DevGrid p, DevGrid t, const double* __restrict__ tile
 
 void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* tileB,
                      const DevGrid* prev, const double* prevB, int /*last*/, double* shared) {
+  ProfScope prof_scope_(c, "assemble");
   long long tot = tile.S * tile.V;
   SB_LAUNCH(k_assemble, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, c.stream, patch, tile, tileB,
             prev ? 1 : 0, prev ? *prev : tile, prevB, shared);
@@ -742,6 +750,7 @@ __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src,
 }
 
 void launch_copy(const LaunchCtx& c, double* dst, const double* src, long long n) {
+  ProfScope prof_scope_(c, "copy");
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
@@ -770,6 +779,7 @@ __global__ void k_nan_scan(const double* __restrict__ phys, long long total, lon
 }
 
 void launch_nan_scan(const LaunchCtx& c, const double* phys, long long N, int V, long long* result) {
+  ProfScope prof_scope_(c, "nan_scan");
   long long total = N * V;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;

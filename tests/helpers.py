@@ -1,0 +1,210 @@
+"""Shared builders for the parity tests: identical seeded inputs for the oracle and the CUDA path."""
+from __future__ import annotations
+
+import numpy as np
+
+import scythe_jl_b200 as S
+from oracle import chebyshev as ch
+from oracle import grids as G
+from oracle import model as M
+from oracle import splines as spl
+
+TRANSFORM_TOL = 1e-12   # BASELINE.json north_star: transform round-trip <= 1e-12 (relative)
+STATE_TOL = 1e-9        # N-step state <= 1e-9 (relative)
+
+
+def to_pkg(gp: G.GridParameters) -> S.GridParameters:
+    names = gp.var_names()
+    sb = lambda d: {n: getattr(S.CubicBSpline, spl.bc_name(gp.var_bc(d, n))) for n in names}  # noqa: E731
+    cb = lambda d: {n: getattr(S.Chebyshev, ch.bc_name(gp.var_bc(d, n))) for n in names}  # noqa: E731
+    return S.GridParameters(geometry=gp.geometry, xmin=gp.xmin, xmax=gp.xmax, num_cells=gp.num_cells, l_q=gp.l_q,
+                            BCL=sb("BCL"), BCR=sb("BCR"), zmin=gp.zmin, zmax=gp.zmax, zDim=gp.zDim, b_zDim=gp.b_zDim,
+                            BCB=cb("BCB"), BCT=cb("BCT"), vars=dict(gp.vars), spectralIndexL=gp.spectralIndexL)
+
+
+def rel_err(a: np.ndarray, b: np.ndarray) -> float:
+    """max |a-b| / max |b| over the whole array (slots that are identically ~0 must be compared
+    against the scale of the full field, so callers pass whole [N,V] slots of non-trivial data)."""
+    s = float(np.abs(b).max())
+    return float(np.abs(a - b).max()) / (s if s > 0 else 1.0)
+
+
+def slot_errs(a: np.ndarray, b: np.ndarray) -> list[float]:
+    return [rel_err(a[:, :, d], b[:, :, d]) for d in range(b.shape[2])]
+
+
+# ------------------------------------------------------------------ transform cases
+def transform_cases():
+    B = spl
+    return {
+        "R_periodic": G.GridParameters(geometry="R", xmin=-50, xmax=50, num_cells=40, BCL={"u": B.PERIODIC},
+                                       BCR={"u": B.PERIODIC}, vars={"u": 1}),
+        "R_mixed_bcs": G.GridParameters(geometry="R", xmin=0, xmax=10, num_cells=17,
+                                        BCL={"a": B.R0, "b": B.R1T0, "c": B.R1T2, "d": B.R2T10, "e": B.R3},
+                                        BCR={"a": B.R1T1, "b": B.R2T20, "c": B.R0, "d": B.R1T0, "e": B.R3},
+                                        vars={"a": 1, "b": 2, "c": 3, "d": 4, "e": 5}),
+        "RL": G.GridParameters(geometry="RL", xmin=0, xmax=10, num_cells=6, BCL={"h": B.R1T1, "u": B.R1T0},
+                               BCR={"h": B.R0, "u": B.R1T1}, vars={"h": 1, "u": 2}),
+        "RL_tile": G.GridParameters(geometry="RL", xmin=3, xmax=7, num_cells=4, vars={"h": 1}, spectralIndexL=4),
+        "RZ": G.GridParameters(geometry="RZ", xmin=0, xmax=10, num_cells=7, zmin=0, zmax=5, zDim=12,
+                               BCL={"s": B.R1T1, "w": B.R2T10}, BCR={"s": B.R3, "w": B.R1T2},
+                               BCB={"s": ch.R0, "w": ch.R1T0}, BCT={"s": ch.R0, "w": ch.R1T0}, vars={"s": 1, "w": 2}),
+        "RLZ": G.GridParameters(geometry="RLZ", xmin=0, xmax=10, num_cells=4, zmin=0, zmax=5, zDim=10,
+                                BCL={"h": B.R1T1, "u": B.R1T0}, BCR={"h": B.R0, "u": B.R2T20},
+                                BCB={"h": ch.R0, "u": ch.R1T1}, BCT={"h": ch.R0, "u": ch.R1T2},
+                                vars={"h": 1, "u": 2}),
+    }
+
+
+def check_transforms(gp: G.GridParameters, lib, seed=0):
+    """spectralTransform! and gridTransform! of seeded random data: CUDA path vs oracle."""
+    og = G.createGrid(gp)
+    g = S.createGrid(to_pkg(gp), lib=lib)
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal((og.N, og.V))
+    og.physical[:, :, 0] = u
+    g.physical[:, :, 0] = u
+    pts = S.getGridpoints(g)
+    assert np.abs(pts.reshape(og.N, -1) - og.getGridpoints().reshape(og.N, -1)).max() < 1e-12 * max(1.0, abs(gp.xmax))
+    og.spectralTransform()
+    S.spectralTransform(g)
+    eB = rel_err(g.spectral, og.spectral)
+    og.gridTransform()
+    S.gridTransform(g)
+    eP = slot_errs(g.physical, og.physical)
+    g.close()
+    return eB, eP
+
+
+# ------------------------------------------------------------------ model cases
+def _slab_case(nc=6):
+    names = ["h", "u", "v", "ub", "vb", "wb"]
+    BCL = {"h": spl.R1T1, "u": spl.R1T0, "v": spl.R1T0, "ub": spl.R1T0, "vb": spl.R1T0, "wb": spl.R1T1}
+    BCR = {"h": spl.R0, "u": spl.R1T1, "v": spl.R0, "ub": spl.R1T1, "vb": spl.R0, "wb": spl.R0}
+    gp = G.GridParameters(geometry="RL", xmin=0, xmax=3e5, num_cells=nc, BCL=BCL, BCR=BCR,
+                          vars={n: i + 1 for i, n in enumerate(names)})
+    r, l = G.createGrid(gp).getGridpoints().T
+    Rmax, V0 = 5e4, 50.0 / 5e4
+    vbar = np.where(r < Rmax, V0 * r, Rmax * Rmax * V0 / r)
+    ic = np.zeros((r.size, 6))
+    ic[:, 2] = vbar * (1 + 0.05 * np.cos(2 * l))
+    ic[:, 4] = vbar
+    ic[:, 3] = -0.1 * vbar
+    ic[:, 0] = 100 * np.exp(-(r / 1e5) ** 2)
+    prm = dict(g=9.81, K=5000.0, Cd=2.4e-3, Hfree=2000.0, Hb=1000.0, f=5e-5, S1=1e-5)
+    return gp, ic, prm
+
+
+def model_cases(small=True):
+    cases = {}
+    gp = G.GridParameters(geometry="R", xmin=-50, xmax=50, num_cells=30, BCL={"u": spl.PERIODIC},
+                          BCR={"u": spl.PERIODIC}, vars={"u": 1})
+    x = G.createGrid(gp).getGridpoints()
+    cases["LinearAdvection1D"] = dict(gp=gp, eq="LinearAdvection1D", prm={"c_0": 1.0, "K": 0.01}, ts=0.05, n=8,
+                                      ic=np.exp(-(x / 20) ** 2)[:, None], tiles=(1, 3))
+    gp = G.GridParameters(geometry="R", xmin=0, xmax=100, num_cells=24, BCL={"h": spl.R1T1, "u": spl.R1T0},
+                          BCR={"h": spl.R1T1, "u": spl.R1T0}, vars={"h": 1, "u": 2})
+    x = G.createGrid(gp).getGridpoints()
+    cases["LinearShallowWater1D"] = dict(gp=gp, eq="LinearShallowWater1D", prm={"g": 9.81, "K": 0.5, "H": 10.0}, ts=0.02,
+                                         n=5, ic=np.stack([np.exp(-((x - 50) / 10) ** 2), 0 * x], 1), tiles=(2,))
+    gp, ic, prm = _slab_case(6)
+    cases["Oneway_ShallowWater_Slab"] = dict(gp=gp, eq="Oneway_ShallowWater_Slab", prm=prm, ts=3.0, n=4, ic=ic, tiles=(1, 2))
+    cases["Twoway_ShallowWater_Slab"] = dict(gp=gp, eq="Twoway_ShallowWater_Slab", prm=prm, ts=3.0, n=3, ic=ic, tiles=(2,))
+    gp3 = G.GridParameters(geometry="RL", xmin=0, xmax=1e5, num_cells=6, vars={"h": 1, "u": 2, "v": 3})
+    r, l = G.createGrid(gp3).getGridpoints().T
+    ic3 = np.zeros((r.size, 3))
+    ic3[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8)
+    ic3[:, 1] = 5 * np.cos(l)
+    ic3[:, 2] = -5 * np.sin(l)
+    cases["LinearAdvectionRL_K0"] = dict(gp=gp3, eq="LinearAdvectionRL", prm={"K": 0.0}, ts=50.0, n=3, ic=ic3, tiles=(2,))
+    cases["LinearAdvectionRL"] = dict(gp=gp3, eq="LinearAdvectionRL", prm={"K": 100.0}, ts=50.0, n=3, ic=ic3, tiles=(1,))
+    cases["LinearShallowWaterRL"] = dict(gp=gp3, eq="LinearShallowWaterRL", prm={"K": 100.0, "g": 9.81, "H": 1000.0},
+                                         ts=5.0, n=3, ic=ic3, tiles=(2,))
+    gp = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=6, zmin=0, zmax=1e3, zDim=10,
+                          vars={"h": 1, "u": 2, "v": 3})
+    r, l, z = G.createGrid(gp).getGridpoints().T
+    ic = np.zeros((r.size, 3))
+    ic[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * np.cos(z / 400.0)
+    ic[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
+    ic[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
+    cases["LinearAdvectionRLZ"] = dict(gp=gp, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=3, ic=ic, tiles=(1, 2))
+    gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e5, num_cells=9, zmin=0, zmax=1e4, zDim=12,
+                          vars={"h": 1, "u": 2, "x": 3, "w": 4})
+    r, z = G.createGrid(gp).getGridpoints().T
+    ic = np.zeros((r.size, 4))
+    ic[:, 0] = np.exp(-((r - 5e4) ** 2 / 4e8 + (z - 5e3) ** 2 / 4e6))
+    ic[:, 1] = 5.0 * np.cos(z / 4e3)
+    ic[:, 2] = np.sin(r / 2e4) * np.cos(z / 3e3)
+    ic[:, 3] = 0.5 * np.sin(r / 3e4 + z / 5e3)
+    cases["LinearAdvectionRZ"] = dict(gp=gp, eq="LinearAdvectionRZ", prm={"K": 10.0}, ts=20.0, n=3, ic=ic, tiles=(1, 3))
+    names = ["h", "u", "v", "ub", "vb", "wb"]
+    gp = G.GridParameters(geometry="RLZ", xmin=0, xmax=2e5, num_cells=6, zmin=0, zmax=2e3, zDim=10,
+                          vars={n: i + 1 for i, n in enumerate(names)},
+                          BCL={"h": spl.R1T1, "u": spl.R1T0, "v": spl.R1T0, "ub": spl.R1T0, "vb": spl.R1T0, "wb": spl.R1T1})
+    r, l, z = G.createGrid(gp).getGridpoints().T
+    Rmax, V0 = 5e4, 30.0 / 5e4
+    vbar = np.where(r < Rmax, V0 * r, Rmax * Rmax * V0 / r)
+    ic = np.zeros((r.size, 6))
+    ic[:, 0] = 50 * np.exp(-(r / 1e5) ** 2) * (1 + 0.1 * np.cos(l))
+    ic[:, 1] = 0.05 * vbar * np.sin(l)
+    ic[:, 2] = vbar
+    ic[:, 3] = -0.2 * vbar * np.exp(-z / 500)
+    ic[:, 4] = vbar * (1 - np.exp(-(z + 50) / 300))
+    cases["Oneway_ShallowWater_HeightResolvedBL"] = dict(
+        gp=gp, eq="Oneway_ShallowWater_HeightResolvedBL",
+        prm=dict(g=9.81, Kh=1500.0, Cd=2.4e-3, Hfree=2000.0, f=5e-5, Um=3.0, Vm=-2.0), ts=2.0, n=3, ic=ic, tiles=(1, 2))
+    gp = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=8, zmin=0, zmax=1e4, zDim=16,
+                          vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5})
+    zc = ch.mish_points(ch.ChebyshevParameters(0, 1e4, 16, 11))
+    T = 280.0
+    rho = (1000e2 / (T * M.Rd)) * np.exp(-M.gravity * zc / (M.Rd * T))
+    xibar = np.log(rho / M.rho_d0)
+    sbar = M.Cvd * np.log(T / M.T_0) - M.Rd * np.log(rho / M.rho_d0)
+    mubar = 2e-3 * np.exp(-zc / 3e3) - 5e-4   # moist below, dry (mu<0) aloft: both ahyp branches
+    ref = M.exact_reference_state_from_profiles(gp, sbar, xibar, mubar, mubar)
+    x, z = G.createGrid(gp).getGridpoints().T
+    ic = np.zeros((x.size, 5))
+    ic[:, 0] = 2.0 * np.exp(-((x) ** 2 + (z - 3e3) ** 2) / 2e3 ** 2)
+    ic[:, 2] = 1e-4 * np.exp(-((x - 2e3) ** 2 + (z - 2e3) ** 2) / 2e3 ** 2)
+    ic[:, 3] = 1.0 * np.sin(z / 2e3)
+    cases["Euler_test_explicit"] = dict(gp=gp, eq="Euler_test", prm={"K": 50.0}, ts=0.05, n=3, ic=ic, tiles=(1,), ref=ref)
+    cases["Euler_test_semiimplicit"] = dict(gp=gp, eq="Euler_test", prm={"K": 50.0}, ts=1.0, n=4, ic=ic, tiles=(1, 2),
+                                            ref=ref, opts={"semiimplicit": True, "exact_reference_state": True})
+    return cases
+
+
+def run_oracle(case, ntiles=1):
+    opts = case.get("opts", {"semiimplicit": False})
+    mp = M.ModelParameters(ts=case["ts"], integration_time=case["ts"] * case["n"], equation_set=case["eq"],
+                           grid_params=case["gp"], physical_params=case["prm"], options=opts)
+    run = M.ModelRun(mp, ntiles, case["ic"], case.get("ref"))
+    run.run(case["n"])
+    return run
+
+
+def pkg_model(case, ntiles, lib, **kw):
+    opts = case.get("opts", {"semiimplicit": False})
+    mp = S.ModelParameters(ts=case["ts"], integration_time=case["ts"] * case["n"], equation_set=case["eq"],
+                           grid_params=to_pkg(case["gp"]), physical_params=case["prm"], options=opts)
+    ref = case.get("ref")
+    sref = S.ReferenceState(ref.sbar, ref.xibar, ref.mubar, ref.mu_lbar, ref.Pxi_bar) if ref is not None else None
+    return S.Model(mp, num_tiles=ntiles, ref_state=sref, lib=lib, **kw)
+
+
+def check_model(case, lib):
+    """N steps on `tiles` tiles: final tile state (var_np1, expdot history) vs the oracle."""
+    errs = []
+    for nt in case["tiles"]:
+        orun = run_oracle(case, nt)
+        m = pkg_model(case, nt, lib)
+        m.initialize(case["ic"])
+        m.run(case["n"])
+        for i, mt in enumerate(orun.mtiles):
+            errs.append(rel_err(m.state(i, "var_np1"), mt.var_np1))
+            errs.append(rel_err(m.state(i, "expdot_nm1"), mt.expdot_nm1))
+        out = m.output()
+        oout = orun.output_patch()
+        errs.append(rel_err(out[:, :, 0], oout[:, :, 0]))   # state
+        errs.append(rel_err(out[:, :, 1], oout[:, :, 1]))   # radial derivative
+        m.close()
+    return max(errs)

@@ -1,0 +1,144 @@
+"""GPU parity tests (-m gpu): the product library through the C ABI vs the oracle, on the same
+seeded inputs; plus size-independent properties at sizes the oracle cannot cover quickly."""
+import numpy as np
+import pytest
+
+import scythe_jl_b200 as S
+from helpers import (STATE_TOL, TRANSFORM_TOL, check_model, check_transforms, model_cases, pkg_model, rel_err,
+                     slot_errs, to_pkg, transform_cases)
+from oracle import grids as G
+from oracle import splines as spl
+
+pytestmark = pytest.mark.gpu
+T_CASES = transform_cases()
+M_CASES = model_cases()
+
+
+def test_native_library_is_the_product_build(gpu_lib):
+    assert b"sm_100a" in gpu_lib.sb_version()
+    assert gpu_lib.path.name == "libscythe_b200.so"
+
+
+@pytest.mark.parametrize("name", sorted(T_CASES))
+def test_transforms_match_oracle(name, gpu_lib):
+    eB, eP = check_transforms(T_CASES[name], gpu_lib)
+    assert eB <= TRANSFORM_TOL, f"spectralTransform rel err {eB}"
+    assert max(eP) <= TRANSFORM_TOL, f"gridTransform rel err per slot {eP}"
+
+
+@pytest.mark.parametrize("name", sorted(M_CASES))
+def test_timestep_matches_oracle(name, gpu_lib):
+    assert check_model(M_CASES[name], gpu_lib) <= STATE_TOL
+
+
+def test_cha_bell_rl_config_transforms(gpu_lib):
+    """C2: RL, 100 cells, 6 variables with the Cha & Bell (2024) boundary conditions
+    (/root/reference/models/cha_bell2024/Oneway_ShallowWater_Slab.jl:9-33), rings 8..1204."""
+    names = ["h", "u", "v", "ub", "vb", "wb"]
+    BCL = {"h": spl.R1T1, "u": spl.R1T0, "v": spl.R1T0, "ub": spl.R1T0, "vb": spl.R1T0, "wb": spl.R1T1}
+    BCR = {"h": spl.R0, "u": spl.R1T1, "v": spl.R0, "ub": spl.R1T1, "vb": spl.R0, "wb": spl.R0}
+    gp = G.GridParameters(geometry="RL", xmin=0, xmax=3e5, num_cells=100, BCL=BCL, BCR=BCR,
+                          vars={n: i + 1 for i, n in enumerate(names)})
+    eB, eP = check_transforms(gp, gpu_lib, seed=3)
+    assert eB <= TRANSFORM_TOL and max(eP) <= TRANSFORM_TOL, (eB, eP)
+
+
+def test_rlz_64_levels_transforms(gpu_lib):
+    """RLZ with the north-star vertical resolution (64 levels -> 43 modes), 20 cells (rings 8..244)."""
+    gp = G.GridParameters(geometry="RLZ", xmin=0, xmax=6e4, num_cells=20, zmin=0, zmax=1.5e4, zDim=64,
+                          BCL={"h": spl.R1T1, "u": spl.R1T0}, vars={"h": 1, "u": 2})
+    eB, eP = check_transforms(gp, gpu_lib, seed=5)
+    assert eB <= TRANSFORM_TOL and max(eP) <= TRANSFORM_TOL, (eB, eP)
+
+
+def test_rz_north_star_config(gpu_lib):
+    """C3: RZ 334 cells x 64 levels, 5 variables."""
+    gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e6, num_cells=334, zmin=0, zmax=2e4, zDim=64,
+                          vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5})
+    eB, eP = check_transforms(gp, gpu_lib, seed=7)
+    assert eB <= TRANSFORM_TOL and max(eP) <= TRANSFORM_TOL, (eB, eP)
+
+
+def test_tiles_equal_single_tile_and_oracle_on_larger_rl(gpu_lib):
+    """N-tile == 1-tile (overlap-add of the 3 seam coefficients) at a size with uneven tiles."""
+    case = dict(M_CASES["Oneway_ShallowWater_Slab"])
+    from helpers import _slab_case
+    gp, ic, prm = _slab_case(24)
+    case.update(gp=gp, ic=ic, prm=prm, n=5)
+    outs = {}
+    for nt in (1, 4, 8):
+        m = pkg_model(case, nt, gpu_lib)
+        m.initialize(ic)
+        m.run(case["n"])
+        outs[nt] = m.output()
+        m.close()
+    for nt in (4, 8):
+        assert max(slot_errs(outs[nt], outs[1])) <= 1e-11
+    from helpers import run_oracle
+    oout = run_oracle(case, 1).output_patch()
+    assert max(slot_errs(outs[1], oout)) <= STATE_TOL
+
+
+def test_full_size_ring_ffts_pure_mode_property(gpu_lib):
+    """Every ring size up to the north-star 4012-point ring (all 1002 Bluestein plans):
+    for u = f(r) cos(k lambda + a) the transform pair must give  u_ll = -k^2 u  and  u_l = d/dlambda u
+    at every point, and spectral energy only in wavenumber k, independent of the radial filter."""
+    gp = S.GridParameters(geometry="RL", xmin=0, xmax=1e6, num_cells=334, vars={"u": 1})
+    g = S.createGrid(gp, lib=gpu_lib)
+    r, l = S.getGridpoints(g).T
+    k = 3
+    f = np.exp(-((r - 4e5) / 2e5) ** 2)
+    g.physical[:, 0, 0] = f * np.cos(k * l + 0.3)
+    S.spectralTransform(g)
+    spec = g.spectral[:, 0].reshape(-1, g.b_rDim)      # [1+2kDim, b_rDim]
+    keep = np.abs(spec).max()
+    other = np.delete(spec, [2 * k - 1, 2 * k], axis=0)
+    assert np.abs(other).max() <= 1e-13 * keep
+    S.gridTransform(g)
+    u, ul, ull = g.physical[:, 0, 0], g.physical[:, 0, 3], g.physical[:, 0, 4]
+    ring_id = np.repeat(np.arange(g.rDim), 4 + 4 * (np.arange(g.rDim) + 1))
+    sel = (ring_id + 1) >= k                           # rings that carry wavenumber k
+    scale = np.abs(u).max()
+    assert np.abs(ull + k * k * u)[sel].max() <= 1e-11 * k * k * scale
+    # u = A(r) cos(k l + 0.3)  ->  u_l^2 + k^2 u^2 = k^2 A^2 is constant on each ring
+    amp2 = (ul ** 2 + (k * u) ** 2)
+    mx = np.maximum.reduceat(amp2, np.r_[0, np.cumsum(4 + 4 * (np.arange(g.rDim) + 1))[:-1]])
+    mn = np.minimum.reduceat(amp2, np.r_[0, np.cumsum(4 + 4 * (np.arange(g.rDim) + 1))[:-1]])
+    rsel = np.arange(g.rDim) + 1 >= k
+    assert ((mx - mn)[rsel]).max() <= 1e-10 * (k * scale) ** 2
+    g.close()
+
+
+def test_linearity_rlz(gpu_lib):
+    gp = S.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=30, zmin=0, zmax=1e4, zDim=64, vars={"a": 1, "b": 2, "c": 3})
+    g = S.createGrid(gp, lib=gpu_lib)
+    rng = np.random.default_rng(11)
+    x, y = rng.standard_normal((2, g.N))
+    g.physical[:, 0, 0], g.physical[:, 1, 0], g.physical[:, 2, 0] = x, y, 2.5 * x - 0.75 * y
+    S.spectralTransform(g)
+    sp = g.spectral
+    assert rel_err(sp[:, 2], 2.5 * sp[:, 0] - 0.75 * sp[:, 1]) <= 1e-13
+    S.gridTransform(g)
+    ph = g.physical
+    for d in range(g.D):
+        assert rel_err(ph[:, 2, d], 2.5 * ph[:, 0, d] - 0.75 * ph[:, 1, d]) <= 1e-12
+    g.close()
+
+
+def test_error_behaviour(gpu_lib):
+    with pytest.raises(S.DomainError):
+        S.createGrid(S.GridParameters(geometry="XYZ", xmin=0, xmax=1, num_cells=4), lib=gpu_lib)
+    with pytest.raises(S.DomainError):
+        S.calcTileSizes(S.GridParameters(geometry="R", xmin=0, xmax=1, num_cells=8), 3, lib=gpu_lib)
+    mp = S.ModelParameters(ts=1.0, equation_set="Kepert2017_TCBL",
+                           grid_params=S.GridParameters(geometry="R", xmin=0, xmax=1, num_cells=8))
+    with pytest.raises(S.UnsupportedError):
+        S.Model(mp, lib=gpu_lib)
+    # checkCFL: NaN -> error naming the variable and the 1-based index (src/semiimplicit.jl:745)
+    g = S.createGrid(S.GridParameters(geometry="R", xmin=0, xmax=1, num_cells=8, vars={"u": 1, "q": 2}), lib=gpu_lib)
+    g.physical[:] = 0.0
+    g.physical[5, 1, 0] = np.nan
+    g.upload_physical(0, 1)
+    with pytest.raises(S.ScytheError, match="NaN found in variable q at index6"):
+        S.checkCFL(g)
+    g.close()

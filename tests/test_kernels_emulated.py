@@ -1,0 +1,27 @@
+"""CPU (-m "not gpu") check of the *kernel sources* themselves: the .cu files are compiled for the
+host against the test-only thread emulation shim (csrc/cuda_emu.h) and compared with the oracle.
+This catches indexing / maths errors before GPU time is spent; the GPU parity tests proper are in
+test_gpu_parity.py.  The emulated library is never reachable from the product package."""
+import pytest
+
+from helpers import STATE_TOL, TRANSFORM_TOL, check_model, check_transforms, model_cases, transform_cases
+
+T_CASES = transform_cases()
+M_CASES = model_cases()
+FAST_MODELS = ["LinearAdvection1D", "LinearShallowWater1D", "LinearAdvectionRL_K0", "LinearAdvectionRZ",
+               "Euler_test_semiimplicit", "LinearAdvectionRLZ"]
+
+
+@pytest.mark.parametrize("name", sorted(T_CASES))
+def test_transforms_match_oracle(name, emu_lib):
+    eB, eP = check_transforms(T_CASES[name], emu_lib)
+    assert eB <= TRANSFORM_TOL, f"spectralTransform rel err {eB}"
+    assert max(eP) <= TRANSFORM_TOL, f"gridTransform rel err per slot {eP}"
+
+
+@pytest.mark.parametrize("name", FAST_MODELS)
+def test_timestep_matches_oracle(name, emu_lib):
+    case = dict(M_CASES[name])
+    case["tiles"] = case["tiles"][-1:]   # the multi-tile variant only (CPU time)
+    case["n"] = min(case["n"], 3)
+    assert check_model(case, emu_lib) <= STATE_TOL
