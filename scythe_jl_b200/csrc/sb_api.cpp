@@ -126,7 +126,7 @@ struct sb_grid {
     vchunk = dg.V;
     if (env && std::atoi(env) > 0) vchunk = std::min(dg.V, std::atoi(env));
     else if (per_v * dg.V * 8 > (4LL << 30)) vchunk = 1;
-    scratch_doubles = std::max<long long>(per_v * vchunk, 1);
+    scratch_doubles = std::max<long long>(per_v * vchunk, 1) + 16;   // + alignment slack of the SZ region
     CU(cudaMalloc((void**)&scratch, (size_t)scratch_doubles * sizeof(double)));
   }
 };
@@ -310,7 +310,7 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
   for (int v0 = 0; v0 < d.V; v0 += G->vchunk) {
     const int nv = std::min(G->vchunk, d.V - v0);
     double* SL = G->scratch;
-    double* SZ = G->scratch + slN * G->vchunk;
+    double* SZ = G->scratch + ((slN * G->vchunk + 15) & ~15LL);   // 128-byte aligned: rows are read as double2
     const double* inv = in + (long long)v0 * d.N;
     double* mir = mirror ? mirror + (long long)v0 * d.N : nullptr;
     if (d.has_l && d.has_z) {
@@ -346,7 +346,7 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
   for (int v0 = 0; v0 < t.V; v0 += T->vchunk) {
     const int nv = std::min(T->vchunk, t.V - v0);
     double* SL = T->scratch;                          // [3][vchunk][slN]
-    double* SZ = T->scratch + 3 * slN * T->vchunk;    // [5][vchunk][szN]
+    double* SZ = T->scratch + ((3 * slN * T->vchunk + 15) & ~15LL);    // [5][vchunk][szN], 128-byte aligned
     const long long sl_fs = slN * T->vchunk, sz_fs = szN * T->vchunk;
     launch_inv_r(c, t, p, nv, P->spectralA + (long long)v0 * p.S, p.S, SL, sl_fs, slN, 0, v0);
     if (t.has_l && t.has_z) {

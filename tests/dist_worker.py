@@ -1,0 +1,42 @@
+"""Worker for test_distributed_gloo.py: one rank = one radial tile; the shared spectral sum is a
+torch.distributed all-reduce on a zero-copy view of the library's buffer (gloo on CPU with the
+test-only emulation build; the same host code runs NCCL on the GPU box)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main(case_name, out_path, lib_path, ntiles):
+    import scythe_jl_b200 as S  # noqa: F401
+    from helpers import model_cases, pkg_model
+    from oracle import grids as G
+    from scythe_jl_b200 import _lib
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lib = _lib.load(lib_path)
+    case = model_cases()[case_name]
+    m = pkg_model(case, int(ntiles), lib, distributed=True)
+    assert m.tile_count == int(ntiles) // world and m.tile_first == rank * m.tile_count
+    # each rank only ever sees its own slice of the initial state
+    patch = G.createGrid(case["gp"])
+    tp = G.calcTileSizes(patch, int(ntiles))
+    pts = np.concatenate([[0], np.cumsum(tp[4]).astype(np.int64)])
+    ics = [case["ic"][pts[t]:pts[t + 1]] for t in range(m.tile_first, m.tile_first + m.tile_count)]
+    m.initialize_tiles(ics)
+    m.run(case["n"])
+    out = m.output()
+    np.save(f"{out_path}.rank{rank}.npy", out)
+    dist.barrier()
+    m.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:5])

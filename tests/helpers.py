@@ -128,7 +128,7 @@ def model_cases(small=True):
     ic[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
     ic[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
     cases["LinearAdvectionRLZ"] = dict(gp=gp, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=3, ic=ic, tiles=(1, 2))
-    gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e5, num_cells=9, zmin=0, zmax=1e4, zDim=12,
+    gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e5, num_cells=12, zmin=0, zmax=1e4, zDim=12,
                           vars={"h": 1, "u": 2, "x": 3, "w": 4})
     r, z = G.createGrid(gp).getGridpoints().T
     ic = np.zeros((r.size, 4))
