@@ -35,21 +35,26 @@ def ring_lambdas(ri: int) -> np.ndarray:
     return ring_ymin(ri) + (2.0 * math.pi / n) * np.arange(n)
 
 
+def ring_phase(ri: int) -> np.ndarray:
+    """exp(-i k ymin), k = 0..ri, with the angle reduced exactly: k*ymin = pi * (k (ri-1) mod 2n) / n."""
+    n = ring_points(ri)
+    q = (np.arange(ri + 1, dtype=np.int64) * (ri - 1)) % (2 * n)
+    return np.exp(-1j * math.pi * q / n)
+
+
 def ring_forward(u: np.ndarray, ri: int, workers: int = 1) -> np.ndarray:
     """u: [yDim, ...] real -> c: [ri+1, ...] complex (FB then FA)."""
     n = ring_points(ri)
     assert u.shape[0] == n
     X = sfft.rfft(u, axis=0, workers=workers)[: ri + 1] / n
-    k = np.arange(ri + 1).reshape((-1,) + (1,) * (u.ndim - 1))
-    return X * np.exp(-1j * k * ring_ymin(ri))
+    return X * ring_phase(ri).reshape((-1,) + (1,) * (u.ndim - 1))
 
 
 def ring_inverse(c: np.ndarray, ri: int, derivative: int = 0, workers: int = 1) -> np.ndarray:
     """c: [ri+1, ...] complex -> u^(derivative): [yDim, ...] real."""
     n = ring_points(ri)
     k = np.arange(ri + 1).reshape((-1,) + (1,) * (c.ndim - 1))
-    Y = c * np.exp(1j * k * ring_ymin(ri))
-    Y = Y.copy()
+    Y = c * np.conj(ring_phase(ri)).reshape(k.shape)
     Y[0] = Y[0].real  # wavenumber 0 is real by construction
     if derivative == 1:
         Y = Y * (1j * k)

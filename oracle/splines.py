@@ -146,6 +146,38 @@ def basis_matrix(spp: SplineParameters, x: np.ndarray, derivative: int = 0) -> s
                          shape=(len(x), spp.bDim))
 
 
+def mish_basis_matrix(spp: SplineParameters, derivative: int = 0) -> sp.csr_matrix:
+    """basis_matrix at the mish points, evaluated from the exact in-cell Gauss offsets
+    ``delta = t_mu + 1 - j`` instead of ``(x - x_m)/DX``: the latter loses ~ (x/DX)*eps in absolute
+    terms (1e-13 at the outer radii of the 334-cell grid), which would dominate oracle-vs-GPU
+    comparisons.  Mathematically identical to Springsteel's ``basis(sp, m, x, derivative)``."""
+    nc = spp.num_cells
+    t = 0.5 + 0.5 * GAUSS_POINTS                       # position of the 3 mish points inside a cell
+    DXr = 1.0 / spp.DX
+    rows, cols, vals = [], [], []
+    cell = np.repeat(np.arange(nc), MUBAR)
+    idx = np.arange(nc * MUBAR)
+    for o in range(4):
+        delta = np.tile(t + 1.0 - o, nc)
+        z = np.abs(delta)
+        sgn = np.where(delta > 0, -1.0, 1.0)
+        z2 = 2.0 - z
+        z1 = np.maximum(1.0 - z, 0.0)
+        if derivative == 0:
+            b = (z2 ** 3 - 4.0 * z1 ** 3) / 6.0
+        elif derivative == 1:
+            b = sgn * 3.0 * DXr * (z2 ** 2 - 4.0 * z1 ** 2) / 6.0
+        elif derivative == 2:
+            b = DXr * DXr * (z2 - 4.0 * z1)
+        else:
+            b = sgn * DXr ** 3 * np.where(z > 1.0, 1.0, np.where(z < 1.0, -3.0, 0.0))
+        rows.append(idx)
+        cols.append(cell + o)
+        vals.append(np.where(z < 2.0, b, 0.0))
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                         shape=(nc * MUBAR, spp.bDim))
+
+
 def gamma_matrix(spp: SplineParameters) -> np.ndarray:
     """BC fold Gamma [(M - rank), M]:  a = Gamma^T a_free  (rank reduction, Ooyama 2002).
 
@@ -185,10 +217,9 @@ def gamma_matrix(spp: SplineParameters) -> np.ndarray:
 def pq_matrix(spp: SplineParameters) -> np.ndarray:
     """P + Q:  P = sum_i w_i phi_m phi_m' (mish quadrature);  Q = eps_q sum_i w_i phi'''_m phi'''_m',
     eps_q = (l_q DX / 2 pi)^6  (sixth-order low-pass, cutoff wavelength l_q*DX)."""
-    x = mish_points(spp)
     w = mish_weights(spp)
-    B0 = basis_matrix(spp, x, 0)
-    B3 = basis_matrix(spp, x, 3)
+    B0 = mish_basis_matrix(spp, 0)
+    B3 = mish_basis_matrix(spp, 3)
     W = sp.diags(w)
     eps_q = (spp.l_q * spp.DX / (2.0 * math.pi)) ** 6
     PQ = (B0.T @ W @ B0) + eps_q * (B3.T @ W @ B3)
@@ -206,7 +237,7 @@ class Spline1D:
         self.pq = pq_matrix(spp)
         self.pq_folded = self.gammaBC @ self.pq @ self.gammaBC.T
         self.pqFactor = sla.cho_factor(self.pq_folded, lower=True)
-        self.B = [basis_matrix(spp, self.mishPoints, d) for d in range(3)]
+        self.B = [mish_basis_matrix(spp, d) for d in range(3)]
         self.uMish = np.zeros(spp.mishDim)
         self.b = np.zeros(spp.bDim)
         self.a = np.zeros(spp.bDim)

@@ -87,7 +87,7 @@ struct sb_grid {
   std::vector<FftClass> classes;
   std::vector<std::vector<LWork>> fwork, iwork;
   std::vector<const LWork*> d_fwork, d_iwork;
-  std::vector<const double*> d_tw;
+  std::vector<const double*> d_tw, d_twp;
   RingPlan* d_plans = nullptr;
   double* d_blob = nullptr;
   double* d_fwdT = nullptr;
@@ -287,6 +287,7 @@ static void build_grid(sb_grid* G) {
       G->d_fwork.push_back(G->up(G->fwork[c]));
       G->d_iwork.push_back(G->up(G->iwork[c]));
       G->d_tw.push_back(G->up(G->classes[c].tw));
+      G->d_twp.push_back(G->up(G->classes[c].twp));
     }
   }
   G->spectralB = dev_zeros(d.S * d.V, G->stream);
@@ -315,10 +316,10 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
     double* mir = mirror ? mirror + (long long)v0 * d.N : nullptr;
     if (d.has_l && d.has_z) {
       launch_fwd_z(c, d, G->d_ztiles, G->nztiles, nv, inv, d.N, mir, d.N, SZ, szN, G->d_fwdT);
-      launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_plans, G->d_blob, nv, SZ, szN,
+      launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, SZ, szN,
                    1, nullptr, 0, SL, slN);
     } else if (d.has_l) {
-      launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_plans, G->d_blob, nv, inv, d.N,
+      launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, inv, d.N,
                    0, mir, d.N, SL, slN);
     } else {
       launch_fwd_z(c, d, G->d_ztiles, G->nztiles, nv, inv, d.N, mir, d.N, SL, slN, G->d_fwdT);
@@ -350,11 +351,11 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
     const long long sl_fs = slN * T->vchunk, sz_fs = szN * T->vchunk;
     launch_inv_r(c, t, p, nv, P->spectralA + (long long)v0 * p.S, p.S, SL, sl_fs, slN, 0, v0);
     if (t.has_l && t.has_z) {
-      launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
+      launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
                    slN, SZ, sz_fs, szN, 0, v0);
       launch_inv_z(c, t, T->d_ztiles, T->nztiles, nv, v0, 5, SZ, sz_fs, szN, T->physical, T->d_invM);
     } else if (t.has_l) {
-      launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
+      launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
                    slN, T->physical, 0, 0, 1, v0);
     } else {
       launch_inv_z(c, t, T->d_ztiles, T->nztiles, nv, v0, 3, SL, sl_fs, slN, T->physical, T->d_invM);

@@ -43,7 +43,15 @@ bool invert(std::vector<double>& A, int n);
 struct FftClass {            // one power-of-two convolution length
   int L = 0, log2L = 0;
   std::vector<double> tw;    // [L] complex: exp(-2 pi i t / L)
+  bool fast = false;         // L in 256..8192: register-resident radix-16 kernel (sb_ringfft.cu)
+  std::vector<double> twp;   // fast: per-pass twiddle tables
+  int twoff[4] = {0, 0, 0, 0};
 };
+// fast-kernel configuration / host mirrors (sb_ringfft.cu)
+bool fast_class_supported(int L);
+void fast_class_config(int L, int* log2L, int* nfull, int* rf, int* T, int* nteams, int* iters, int* nrows);
+void fast_class_twiddles(int L, std::vector<double>& tab, int off[4]);
+void host_fft_dif16(double* x, int L);   // natural -> the fast kernel's digit-reversed order
 struct RingPlan {            // Bluestein plan of one ring (sub-DFT length m = n/4)
   int n = 0, m = 0, L = 0, cls = 0;
   long long off = 0;         // offset (in doubles) of this ring's tables in the blob
@@ -108,12 +116,12 @@ void launch_inv_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int 
                   double* phys, const double* invM /* [V][3][bz][zDim] */);
 void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes,
-                  const double* const* tw, const RingPlan* plans, const double* blob, int nvars,
+                  const double* const* tw, const double* const* twp, const RingPlan* plans, const double* blob, int nvars,
                   const double* in, long long in_vstride, int in_is_z, double* mirror, long long mirror_vstride,
                   double* out, long long out_vstride);
 void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes,
-                  const double* const* tw, const RingPlan* plans, const double* blob, int nvars,
+                  const double* const* tw, const double* const* twp, const RingPlan* plans, const double* blob, int nvars,
                   const double* in, long long in_fstride, long long in_vstride,
                   double* out, long long out_fstride, long long out_vstride, int out_is_phys, int var0);
 void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride,
@@ -121,6 +129,13 @@ void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double*
 void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch, int nvars,
                   const double* A, long long A_vstride, double* out, long long out_fstride,
                   long long out_vstride, int out_is_phys, int var0);
+void launch_fwd_l_fast(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                       const int twoff[4], const RingPlan* plans, const double* blob, int nvars, const double* in,
+                       long long in_vs, double* mirror, long long mirror_vs, double* out, long long out_vs);
+void launch_inv_l_fast(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                       const int twoff[4], const RingPlan* plans, const double* blob, int nvars, const double* in,
+                       long long in_fs, long long in_vs, double* out, long long out_fs, long long out_vs, int out_is_phys,
+                       int var0);
 struct DevSplineFactor {
   int M, rL, rR, nfree, periodic;
   double foldL[2], foldR[2];

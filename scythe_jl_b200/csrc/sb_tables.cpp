@@ -393,6 +393,8 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
       c.tw[2 * t] = (double)cosl(-2.0L * kPiL * t / L);
       c.tw[2 * t + 1] = (double)sinl(-2.0L * kPiL * t / L);
     }
+    c.fast = fast_class_supported(L);
+    if (c.fast) fast_class_twiddles(L, c.twp, c.twoff);
     classes.push_back(std::move(c));
     return (int)classes.size() - 1;
   };
@@ -428,9 +430,20 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
       h[2 * j] = chirp[2 * j]; h[2 * j + 1] = -chirp[2 * j + 1];
       if (j > 0) { h[2 * (L - j)] = chirp[2 * j]; h[2 * (L - j) + 1] = -chirp[2 * j + 1]; }
     }
-    host_fft_dif(h.data(), L, classes[p.cls].tw.data());
     const double invL = 1.0 / L;
-    for (int i = 0; i < 2 * L; ++i) FH[i] = h[i] * invL;
+    if (classes[p.cls].fast) {
+      // fast kernel: DIF16 order, laid out [e][tl] so that thread tl reads element tl*16+e coalesced
+      host_fft_dif16(h.data(), L);
+      const int T = L / 16;
+      for (int tl = 0; tl < T; ++tl)
+        for (int e = 0; e < 16; ++e) {
+          FH[2 * (e * T + tl)] = h[2 * (tl * 16 + e)] * invL;
+          FH[2 * (e * T + tl) + 1] = h[2 * (tl * 16 + e) + 1] * invL;
+        }
+    } else {
+      host_fft_dif(h.data(), L, classes[p.cls].tw.data());
+      for (int i = 0; i < 2 * L; ++i) FH[i] = h[i] * invL;
+    }
   }
 }
 

@@ -360,6 +360,11 @@ __global__ void __launch_bounds__(512) k_fwd_l(DevGrid g, const LWork* __restric
 }
 
 int sb_rows_per_cta(int L) {
+  if (fast_class_supported(L)) {
+    int log2L, nfull, rf, T, nteams, iters, nrows;
+    fast_class_config(L, &log2L, &nfull, &rf, &T, &nteams, &iters, &nrows);
+    return nrows;
+  }
   int r = (192 * 1024) / (2 * L * 16);
   if (r > 16) r = 16;
   if (r < 1) r = 1;
@@ -368,13 +373,19 @@ int sb_rows_per_cta(int L) {
 
 void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes, const double* const* tw,
-                  const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vstride,
-                  int /*in_is_z*/, double* mirror, long long mirror_vstride, double* out, long long out_vstride) {
+                  const double* const* twp, const RingPlan* plans, const double* blob, int nvars, const double* in,
+                  long long in_vstride, int /*in_is_z*/, double* mirror, long long mirror_vstride, double* out,
+                  long long out_vstride) {
   ProfScope prof_scope_(c, "fwd_l");
-  for (size_t ci = 0; ci < classes.size(); ++ci) {
+  for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
     int nwork = (int)hostwork[ci].size();
     if (!nwork) continue;
     int L = classes[ci].L;
+    if (classes[ci].fast) {
+      launch_fwd_l_fast(c, g, work[ci], nwork, L, twp[ci], classes[ci].twoff, plans, blob, nvars, in, in_vstride, mirror,
+                        mirror_vstride, out, out_vstride);
+      continue;
+    }
     int nr = sb_rows_per_cta(L);
     size_t smem = (size_t)2 * nr * L * 16;
     opt_in_smem(k_fwd_l, smem);
@@ -472,14 +483,19 @@ __global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restric
 
 void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes, const double* const* tw,
-                  const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fstride,
-                  long long in_vstride, double* out, long long out_fstride, long long out_vstride,
+                  const double* const* twp, const RingPlan* plans, const double* blob, int nvars, const double* in,
+                  long long in_fstride, long long in_vstride, double* out, long long out_fstride, long long out_vstride,
                   int out_is_phys, int var0) {
   ProfScope prof_scope_(c, "inv_l");
-  for (size_t ci = 0; ci < classes.size(); ++ci) {
+  for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
     int nwork = (int)hostwork[ci].size();
     if (!nwork) continue;
     int L = classes[ci].L;
+    if (classes[ci].fast) {
+      launch_inv_l_fast(c, g, work[ci], nwork, L, twp[ci], classes[ci].twoff, plans, blob, nvars, in, in_fstride,
+                        in_vstride, out, out_fstride, out_vstride, out_is_phys, var0);
+      continue;
+    }
     int nr = sb_rows_per_cta(L);
     size_t smem = (size_t)2 * nr * L * 16;
     opt_in_smem(k_inv_l, smem);
