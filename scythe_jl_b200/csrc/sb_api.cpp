@@ -92,6 +92,8 @@ struct sb_grid {
   double* d_blob = nullptr;
   double* d_fwdT = nullptr;
   double* d_invM = nullptr;
+  double* d_parM = nullptr;     // parity tables for the BC-free fast Chebyshev inverse
+  std::vector<char> z_bcfree;   // per variable: BCB == BCT == R0
   long long launches = 0;
   long long* d_nan = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -243,6 +245,11 @@ static void build_grid(sb_grid* G) {
           }
     }
     G->d_invM = G->up(invM);
+    G->z_bcfree.assign(d.V, 0);
+    for (int v = 0; v < d.V; ++v) G->z_bcfree[v] = ((G->bcb.empty() || G->bcb[v] == 0) && (G->bct.empty() || G->bct[v] == 0)) ? 1 : 0;
+    std::vector<double> parM;
+    build_inv_z_par_tables(d.zDim, d.bz, G->cheb.T0.data(), G->cheb.T1.data(), G->cheb.T2.data(), parM);
+    G->d_parM = G->up(parM);
     // z tiles
     std::vector<ZTile> zt;
     if (d.has_l) {
@@ -328,6 +335,8 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
   }
 }
 
+static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in, long long fs, long long vs);
+
 // inverse transform: patch A -> tile physical (K3)
 static void grid_inverse(sb_grid* P, sb_grid* T) {
   DevGrid& t = T->dg;
@@ -353,14 +362,24 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
     if (t.has_l && t.has_z) {
       launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
                    slN, SZ, sz_fs, szN, 0, v0);
-      launch_inv_z(c, t, T->d_ztiles, T->nztiles, nv, v0, 5, SZ, sz_fs, szN, T->physical, T->d_invM);
+      grid_inv_z(T, nv, v0, 5, SZ, sz_fs, szN);
     } else if (t.has_l) {
       launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
                    slN, T->physical, 0, 0, 1, v0);
     } else {
-      launch_inv_z(c, t, T->d_ztiles, T->nztiles, nv, v0, 3, SL, sl_fs, slN, T->physical, T->d_invM);
+      grid_inv_z(T, nv, v0, 3, SL, sl_fs, slN);
     }
   }
+}
+
+// Chebyshev inverse of a variable chunk: parity fast path when no variable of the chunk has vertical BCs
+static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in, long long fs, long long vs) {
+  bool fast = inv_z_par_ok(T->dg, nfields) && !std::getenv("SB_INVZ_GENERIC");
+  for (int v = v0; v < v0 + nv && fast; ++v) fast = T->z_bcfree[v] != 0;
+  if (fast)
+    launch_inv_z_par(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parM);
+  else
+    launch_inv_z(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_invM);
 }
 
 static void grid_spline(sb_grid* P, const double* B) {

@@ -176,6 +176,130 @@ __global__ void __launch_bounds__(512) k_inv_z(DevGrid g, const ZTile* __restric
   }
 }
 
+// -------------------------------------------------------------------------------------
+// parity fast path (no vertical BCs, even zDim <= 64, bz <= KMAX): T_k(-xi) = (-1)^k T_k(xi), so
+// level z and its mirror zDim-1-z share the even-mode and odd-mode partial sums E, O:
+//   out[z] = E + O,  out[zDim-1-z] = sigma (E - O)   (sigma = -1 for d/dz).
+// lane = level (matrix row in REGISTERS), coefficients broadcast from smem as 128-bit pairs,
+// warp = columns; every store is a coalesced 256-byte row segment.
+// parM: [3][KMAX][32] (matrix, mode, lane), zero padded.
+// -------------------------------------------------------------------------------------
+#define ZPAR_KMAX 44
+#define ZPAR_ZS (ZPAR_KMAX + 2)
+
+__global__ void __launch_bounds__(256, 1) k_inv_z_par(DevGrid g, const ZTile* __restrict__ tiles, int ntiles, int var0,
+                                                      int nfields, const double* __restrict__ in, long long in_fs,
+                                                      long long in_vs, double* __restrict__ phys,
+                                                      const double* __restrict__ parM) {
+  SB_DYN_SMEM(double, a);   // [nfields][32][ZPAR_ZS]
+  const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v = blockIdx.y;
+  for (int i = tid; i < nfields * 32 * ZPAR_ZS; i += 256) a[i] = 0.0;   // the zero padding k >= bz stays zero
+  const long long slotN = (long long)g.V * g.N;
+  double* const pv = phys + (long long)(var0 + v) * g.N;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const ZTile zt = tiles[t];
+    __syncthreads();
+    for (int row = warp; row < nfields * bz; row += 8) {
+      const int f = row / bz, zb = row - f * bz;
+      double val = 0.0;
+      if (lane < zt.ncols)
+        val = in[(long long)f * in_fs + (long long)v * in_vs + zt.out_base + (long long)zb * zt.out_stride + lane];
+      a[(f * 32 + lane) * ZPAR_ZS + zb] = val;
+    }
+    __syncthreads();
+    const long long colbase = (long long)zt.hcol0 * zDim;
+#pragma unroll 1
+    for (int mat = 0; mat < 3; ++mat) {
+      double Mr[ZPAR_KMAX];
+#pragma unroll
+      for (int k = 0; k < ZPAR_KMAX; ++k) Mr[k] = parM[(mat * ZPAR_KMAX + k) * 32 + lane];
+      if (mat == 0) {
+        // value matrix: all fields of one column at once (2*nfields independent FMA chains)
+        for (int c = warp; c < zt.ncols; c += 8) {
+          double E[5] = {0, 0, 0, 0, 0}, O[5] = {0, 0, 0, 0, 0};
+          const double2* ap = reinterpret_cast<const double2*>(a + c * ZPAR_ZS);
+#pragma unroll
+          for (int k2 = 0; k2 < ZPAR_KMAX / 2; ++k2) {
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+              if (f < nfields) {
+                const double2 x = ap[f * (32 * ZPAR_ZS / 2) + k2];
+                E[f] = fma(Mr[2 * k2], x.x, E[f]);
+                O[f] = fma(Mr[2 * k2 + 1], x.y, O[f]);
+              }
+            }
+          }
+          if (lane < zh) {
+            double* o = pv + colbase + (long long)c * zDim;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+              if (f < nfields) {
+                o[f * slotN + lane] = E[f] + O[f];
+                o[f * slotN + zDim - 1 - lane] = E[f] - O[f];
+              }
+            }
+          }
+        }
+      } else {
+        // d/dz (mat 1, sigma = -1) and d2/dz2 (mat 2) of field 0: four columns at once
+        const double sigma = (mat == 1) ? -1.0 : 1.0;
+        double* const oslot = pv + (long long)(nfields + mat - 1) * slotN + colbase;
+        for (int c0 = warp * 4; c0 < zt.ncols; c0 += 32) {   // 8 warps x 4 columns = one 32-column tile
+          double E[4] = {0, 0, 0, 0}, O[4] = {0, 0, 0, 0};
+          const double2* ap = reinterpret_cast<const double2*>(a + c0 * ZPAR_ZS);
+#pragma unroll
+          for (int k2 = 0; k2 < ZPAR_KMAX / 2; ++k2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double2 x = ap[j * (ZPAR_ZS / 2) + k2];
+              E[j] = fma(Mr[2 * k2], x.x, E[j]);
+              O[j] = fma(Mr[2 * k2 + 1], x.y, O[j]);
+            }
+          }
+          if (lane < zh) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c0 + j < zt.ncols) {
+                double* o = oslot + (long long)(c0 + j) * zDim;
+                o[lane] = E[j] + O[j];
+                o[zDim - 1 - lane] = sigma * (E[j] - O[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+bool inv_z_par_ok(const DevGrid& g, int nfields) {
+  return g.zDim >= 2 && g.zDim <= 64 && (g.zDim & 1) == 0 && g.bz <= ZPAR_KMAX && nfields <= 5;
+}
+
+// host: parity matrices [3][KMAX][32] from the full synthesis matrices T_k[z][q] (no BC fold)
+void build_inv_z_par_tables(int zDim, int bz, const double* T0, const double* T1, const double* T2, std::vector<double>& out) {
+  out.assign((size_t)3 * ZPAR_KMAX * 32, 0.0);
+  const double* T[3] = {T0, T1, T2};
+  for (int m = 0; m < 3; ++m)
+    for (int k = 0; k < bz && k < ZPAR_KMAX; ++k)
+      for (int z = 0; z < zDim / 2 && z < 32; ++z) out[((size_t)m * ZPAR_KMAX + k) * 32 + z] = T[m][(size_t)z * zDim + k];
+}
+
+void launch_inv_z_par(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
+                      int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
+                      const double* parM) {
+  ProfScope prof_scope_(c, "inv_z");
+  size_t smem = (size_t)nfields * 32 * ZPAR_ZS * sizeof(double);
+  opt_in_smem(k_inv_z_par, smem);
+  int gx = ntiles < 148 * 2 * 4 ? ntiles : 148 * 2 * 4;
+  SB_LAUNCH(k_inv_z_par, dim3(gx, nvars), dim3(256), smem, c.stream, g, tiles, ntiles, var0, nfields, in, in_fstride,
+            in_vstride, phys, parM);
+  SB_CHECK_LAUNCH();
+  count(c);
+}
+
 void launch_inv_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
                   int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
                   const double* invM) {
