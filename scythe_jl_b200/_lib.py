@@ -118,7 +118,7 @@ class Library:
                 f"{path} is missing: build the sm_100a library with `python -m scythe_jl_b200.build` "
                 "(nvcc required).  scythe_jl_b200 has no CPU fallback.")
         self.path = path
-        self.dll = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+        self.dll = C.CDLL(str(path), mode=C.RTLD_LOCAL)   # LOCAL: the test-only emulation build exports the same C++ symbols
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(self.dll, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res

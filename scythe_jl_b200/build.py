@@ -18,7 +18,7 @@ REPO = ROOT.parent
 LIB = ROOT / "libscythe_b200.so"
 EMU_DIR = REPO / "tests" / "_emu"
 EMU_LIB = EMU_DIR / "libscythe_b200_emu.so"
-SOURCES = ["sb_transforms.cu", "sb_ringfft.cu", "sb_model.cu", "sb_api.cpp", "sb_tables.cpp"]
+SOURCES = ["sb_transforms.cu", "sb_ringfft.cu", "sb_chebmma.cu", "sb_model.cu", "sb_api.cpp", "sb_tables.cpp"]
 HEADERS = ["sb_internal.hpp", "cuda_emu.h", "../../include/scythe_b200.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(4) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
-          "-Xcompiler", "-fPIC", "-ldl", "-lcudart"])
+          "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-ldl", "-lcudart"])
     return LIB
 
 
@@ -85,7 +85,7 @@ def build_emu(force: bool = False) -> Path:
 
     with ThreadPoolExecutor(5) as ex:
         objs = list(ex.map(compile_one, srcs))
-    _run(["g++", "-shared", "-pthread", "-o", str(EMU_LIB), *map(str, objs), "-ldl"])
+    _run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(EMU_LIB), *map(str, objs), "-ldl"])
     return EMU_LIB
 
 

@@ -92,7 +92,8 @@ struct sb_grid {
   double* d_blob = nullptr;
   double* d_fwdT = nullptr;
   double* d_invM = nullptr;
-  double* d_parM = nullptr;     // parity tables for the BC-free fast Chebyshev inverse
+  double* d_parM = nullptr;     // parity tables for the BC-free fast Chebyshev inverse (FMA form)
+  double* d_parB = nullptr;     // DMMA B-fragment tables of the same matrices
   std::vector<char> z_bcfree;   // per variable: BCB == BCT == R0
   long long launches = 0;
   long long* d_nan = nullptr;
@@ -250,6 +251,9 @@ static void build_grid(sb_grid* G) {
     std::vector<double> parM;
     build_inv_z_par_tables(d.zDim, d.bz, G->cheb.T0.data(), G->cheb.T1.data(), G->cheb.T2.data(), parM);
     G->d_parM = G->up(parM);
+    std::vector<double> parB;
+    build_inv_z_mma_tables(d.zDim, d.bz, G->cheb.T0.data(), G->cheb.T1.data(), G->cheb.T2.data(), parB);
+    G->d_parB = G->up(parB);
     // z tiles
     std::vector<ZTile> zt;
     if (d.has_l) {
@@ -374,9 +378,13 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
 
 // Chebyshev inverse of a variable chunk: parity fast path when no variable of the chunk has vertical BCs
 static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in, long long fs, long long vs) {
-  bool fast = inv_z_par_ok(T->dg, nfields) && !std::getenv("SB_INVZ_GENERIC");
-  for (int v = v0; v < v0 + nv && fast; ++v) fast = T->z_bcfree[v] != 0;
-  if (fast)
+  const char* mode = std::getenv("SB_INVZ");   // A/B switch: "generic" | "fma" | (default) "mma"
+  const std::string md = mode ? mode : "mma";
+  bool bcfree = md != "generic";
+  for (int v = v0; v < v0 + nv && bcfree; ++v) bcfree = T->z_bcfree[v] != 0;
+  if (bcfree && md == "mma" && inv_z_mma_ok(T->dg, nfields))
+    launch_inv_z_mma(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parB);
+  else if (bcfree && inv_z_par_ok(T->dg, nfields))
     launch_inv_z_par(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parM);
   else
     launch_inv_z(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_invM);

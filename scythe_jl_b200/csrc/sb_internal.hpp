@@ -114,6 +114,11 @@ void launch_fwd_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int 
 void launch_inv_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
                   int nfields, const double* in, long long in_fstride, long long in_vstride,
                   double* phys, const double* invM /* [V][3][bz][zDim] */);
+bool inv_z_mma_ok(const DevGrid& g, int nfields);
+void build_inv_z_mma_tables(int zDim, int bz, const double* T0, const double* T1, const double* T2, std::vector<double>& out);
+void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
+                      int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
+                      const double* parB);
 bool inv_z_par_ok(const DevGrid& g, int nfields);
 void build_inv_z_par_tables(int zDim, int bz, const double* T0, const double* T1, const double* T2, std::vector<double>& out);
 void launch_inv_z_par(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,

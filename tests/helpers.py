@@ -53,6 +53,11 @@ def transform_cases():
                                 BCL={"h": B.R1T1, "u": B.R1T0}, BCR={"h": B.R0, "u": B.R2T20},
                                 BCB={"h": ch.R0, "u": ch.R1T1}, BCT={"h": ch.R0, "u": ch.R1T2},
                                 vars={"h": 1, "u": 2}),
+        # no vertical BCs + zDim in {16, 32, 64}: the DMMA (tensor-core) Chebyshev synthesis path
+        "RLZ_z16_nobc": G.GridParameters(geometry="RLZ", xmin=0, xmax=10, num_cells=3, zmin=0, zmax=5, zDim=16,
+                                         BCL={"h": B.R1T1, "u": B.R1T0}, vars={"h": 1, "u": 2}),
+        "RZ_z32_nobc": G.GridParameters(geometry="RZ", xmin=0, xmax=10, num_cells=13, zmin=0, zmax=5, zDim=32,
+                                        vars={"s": 1, "w": 2}),
     }
 
 
