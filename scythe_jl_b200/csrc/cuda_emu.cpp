@@ -3,6 +3,7 @@
 #include "cuda_emu.h"
 
 #include <chrono>
+#include <mutex>
 
 namespace sbemu {
 thread_local uint3 t_threadIdx, t_blockIdx;
@@ -13,8 +14,25 @@ std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
 double g_warp_buf[64][32];
 unsigned char* g_dyn_smem = nullptr;
 
+static std::mutex g_named_mu;
+static std::unique_ptr<std::barrier<>> g_named[16];
+static int g_named_cnt[16];
+void named_barrier(int id, int nthreads) {
+  std::barrier<>* b;
+  {
+    std::lock_guard<std::mutex> lk(g_named_mu);
+    if (!g_named[id] || g_named_cnt[id] != nthreads) {
+      g_named[id].reset(new std::barrier<>(nthreads));
+      g_named_cnt[id] = nthreads;
+    }
+    b = g_named[id].get();
+  }
+  b->arrive_and_wait();
+}
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   const int nthreads = (int)(block.x * block.y * block.z);
+  for (int i = 0; i < 16; ++i) g_named[i].reset();
   std::barrier<> bar(nthreads);
   g_block_barrier = &bar;
   g_warp_barriers.clear();

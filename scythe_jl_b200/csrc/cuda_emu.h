@@ -141,6 +141,14 @@ static inline void sb_dmma(double& d0, double& d1, double a, double b) {
     d1 += aik * b1;
   }
 }
+// asynchronous global->shared copies (LDGSTS): the emulation copies at once
+static inline void sb_cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+static inline void sb_cp_async8(void* dst, const void* src) { std::memcpy(dst, src, 8); }
+static inline void sb_cp_commit() {}
+template <int N> static inline void sb_cp_wait() {}
+// named barrier for a subset of the block (bar.sync id, nthreads)
+namespace sbemu { void named_barrier(int id, int nthreads); }
+static inline void sb_bar_sync(int id, int nthreads) { sbemu::named_barrier(id, nthreads); }
 #define SB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(sbemu::g_dyn_smem)
 #define SB_LAUNCH(kernel, grid, block, smem, stream, ...) \
   sbemu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
@@ -153,6 +161,17 @@ static inline void sb_dmma(double& d0, double& d1, double a, double b) {
 __device__ __forceinline__ void sb_dmma(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void sb_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sb_cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sb_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sb_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sb_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 #endif
 #define SB_DYN_SMEM(type, name)                                   \

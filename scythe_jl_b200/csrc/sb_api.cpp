@@ -94,6 +94,7 @@ struct sb_grid {
   double* d_invM = nullptr;
   double* d_parM = nullptr;     // parity tables for the BC-free fast Chebyshev inverse (FMA form)
   double* d_parB = nullptr;     // DMMA B-fragment tables of the same matrices
+  double* d_fwdB = nullptr;     // DMMA B-fragment tables of the analysis (forward) matrix
   std::vector<char> z_bcfree;   // per variable: BCB == BCT == R0
   long long launches = 0;
   long long* d_nan = nullptr;
@@ -254,6 +255,9 @@ static void build_grid(sb_grid* G) {
     std::vector<double> parB;
     build_inv_z_mma_tables(d.zDim, d.bz, G->cheb.T0.data(), G->cheb.T1.data(), G->cheb.T2.data(), parB);
     G->d_parB = G->up(parB);
+    std::vector<double> fwdB;
+    build_fwd_z_mma_tables(d.zDim, d.bz, G->cheb.fwd.data(), fwdB);
+    G->d_fwdB = G->up(fwdB);
     // z tiles
     std::vector<ZTile> zt;
     if (d.has_l) {
@@ -308,6 +312,8 @@ static void build_grid(sb_grid* G) {
   CU(cudaEventCreate(&G->ev1));
 }
 
+static void grid_fwd_z(sb_grid* G, int nv, const double* in, double* mir, double* out, long long out_vs);
+
 // forward transform of `in` ([V][N] var-major) into G->spectralB (K1)
 static void grid_forward(sb_grid* G, const double* in, double* mirror) {
   DevGrid& d = G->dg;
@@ -326,20 +332,30 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
     const double* inv = in + (long long)v0 * d.N;
     double* mir = mirror ? mirror + (long long)v0 * d.N : nullptr;
     if (d.has_l && d.has_z) {
-      launch_fwd_z(c, d, G->d_ztiles, G->nztiles, nv, inv, d.N, mir, d.N, SZ, szN, G->d_fwdT);
+      grid_fwd_z(G, nv, inv, mir, SZ, szN);
       launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, SZ, szN,
                    1, nullptr, 0, SL, slN);
     } else if (d.has_l) {
       launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, inv, d.N,
                    0, mir, d.N, SL, slN);
     } else {
-      launch_fwd_z(c, d, G->d_ztiles, G->nztiles, nv, inv, d.N, mir, d.N, SL, slN, G->d_fwdT);
+      grid_fwd_z(G, nv, inv, mir, SL, slN);
     }
     launch_fwd_r(c, d, nv, SL, slN, G->spectralB + (long long)v0 * d.S, d.S);
   }
 }
 
 static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in, long long fs, long long vs);
+
+// Chebyshev analysis of a variable chunk: tensor-core (DMMA) kernel when the level count allows it
+static void grid_fwd_z(sb_grid* G, int nv, const double* in, double* mir, double* out, long long out_vs) {
+  const DevGrid& d = G->dg;
+  static const bool generic = std::getenv("SB_FWDZ_GENERIC") != nullptr;   // A/B switch
+  if (!generic && fwd_z_mma_ok(d) && (uintptr_t)in % 16 == 0)
+    launch_fwd_z_mma(G->ctx(), d, G->d_ztiles, G->nztiles, nv, in, d.N, mir, d.N, out, out_vs, G->d_fwdB);
+  else
+    launch_fwd_z(G->ctx(), d, G->d_ztiles, G->nztiles, nv, in, d.N, mir, d.N, out, out_vs, G->d_fwdT);
+}
 
 // inverse transform: patch A -> tile physical (K3)
 static void grid_inverse(sb_grid* P, sb_grid* T) {

@@ -16,24 +16,32 @@
 // transposing stores and the fragment loads bank-conflict-free.
 #include "sb_internal.hpp"
 
+#include <cstdint>
 #include <stdexcept>
 
 namespace sb {
 
 #define ZM_KT 6                 // k-tiles (of 4 modes) per parity  -> b_zDim <= 48
 #define ZM_KK (4 * ZM_KT)       // modes per parity held in smem
-#define ZM_CS 40                // column stride of the smem tile: 32 columns + 8 pad (== 8 mod 16)
+#define ZM_CS 36                // column stride of the smem tile: 32 columns + 4 pad (== 4 mod 16: the
+                                // half-warp fragment load q*CS + i, q,i = 0..3 touches 16 distinct banks)
+#define ZM_THREADS 512
 
-__global__ void __launch_bounds__(256, 2) k_inv_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles, int var0,
-                                                      int nfields, const double* __restrict__ in, long long in_fs,
-                                                      long long in_vs, double* __restrict__ phys,
-                                                      const double* __restrict__ parB) {
-  SB_DYN_SMEM(double, a);       // [nfields][2 parities][ZM_KK][ZM_CS]
-  const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = 8 / nzt;
+// One persistent CTA per SM, 16 warps = (4 level tiles) x (4 column groups); the [mode][column] tile of the
+// NEXT work item streams into the second smem buffer with cp.async (LDGSTS) while the tensor cores
+// work on the current one.  CB = bytes per async copy (16 when every row is 16-byte aligned, else 8).
+template <int CB>
+__global__ void __launch_bounds__(ZM_THREADS, 1) k_inv_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles,
+                                                             int nvars, int var0, int nfields,
+                                                             const double* __restrict__ in, long long in_fs,
+                                                             long long in_vs, double* __restrict__ phys,
+                                                             const double* __restrict__ parB) {
+  SB_DYN_SMEM(double, a);       // [2 buffers][nfields][2 parities][ZM_KK][ZM_CS]
+  const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = (ZM_THREADS / 32) / nzt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = lane & 3, i = lane >> 2;
   const int zt = warp % nzt, cg = warp / nzt;
-  const int v = blockIdx.y;
+  const int bufsz = nfields * 2 * ZM_KK * ZM_CS;
   double B[3][2][ZM_KT];
 #pragma unroll
   for (int m = 0; m < 3; ++m)
@@ -41,26 +49,43 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_mma(DevGrid g, const ZTile* __
     for (int p = 0; p < 2; ++p)
 #pragma unroll
       for (int kt = 0; kt < ZM_KT; ++kt) B[m][p][kt] = parB[((((m * 2 + p) * ZM_KT + kt) * 4) + zt) * 32 + lane];
-  for (int j = tid; j < nfields * 2 * ZM_KK * ZM_CS; j += 256) a[j] = 0.0;   // zero padding (modes >= bz) stays zero
+  for (int j = tid; j < 2 * bufsz; j += ZM_THREADS) a[j] = 0.0;   // zero padding (modes >= bz) stays zero
+  __syncthreads();
   const long long slotN = (long long)g.V * g.N;
-  double* const pv = phys + (long long)(var0 + v) * g.N;
   const int z0 = zt * 8 + 2 * q;                 // this lane's pair of levels (z0, z0+1) and mirror (zDim-2-z0, +1)
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const ZTile ztile = tiles[t];
-    __syncthreads();
-    for (int row = warp; row < nfields * bz; row += 8) {
+  const int nwork = ntiles * nvars;
+  constexpr int CPR = 256 / CB, CE = CB / 8;     // copies per 32-column row, doubles per copy
+  auto issue = [&](int w, double* dst) {
+    const int v = w / ntiles;
+    const ZTile ztile = tiles[w - v * ntiles];
+    const double* src = in + (long long)v * in_vs + ztile.out_base;
+    const int total = nfields * bz * CPR;
+    for (int c = tid; c < total; c += ZM_THREADS) {
+      const int row = c / CPR, col = (c - row * CPR) * CE;
       const int f = row / bz, zb = row - f * bz;
-      double val = 0.0;
-      if (lane < ztile.ncols)
-        val = in[(long long)f * in_fs + (long long)v * in_vs + ztile.out_base + (long long)zb * ztile.out_stride + lane];
-      a[((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS + lane] = val;
+      if (col < ztile.ncols) {
+        const double* sp = src + (long long)f * in_fs + (long long)zb * ztile.out_stride + col;
+        double* dp = dst + ((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS + col;
+        if (CB == 16) sb_cp_async16(dp, sp); else sb_cp_async8(dp, sp);
+      }
     }
-    __syncthreads();
+    sb_cp_commit();
+  };
+  int w = blockIdx.x, cur = 0;
+  if (w < nwork) issue(w, a);
+  for (; w < nwork; w += gridDim.x) {
+    sb_cp_wait<0>();
+    __syncthreads();            // tile w has landed; everybody is done with the other buffer
+    if (w + (int)gridDim.x < nwork) issue(w + gridDim.x, a + (cur ^ 1) * bufsz);
+    const int v = w / ntiles;
+    const ZTile ztile = tiles[w - v * ntiles];
+    const double* ab = a + cur * bufsz;
+    double* const pv = phys + (long long)(var0 + v) * g.N;
     for (int ct = cg; ct < 4; ct += ncg) {
       const int c = ct * 8 + i;
       const bool live = c < ztile.ncols;
       double* const o = pv + ((long long)ztile.hcol0 + c) * zDim;
-      const double* ap = a + q * ZM_CS + c;        // + (parity*ZM_KK + kt*4) * ZM_CS per fragment
+      const double* ap = ab + q * ZM_CS + c;        // + (parity*ZM_KK + kt*4) * ZM_CS per fragment
       // ---- field 0: value, d/dz, d2/dz2 share the A fragments
       {
         double E0[2] = {0, 0}, O0[2] = {0, 0}, E1[2] = {0, 0}, O1[2] = {0, 0}, E2[2] = {0, 0}, O2[2] = {0, 0};
@@ -102,6 +127,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_mma(DevGrid g, const ZTile* __
         }
       }
     }
+    cur ^= 1;
   }
 }
 
@@ -129,16 +155,131 @@ void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
                       int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
                       const double* parB) {
   ProfScope prof_scope_(c, "inv_z");
-  size_t smem = (size_t)nfields * 2 * ZM_KK * ZM_CS * sizeof(double);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_inv_z_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  }
-  int gx = ntiles < 148 * 2 * 8 ? ntiles : 148 * 2 * 8;
-  SB_LAUNCH(k_inv_z_mma, dim3(gx, nvars), dim3(256), smem, c.stream, g, tiles, ntiles, var0, nfields, in, in_fstride,
-            in_vstride, phys, parB);
-  cudaError_t e = cudaGetLastError();
+  const size_t smem = (size_t)2 * nfields * 2 * ZM_KK * ZM_CS * sizeof(double);
+  // 16-byte async copies need every [mode] row of every tile 16-byte aligned
+  const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0 && in_vstride % 2 == 0 && (g.has_l || g.rDim % 2 == 0);
+  auto kern = al16 ? k_inv_z_mma<16> : k_inv_z_mma<8>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int nwork = ntiles * nvars;
+  const int gx = nwork < 148 ? nwork : 148;
+  if (al16)
+    SB_LAUNCH(k_inv_z_mma<16>, dim3(gx), dim3(ZM_THREADS), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
+              in_fstride, in_vstride, phys, parB);
+  else
+    SB_LAUNCH(k_inv_z_mma<8>, dim3(gx), dim3(ZM_THREADS), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
+              in_fstride, in_vstride, phys, parB);
+  e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_z_mma launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+// =====================================================================================
+// Chebyshev analysis (forward): b[zb] = sum_z fwd[zb][z] u[z].  fwd[zb][zDim-1-z] = (-1)^zb fwd[zb][z], so
+// even modes see s = u[z] + u[zDim-1-z] and odd modes d = u[z] - u[zDim-1-z] over the lower half only.
+// D[8 columns x 8 modes] += A[8 columns x 4 levels] . B[4 levels x 8 modes]; warp = (column group, parity).
+// The [column][level] input tile is contiguous in HBM and arrives by cp.async (double buffered); the
+// same tile is mirrored into physical slot 0 (calcTendency's `physical .= var_np1`).
+// =====================================================================================
+#define FZ_US 68                // level stride of the u tile (== 4 mod 16, 16-byte aligned rows)
+#define FZ_THREADS 256
+
+__global__ void __launch_bounds__(FZ_THREADS) k_fwd_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles, int nvars,
+                                                          const double* __restrict__ in, long long in_vs,
+                                                          double* __restrict__ mirror, long long mirror_vs,
+                                                          double* __restrict__ out, long long out_vs,
+                                                          const double* __restrict__ fwdB) {
+  SB_DYN_SMEM(double, u);       // [2 buffers][32 columns][FZ_US]
+  const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nkt = zh >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane & 3, i = lane >> 2;
+  const int cg = warp & 3, par = warp >> 2;
+  double Bf[3][8];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) Bf[nt][kt] = fwdB[(((par * 3 + nt) * 8 + kt) * 32) + lane];
+  const int nwork = ntiles * nvars;
+  const int cpc = zDim >> 1;     // 16-byte copies per column
+  auto issue = [&](int w, double* dst) {
+    const int v = w / ntiles;
+    const ZTile zt = tiles[w - v * ntiles];
+    const double* src = in + (long long)v * in_vs + (long long)zt.hcol0 * zDim;
+    const int total = zt.ncols * cpc;
+    for (int c = tid; c < total; c += FZ_THREADS) {
+      const int col = c / cpc, z = (c - col * cpc) * 2;
+      sb_cp_async16(dst + col * FZ_US + z, src + (long long)col * zDim + z);
+    }
+    sb_cp_commit();
+  };
+  int w = blockIdx.x, cur = 0;
+  if (w < nwork) issue(w, u);
+  for (; w < nwork; w += gridDim.x) {
+    sb_cp_wait<0>();
+    __syncthreads();
+    if (w + (int)gridDim.x < nwork) issue(w + gridDim.x, u + (cur ^ 1) * 32 * FZ_US);
+    const int v = w / ntiles;
+    const ZTile zt = tiles[w - v * ntiles];
+    const double* ub = u + cur * 32 * FZ_US;
+    if (mirror) {
+      double* mv = mirror + (long long)v * mirror_vs + (long long)zt.hcol0 * zDim;
+      const int total = zt.ncols * cpc;
+      for (int c = tid; c < total; c += FZ_THREADS) {
+        const int col = c / cpc, z = (c - col * cpc) * 2;
+        *reinterpret_cast<double2*>(mv + (long long)col * zDim + z) = *reinterpret_cast<const double2*>(ub + col * FZ_US + z);
+      }
+    }
+    const int col = cg * 8 + i;
+    const double* uc = ub + col * FZ_US;
+    double D[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+      if (kt < nkt) {
+        const int z = kt * 4 + q;
+        const double x = uc[z], y = uc[zDim - 1 - z];
+        const double av = par ? x - y : x + y;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) sb_dmma(D[nt][0], D[nt][1], av, Bf[nt][kt]);
+      }
+    }
+    if (col < zt.ncols) {
+      double* o = out + (long long)v * out_vs + zt.out_base + col;
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const int zb0 = 2 * (nt * 8 + 2 * q) + par, zb1 = zb0 + 2;
+        if (zb0 < bz) o[(long long)zb0 * zt.out_stride] = D[nt][0];
+        if (zb1 < bz) o[(long long)zb1 * zt.out_stride] = D[nt][1];
+      }
+    }
+    cur ^= 1;
+  }
+}
+
+bool fwd_z_mma_ok(const DevGrid& g) { return (g.zDim == 16 || g.zDim == 32 || g.zDim == 64) && g.bz <= 48; }
+
+// fwdB[2 parities][3 n-tiles][8 k-tiles][32 lanes]: B fragment = fwd[mode = 2*(nt*8 + lane/4) + par][level = kt*4 + lane%4]
+void build_fwd_z_mma_tables(int zDim, int bz, const double* fwd /*[bz][zDim]*/, std::vector<double>& out) {
+  out.assign((size_t)2 * 3 * 8 * 32, 0.0);
+  for (int par = 0; par < 2; ++par)
+    for (int nt = 0; nt < 3; ++nt)
+      for (int kt = 0; kt < 8; ++kt)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int mode = 2 * (nt * 8 + lane / 4) + par, z = kt * 4 + lane % 4;
+          if (mode < bz && z < zDim / 2) out[(((size_t)(par * 3 + nt) * 8 + kt) * 32) + lane] = fwd[(size_t)mode * zDim + z];
+        }
+}
+
+void launch_fwd_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, const double* in,
+                      long long in_vstride, double* mirror, long long mirror_vstride, double* out, long long out_vstride,
+                      const double* fwdB) {
+  ProfScope prof_scope_(c, "fwd_z");
+  const size_t smem = (size_t)2 * 32 * FZ_US * sizeof(double);
+  const int nwork = ntiles * nvars;
+  const int gx = nwork < 148 * 4 ? nwork : 148 * 4;
+  SB_LAUNCH(k_fwd_z_mma, dim3(gx), dim3(FZ_THREADS), smem, c.stream, g, tiles, ntiles, nvars, in, in_vstride, mirror,
+            mirror_vstride, out, out_vstride, fwdB);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_z_mma launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;
 }
 

@@ -119,6 +119,11 @@ void build_inv_z_mma_tables(int zDim, int bz, const double* T0, const double* T1
 void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
                       int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
                       const double* parB);
+bool fwd_z_mma_ok(const DevGrid& g);
+void build_fwd_z_mma_tables(int zDim, int bz, const double* fwd, std::vector<double>& out);
+void launch_fwd_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, const double* in,
+                      long long in_vstride, double* mirror, long long mirror_vstride, double* out, long long out_vstride,
+                      const double* fwdB);
 bool inv_z_par_ok(const DevGrid& g, int nfields);
 void build_inv_z_par_tables(int zDim, int bz, const double* T0, const double* T1, const double* T2, std::vector<double>& out);
 void launch_inv_z_par(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
