@@ -87,6 +87,8 @@ struct sb_grid {
   std::vector<FftClass> classes;
   std::vector<std::vector<LWork>> fwork, iwork;
   std::vector<const LWork*> d_fwork, d_iwork;
+  std::vector<std::vector<LWork>> fwork2, iwork2;     // v2 persistent ring-FFT items (bigger row ranges)
+  std::vector<const LWork*> d_fwork2, d_iwork2;
   std::vector<const double*> d_tw, d_twp;
   RingPlan* d_plans = nullptr;
   double* d_blob = nullptr;
@@ -298,7 +300,23 @@ static void build_grid(sb_grid* G) {
       for (int row0 = 0; row0 < d.bz; row0 += nr) G->fwork[plans[r].cls].push_back(LWork{r, row0, std::min(nr, d.bz - row0), 0});
       for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork[plans[r].cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
     }
+    G->fwork2.assign(G->classes.size(), {});
+    G->iwork2.assign(G->classes.size(), {});
+    for (int r = d.rDim - 1; r >= 0; --r) {
+      const int L = plans[r].L, cls = plans[r].cls;
+      if (!G->classes[cls].fast) continue;
+      if (fft2_supported(L, true)) {
+        const int nr = fft2_rows_per_item(L, true);
+        for (int row0 = 0; row0 < d.bz; row0 += nr) G->fwork2[cls].push_back(LWork{r, row0, std::min(nr, d.bz - row0), 0});
+      }
+      if (fft2_supported(L, false)) {
+        const int nr = fft2_rows_per_item(L, false);
+        for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork2[cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
+      }
+    }
     for (size_t c = 0; c < G->classes.size(); ++c) {
+      G->d_fwork2.push_back(G->up(G->fwork2[c]));
+      G->d_iwork2.push_back(G->up(G->iwork2[c]));
       G->d_fwork.push_back(G->up(G->fwork[c]));
       G->d_iwork.push_back(G->up(G->iwork[c]));
       G->d_tw.push_back(G->up(G->classes[c].tw));
@@ -334,10 +352,10 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
     if (d.has_l && d.has_z) {
       grid_fwd_z(G, nv, inv, mir, SZ, szN);
       launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, SZ, szN,
-                   1, nullptr, 0, SL, slN);
+                   1, nullptr, 0, SL, slN, &G->fwork2, G->d_fwork2.data());
     } else if (d.has_l) {
       launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, inv, d.N,
-                   0, mir, d.N, SL, slN);
+                   0, mir, d.N, SL, slN, &G->fwork2, G->d_fwork2.data());
     } else {
       grid_fwd_z(G, nv, inv, mir, SL, slN);
     }
@@ -381,11 +399,11 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
     launch_inv_r(c, t, p, nv, P->spectralA + (long long)v0 * p.S, p.S, SL, sl_fs, slN, 0, v0);
     if (t.has_l && t.has_z) {
       launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
-                   slN, SZ, sz_fs, szN, 0, v0);
+                   slN, SZ, sz_fs, szN, 0, v0, &T->iwork2, T->d_iwork2.data());
       grid_inv_z(T, nv, v0, 5, SZ, sz_fs, szN);
     } else if (t.has_l) {
       launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
-                   slN, T->physical, 0, 0, 1, v0);
+                   slN, T->physical, 0, 0, 1, v0, &T->iwork2, T->d_iwork2.data());
     } else {
       grid_inv_z(T, nv, v0, 3, SL, sl_fs, slN);
     }

@@ -55,8 +55,11 @@ void host_fft_dif16(double* x, int L);   // natural -> the fast kernel's digit-r
 struct RingPlan {            // Bluestein plan of one ring (sub-DFT length m = n/4)
   int n = 0, m = 0, L = 0, cls = 0;
   long long off = 0;         // offset (in doubles) of this ring's tables in the blob
+  long long off2 = 0;        // offset of the pre-combined v2 tables (PQ[4][2m] | AF[4][2m]); 0 if absent
 };
-// blob layout per ring: chirp[2m] | wk[2m] | ph[2m] | FHp[2L]  (interleaved re,im)
+// blob layout per ring: chirp[2m] | wk[2m] | ph[2m] | FHp[2L] | P0,Q0,P1,Q1[2m each] | A0..A3[2m each]  (interleaved re,im)
+//   inverse prologue:  u[k] = conj(c_k D_k) P_h[k] + (c_{m-k} D_{m-k}) Q_h[k]          (sequence half h = 0,1)
+//   forward epilogue:  X[k] = b0[k] A0[k] + conj(b0[m-k]) A1[k] + b1[k] A2[k] + conj(b1[m-k]) A3[k]
 void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& classes,
                       std::vector<RingPlan>& plans, std::vector<double>& blob);
 // host reference of the device FFT (used to build FHp and by self-tests)
@@ -133,12 +136,23 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   const LWork* const* work, const std::vector<FftClass>& classes,
                   const double* const* tw, const double* const* twp, const RingPlan* plans, const double* blob, int nvars,
                   const double* in, long long in_vstride, int in_is_z, double* mirror, long long mirror_vstride,
-                  double* out, long long out_vstride);
+                  double* out, long long out_vstride,
+                  const std::vector<std::vector<LWork>>* hostwork2 = nullptr, const LWork* const* work2 = nullptr);
 void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes,
                   const double* const* tw, const double* const* twp, const RingPlan* plans, const double* blob, int nvars,
                   const double* in, long long in_fstride, long long in_vstride,
-                  double* out, long long out_fstride, long long out_vstride, int out_is_phys, int var0);
+                  double* out, long long out_fstride, long long out_vstride, int out_is_phys, int var0,
+                  const std::vector<std::vector<LWork>>* hostwork2 = nullptr, const LWork* const* work2 = nullptr);
+// v2 persistent ring FFT (sb_ringfft2.cu)
+bool fft2_supported(int L, bool forward);
+int fft2_rows_per_item(int L, bool forward);
+void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
+                   double* out, long long out_fs, long long out_vs, int out_is_phys, int var0);
+void launch_fwd_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs);
 void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride,
                   double* B, long long B_vstride);
 void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch, int nvars,

@@ -1,0 +1,403 @@
+// sb_ringfft2.cu -- persistent, table-resident Bluestein ring FFT (convolution lengths L = 256 .. 8192).
+//
+// Same mathematics as sb_ringfft.cu (ring of n = 4m points -> two packed complex DFT_m per real row,
+// each a chirp-z convolution of power-of-two length L >= 2m-1 done as radix-16 passes with 16 complex
+// values per thread), re-organised around what ncu showed on B200: the v1 kernel ran the FP64 pipe at
+// 33 % because every pass waited on an L2 round trip for its twiddles / chirp / FH tables (one CTA per
+// row, tables re-fetched each time) and both sequences of a CTA met at every __syncthreads.  Here
+//   * one persistent 512-thread CTA per SM walks a list of (ring, row-range) items; the class twiddles,
+//     the ring's pre-transformed chirp FH and the chirp itself live in shared memory for the whole item;
+//   * teams of T = L/16 threads are decoupled: they meet only on their own named barrier (bar.sync id, T);
+//   * L is a template parameter, so every pass stride / padded index is an immediate;
+//   * the zero-padded upper half of the Bluestein input and the unused upper half of its output are pruned
+//     from the first forward and the last inverse radix-16 pass;
+//   * the spectrum-side prologue (Hermitian symmetrisation, derivative factor, ring phase, 4-way
+//     decimation weights, chirp) is two complex multiplies against tables pre-combined on the host
+//     (sb_tables.cpp: P_h, Q_h), and so is the forward epilogue (A0..A3);  both work straight from
+//     registers, without the staging pass through shared memory.
+#include "sb_internal.hpp"
+#include "sb_fftcore.hpp"
+
+#include <cstdlib>
+#include <stdexcept>
+
+namespace sb {
+
+template <int LOG2L>
+struct RCfg {
+  static constexpr int L = 1 << LOG2L;
+  static constexpr int T = L / 16;                       // threads per team (one complex sequence)
+  static constexpr int NFULL = (LOG2L - 1) / 4;          // strided radix-16 passes
+  static constexpr int RF = 1 << (LOG2L - 4 * NFULL);    // register-local final radix
+  static constexpr int LP = L + L / 16;                  // padded team buffer (complex)
+  static constexpr int NT = 512;
+  static constexpr int NTEAMS = NT / T;
+  static constexpr int TW0 = 15 * T;                     // pass-0 twiddles (complex)
+  static constexpr int TWR = (NFULL >= 2 ? 15 * (L >> 8) : 0) + (NFULL >= 3 ? 15 * (L >> 12) : 0);
+  static constexpr int TWRP = (TWR + 1) & ~1;
+  static constexpr bool FH_SMEM = LOG2L <= 12;
+  static constexpr bool CH_SMEM = LOG2L <= 11;
+  static constexpr bool TW0_SMEM = LOG2L <= 11;
+  static constexpr size_t SMEM = sizeof(double2) * ((size_t)NTEAMS * LP + TWRP + (TW0_SMEM ? TW0 : 0) + (FH_SMEM ? L : 0) +
+                                                   (CH_SMEM ? L / 2 : 0));
+};
+
+template <int T>
+__device__ __forceinline__ void team_sync(int team) {
+  if (T >= 64) sb_bar_sync(1 + team, T);
+  else __syncwarp();
+}
+template <int T>
+__device__ __forceinline__ void pair_sync(int pair) {
+  if (2 * T >= 64) sb_bar_sync((T >= 64 ? 9 : 1) + pair, 2 * T);
+  else __syncwarp();
+}
+
+// circular convolution with the pre-transformed chirp.  In: v[n1] = element n1*T + tl, n1 < 8 (upper half zero).
+// Out: v[n1] = element n1*T + tl of the result for n1 < 8 (the upper half is not produced).
+template <int LOG2L>
+__device__ __forceinline__ void conv2(double2 (&v)[16], double2* buf, const double2* __restrict__ tw0,
+                                      const double2* __restrict__ twr, const double2* __restrict__ FHt, int tl, int team,
+                                      bool active) {
+  typedef RCfg<LOG2L> C;
+  constexpr int L = C::L, T = C::T;
+  // ---- forward strided passes
+#pragma unroll
+  for (int p = 0; p < C::NFULL; ++p) {
+    const int Ms = L >> (4 * (p + 1)), Lb = Ms << 4;
+    const int b = tl / Ms, j = tl - b * Ms, base = padi(b * Lb + j);
+    if (p > 0) {
+      team_sync<T>(team);
+      if (active) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) v[n] = buf[base + n * Ms + ((n * Ms) >> 4)];
+      }
+    }
+    if (active) {
+      if (p == 0) fft16_fwd_lo8(v); else fft16<false>(v);
+      const double2* tw = (p == 0 ? tw0 : twr + (p == 1 ? 0 : 15 * (L >> 8))) + j;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) v[k] = cm(v[k], tw[(k - 1) * Ms]);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) buf[base + k * Ms + ((k * Ms) >> 4)] = v[k];
+    }
+  }
+  team_sync<T>(team);
+  // ---- final forward pass, pointwise product, first inverse pass: all in registers
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = buf[tl * 17 + e];
+    fft_final<false>(v, C::RF);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = cm(v[e], FHt[e * T + tl]);
+    fft_final<true>(v, C::RF);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) buf[tl * 17 + e] = v[e];
+  }
+  // ---- inverse strided passes (reverse order)
+#pragma unroll
+  for (int p = C::NFULL - 1; p >= 0; --p) {
+    const int Ms = L >> (4 * (p + 1)), Lb = Ms << 4;
+    const int b = tl / Ms, j = tl - b * Ms, base = padi(b * Lb + j);
+    team_sync<T>(team);
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = buf[base + k * Ms + ((k * Ms) >> 4)];
+      const double2* tw = (p == 0 ? tw0 : twr + (p == 1 ? 0 : 15 * (L >> 8))) + j;
+#pragma unroll
+      for (int k = 1; k < 16; ++k) v[k] = cmc(v[k], tw[(k - 1) * Ms]);
+      fft16<true>(v);
+      if (p > 0) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) buf[base + n * Ms + ((n * Ms) >> 4)] = v[n];
+      }
+    }
+  }
+}
+
+// class tables -> shared memory (once per CTA); returns the pointers the passes use
+template <int LOG2L>
+__device__ __forceinline__ void load_class_tables(double2* sm, const double2* __restrict__ twp, const double2*& tw0,
+                                                  const double2*& twr, double2*& s_FH, double2*& s_ch) {
+  typedef RCfg<LOG2L> C;
+  double2* s_twr = sm + (size_t)C::NTEAMS * C::LP;
+  double2* s_tw0 = s_twr + C::TWRP;
+  s_FH = s_tw0 + (C::TW0_SMEM ? C::TW0 : 0);
+  s_ch = s_FH + (C::FH_SMEM ? C::L : 0);
+  for (int i = threadIdx.x; i < C::TWR; i += C::NT) s_twr[i] = twp[C::TW0 + i];
+  if (C::TW0_SMEM)
+    for (int i = threadIdx.x; i < C::TW0; i += C::NT) s_tw0[i] = twp[i];
+  tw0 = C::TW0_SMEM ? s_tw0 : twp;
+  twr = s_twr;
+}
+
+// =====================================================================================
+// inverse: spectra (value, d/dr, d2/dr2) -> 5 real rows; rows of a ring are rho = zb*5 + f
+// =====================================================================================
+template <int LOG2L>
+__global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
+                                                   const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
+                                                   const double* __restrict__ blob, const double* __restrict__ in,
+                                                   long long in_fs, long long in_vs, double* __restrict__ out,
+                                                   long long out_fs, long long out_vs, int out_is_phys, int var0) {
+  typedef RCfg<LOG2L> C;
+  constexpr int L = C::L, T = C::T;
+  SB_DYN_SMEM(double2, sm);
+  const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
+  double2* const buf = sm + (size_t)team * C::LP;
+  const double2 *tw0, *twr;
+  double2 *s_FH, *s_ch;
+  load_class_tables<LOG2L>(sm, twp, tw0, twr, s_FH, s_ch);
+  int cur_ring = -1;
+  const int total = nwork * nvars;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int item = w / nvars, v_ = w - item * nvars;
+    const LWork wk = work[item];
+    const RingPlan pl = plans[wk.r];
+    const int n = pl.n, m = pl.m;
+    const double2* chirp_g = reinterpret_cast<const double2*>(blob + pl.off);
+    const double2* FH_g = chirp_g + 3 * m;
+    const double2* PQ = reinterpret_cast<const double2*>(blob + pl.off2);
+    if (wk.r != cur_ring) {          // ring tables -> shared memory
+      __syncthreads();
+      if (C::FH_SMEM)
+        for (int i = tid; i < L; i += C::NT) s_FH[i] = FH_g[i];
+      if (C::CH_SMEM)
+        for (int i = tid; i < m; i += C::NT) s_ch[i] = chirp_g[i];
+      __syncthreads();
+      cur_ring = wk.r;
+    }
+    const double2* FHt = C::FH_SMEM ? s_FH : FH_g;
+    const double2* chirp = C::CH_SMEM ? s_ch : chirp_g;
+    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const int nseq = 2 * wk.nrows;
+    for (int s = team; s - team < nseq; s += C::NTEAMS) {
+      const bool active = s < nseq;
+      const int row = s >> 1, half = s & 1;
+      const int rho = wk.row0 + row;
+      const int zb = rho / 5, f = rho - zb * 5;
+      double2 v[16];
+      team_sync<T>(team);            // the team's previous sequence has finished reading buf
+      if (active) {
+        const int fin = (f < 3) ? f : 0;
+        const double* sp = in + (long long)fin * in_fs + (long long)v_ * in_vs + (long long)zb * g.W + woff;
+        const double2* Ph = PQ + (size_t)(2 * half) * m;
+        const double2* Qh = Ph + m;
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int k = n1 * T + tl;
+          double2 u = make_double2(0.0, 0.0);
+          if (k < m) {
+            const int km = k ? m - k : 0;
+            const double2 ck = k ? make_double2(sp[2 * k - 1], sp[2 * k]) : make_double2(sp[0], 0.0);
+            const double2 cq = km ? make_double2(sp[2 * km - 1], sp[2 * km]) : make_double2(sp[0], 0.0);
+            // derivative factor D(q): 1 | i q | -q^2 ;  X = conj(c_k D_k), Y = c_km D_km
+            double2 X, Y;
+            if (f < 3) {
+              X = make_double2(ck.x, -ck.y);
+              Y = cq;
+            } else if (f == 3) {
+              const double dk = (double)k, dq = (double)km;
+              X = make_double2(-dk * ck.y, -dk * ck.x);
+              Y = make_double2(-dq * cq.y, dq * cq.x);
+            } else {
+              const double sk = -(double)k * (double)k, sq = -(double)km * (double)km;
+              X = make_double2(sk * ck.x, -sk * ck.y);
+              Y = make_double2(sq * cq.x, sq * cq.y);
+            }
+            u = cm(X, Ph[k]) + cm(Y, Qh[k]);
+          }
+          v[n1] = u;
+        }
+      }
+      conv2<LOG2L>(v, buf, tw0, twr, FHt, tl, team, active);
+      if (active) {
+        double* orow;
+        if (out_is_phys)
+          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
+        else
+          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a = n1 * T + tl;
+          if (a < m) {
+            const double2 Y = cm(v[n1], chirp[a]);
+            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+          }
+        }
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// forward: real ring rows -> retained coefficients k = 0..ri.  Teams work in pairs (the two packed
+// sequences of one row); the raw convolution outputs are parked in the teams' own buffers and the
+// pair combines them with the pre-combined tables A0..A3.
+// =====================================================================================
+template <int LOG2L>
+__global__ void __launch_bounds__(512, 1) k_fwd_l2(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
+                                                   const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
+                                                   const double* __restrict__ blob, const double* __restrict__ in,
+                                                   long long in_vs, double* __restrict__ mirror, long long mirror_vs,
+                                                   double* __restrict__ out, long long out_vs) {
+  typedef RCfg<LOG2L> C;
+  constexpr int L = C::L, T = C::T, NPAIRS = C::NTEAMS / 2;
+  SB_DYN_SMEM(double2, sm);
+  const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
+  const int pair = team >> 1, half = team & 1;
+  double2* const buf = sm + (size_t)team * C::LP;
+  const double2* const buf0 = sm + (size_t)(2 * pair) * C::LP;
+  const double2* const buf1 = buf0 + C::LP;
+  const double2 *tw0, *twr;
+  double2 *s_FH, *s_ch;
+  load_class_tables<LOG2L>(sm, twp, tw0, twr, s_FH, s_ch);
+  int cur_ring = -1;
+  const int total = nwork * nvars;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int item = w / nvars, v_ = w - item * nvars;
+    const LWork wk = work[item];
+    const RingPlan pl = plans[wk.r];
+    const int n = pl.n, m = pl.m;
+    const double2* chirp_g = reinterpret_cast<const double2*>(blob + pl.off);
+    const double2* FH_g = chirp_g + 3 * m;
+    const double2* AF = reinterpret_cast<const double2*>(blob + pl.off2) + (size_t)4 * m;
+    if (wk.r != cur_ring) {
+      __syncthreads();
+      if (C::FH_SMEM)
+        for (int i = tid; i < L; i += C::NT) s_FH[i] = FH_g[i];
+      if (C::CH_SMEM)
+        for (int i = tid; i < m; i += C::NT) s_ch[i] = chirp_g[i];
+      __syncthreads();
+      cur_ring = wk.r;
+    }
+    const double2* FHt = C::FH_SMEM ? s_FH : FH_g;
+    const double2* chirp = C::CH_SMEM ? s_ch : chirp_g;
+    const long long hoff = g.ring_hoff[wk.r];
+    const double* src = in + (long long)v_ * in_vs + (long long)g.bz * hoff;
+    double* mir = mirror ? mirror + (long long)v_ * mirror_vs + (long long)g.bz * hoff : nullptr;
+    double* dst = out + (long long)v_ * out_vs + g.ring_woff[wk.r];
+    for (int row = pair; row - pair < wk.nrows; row += NPAIRS) {
+      const bool active = row < wk.nrows;
+      double2 v[16];
+      pair_sync<T>(pair);            // the pair has finished combining the previous row out of buf0 / buf1
+      if (active) {
+        const double* rp = src + (long long)(wk.row0 + row) * n + 2 * half;
+        double* mp = mir ? mir + (long long)(wk.row0 + row) * n + 2 * half : nullptr;
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a = n1 * T + tl;
+          double2 y = make_double2(0.0, 0.0);
+          if (a < m) {
+            const double2 x = *reinterpret_cast<const double2*>(rp + 4 * a);
+            if (mp) *reinterpret_cast<double2*>(mp + 4 * a) = x;
+            y = cm(x, chirp[a]);
+          }
+          v[n1] = y;
+        }
+      }
+      conv2<LOG2L>(v, buf, tw0, twr, FHt, tl, team, active);
+      team_sync<T>(team);            // every thread of the team has read its last-pass inputs
+      if (active) {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a = n1 * T + tl;
+          if (a < m) buf[a] = v[n1];
+        }
+      }
+      pair_sync<T>(pair);
+      if (active) {
+        const double invn = 1.0;      // 1/n is folded into A0..A3
+        (void)invn;
+        double* o = dst + (long long)(wk.row0 + row) * g.W;
+        for (int k = half * T + tl; k < m; k += 2 * T) {
+          const int km = k ? m - k : 0;
+          const double2 b0 = buf0[k], b0m = buf0[km], b1 = buf1[k], b1m = buf1[km];
+          double2 X = cm(b0, AF[k]) + cm(make_double2(b0m.x, -b0m.y), AF[m + k]);
+          X = X + cm(b1, AF[2 * m + k]) + cm(make_double2(b1m.x, -b1m.y), AF[3 * m + k]);
+          if (k == 0) {
+            o[0] = X.x;
+          } else {
+            o[2 * k - 1] = X.x;
+            o[2 * k] = X.y;
+          }
+        }
+      }
+    }
+  }
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+bool fft2_supported(int L, bool forward) {
+  static const char* env = std::getenv("SB_FFT");
+  if (env && std::string(env) == "v1") return false;   // A/B switch
+  return L >= 256 && L <= (forward ? 4096 : 8192);
+}
+
+int fft2_rows_per_item(int L, bool forward) {
+  const int T = L / 16, nteams = 512 / T;
+  const int wave = forward ? (nteams / 2) : (nteams > 1 ? nteams / 2 : 1);   // rows in flight per CTA
+  return 8 * (wave < 1 ? 1 : wave);
+}
+
+template <int LOG2L>
+static void launch_inv2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, const double* twp,
+                        const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs,
+                        long long in_vs, double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
+  const size_t smem = RCfg<LOG2L>::SMEM;
+  cudaError_t e = cudaFuncSetAttribute(k_inv_l2<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int total = nwork * nvars, gx = total < 148 ? total : 148;
+  SB_LAUNCH(k_inv_l2<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l2 launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
+                   double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
+#define SB_INV2(LG)                                                                                                    \
+  case (1 << LG):                                                                                                      \
+    launch_inv2<LG>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); \
+    break;
+  switch (L) {
+    SB_INV2(8) SB_INV2(9) SB_INV2(10) SB_INV2(11) SB_INV2(12) SB_INV2(13)
+    default: throw std::runtime_error("launch_inv_l2: unsupported convolution length");
+  }
+#undef SB_INV2
+}
+
+template <int LOG2L>
+static void launch_fwd2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, const double* twp,
+                        const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs,
+                        double* mirror, long long mirror_vs, double* out, long long out_vs) {
+  const size_t smem = RCfg<LOG2L>::SMEM;
+  cudaError_t e = cudaFuncSetAttribute(k_fwd_l2<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int total = nwork * nvars, gx = total < 148 ? total : 148;
+  SB_LAUNCH(k_fwd_l2<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_l2 launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+void launch_fwd_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs) {
+#define SB_FWD2(LG)                                                                                             \
+  case (1 << LG):                                                                                               \
+    launch_fwd2<LG>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs);     \
+    break;
+  switch (L) {
+    SB_FWD2(8) SB_FWD2(9) SB_FWD2(10) SB_FWD2(11) SB_FWD2(12)
+    default: throw std::runtime_error("launch_fwd_l2: unsupported convolution length");
+  }
+#undef SB_FWD2
+}
+
+}  // namespace sb

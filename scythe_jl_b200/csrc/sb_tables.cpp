@@ -7,6 +7,7 @@
 #include "sb_internal.hpp"
 
 #include <cmath>
+#include <complex>
 #include <cstring>
 #include <stdexcept>
 
@@ -443,6 +444,35 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
     } else {
       host_fft_dif(h.data(), L, classes[p.cls].tw.data());
       for (int i = 0; i < 2 * L; ++i) FH[i] = h[i] * invL;
+    }
+      if (classes[p.cls].fast) {
+      // v2 pre-combined tables (long double): see sb_internal.hpp for the formulas they implement
+      typedef std::complex<long double> cld;
+      const cld I(0.0L, 1.0L);
+      auto chirpL = [&](int a) { long long q = ((long long)a * a) % (2LL * m); return std::polar(1.0L, -kPiL * (long double)q / m); };
+      auto wL = [&](int a) { return std::polar(1.0L, -2.0L * kPiL * (long double)a / n); };
+      auto phL = [&](int a) { long long q2 = ((long long)a * (ri - 1)) % (2LL * n); return std::polar(1.0L, -kPiL * (long double)q2 / n); };
+      p.off2 = (long long)blob.size();
+      blob.resize(blob.size() + (size_t)16 * m);
+      double* PQ = blob.data() + p.off2;
+      double* AF = PQ + 8 * m;
+      for (int k = 0; k < m; ++k) {
+        const int km = k ? m - k : 0;
+        const cld ek = k ? 2.0L * std::conj(phL(k)) : cld(1.0L), ekm = km ? 2.0L * std::conj(phL(km)) : cld(1.0L);
+        const cld wk_ = wL(k), wkm = wL(km), ck = chirpL(k), ckm = chirpL(km);
+        for (int h = 0; h < 2; ++h) {
+          const cld sk = h ? std::conj(wk_ * wk_) : cld(1.0L), skm = h ? std::conj(wkm * wkm) : cld(1.0L);
+          const cld alpha = 0.5L * ek * sk * (cld(1.0L) + I * std::conj(wk_));
+          const cld beta = 0.5L * std::conj(ekm * skm) * (cld(1.0L) + I * wkm);
+          const cld P = std::conj(alpha) * ck, Q = std::conj(beta) * ck;
+          PQ[(size_t)(2 * h) * 2 * m + 2 * k] = (double)P.real(); PQ[(size_t)(2 * h) * 2 * m + 2 * k + 1] = (double)P.imag();
+          PQ[(size_t)(2 * h + 1) * 2 * m + 2 * k] = (double)Q.real(); PQ[(size_t)(2 * h + 1) * 2 * m + 2 * k + 1] = (double)Q.imag();
+        }
+        const cld pn = phL(k) / (long double)n, w1 = wk_, w2 = w1 * w1, w3 = w2 * w1;
+        const cld A[4] = {pn * 0.5L * (cld(1.0L) - I * w1) * ck, pn * 0.5L * (cld(1.0L) + I * w1) * std::conj(ckm),
+                          pn * 0.5L * (w2 - I * w3) * ck, pn * 0.5L * (w2 + I * w3) * std::conj(ckm)};
+        for (int j = 0; j < 4; ++j) { AF[(size_t)j * 2 * m + 2 * k] = (double)A[j].real(); AF[(size_t)j * 2 * m + 2 * k + 1] = (double)A[j].imag(); }
+      }
     }
   }
 }

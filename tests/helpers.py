@@ -56,6 +56,10 @@ def transform_cases():
         # no vertical BCs + zDim in {16, 32, 64}: the DMMA (tensor-core) Chebyshev synthesis path
         "RLZ_z16_nobc": G.GridParameters(geometry="RLZ", xmin=0, xmax=10, num_cells=3, zmin=0, zmax=5, zDim=16,
                                          BCL={"h": B.R1T1, "u": B.R1T0}, vars={"h": 1, "u": 2}),
+        # rings with m = ri+1 >= 65 use the persistent table-resident Bluestein kernels (L = 256)
+        "RL_24cells_fft2": G.GridParameters(geometry="RL", xmin=0, xmax=24, num_cells=24, BCL={"h": B.R1T1}, vars={"h": 1}),
+        "RLZ_22cells_fft2": G.GridParameters(geometry="RLZ", xmin=0, xmax=22, num_cells=22, zmin=0, zmax=5, zDim=8,
+                                             BCL={"h": B.R1T1}, vars={"h": 1}),
         "RZ_z32_nobc": G.GridParameters(geometry="RZ", xmin=0, xmax=10, num_cells=13, zmin=0, zmax=5, zDim=32,
                                         vars={"s": 1, "w": 2}),
     }
