@@ -691,11 +691,72 @@ __global__ void __launch_bounds__(RQ) k_fwd_r(DevGrid g, const double* __restric
   }
 }
 
+// chunked version: thread = (spline column, 32 consecutive coefficients).  b_m only needs cells m-3..m, so a
+// chunk re-reads 3 cells of overlap and the radial loop of 1000 dependent iterations becomes 11x more
+// CTAs with 105 independent coalesced loads each; all-zero chunks (column beyond every ring's wavenumber
+// range) are written without touching the input.
+#define RM 32
+__global__ void __launch_bounds__(RQ) k_fwd_r2(DevGrid g, int nvars, const double* __restrict__ in, long long in_vs,
+                                               double* __restrict__ B, long long B_vs) {
+  __shared__ double tile[RQ][RM + 1];
+  __shared__ long long s_wo[3 * (RM + 3) + 1];
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * RQ, q = q0 + tid;
+  const int m0 = blockIdx.y * RM;
+  const int zb = blockIdx.z / nvars, v = blockIdx.z - zb * nvars;
+  const int M = g.b_rDim, nc = g.num_cells;
+  const int mcnt = (M - m0 < RM) ? M - m0 : RM;
+  const int c_lo = (m0 - 3 > 0) ? m0 - 3 : 0;
+  const int c_hi = (m0 + RM - 1 < nc - 1) ? m0 + RM - 1 : nc - 1;       // inclusive
+  for (int i = tid; i <= 3 * (c_hi - c_lo + 1); i += RQ) s_wo[i] = g.ring_woff[3 * c_lo + i];
+  __syncthreads();
+  const double* plane = in + (long long)v * in_vs + (long long)zb * g.W;
+  double* Bv = B + (long long)v * B_vs;
+  const int nrings = 3 * (c_hi - c_lo + 1);
+  const int ncol_max = nrings > 0 ? (int)(s_wo[nrings] - s_wo[nrings - 1]) : 0;   // widest ring of the chunk
+  if (q0 < ncol_max) {
+    double w[3][4];
+#pragma unroll
+    for (int mu = 0; mu < 3; ++mu)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[mu][j] = g.wq[mu] * g.phi[0][mu][j];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int cc = m0 - 3; cc < m0 + mcnt; ++cc) {
+      if (cc >= c_lo && cc <= c_hi) {
+#pragma unroll
+        for (int mu = 0; mu < 3; ++mu) {
+          const int ir = 3 * (cc - c_lo) + mu;
+          const long long wo = s_wo[ir];
+          const int ncol_r = (int)(s_wo[ir + 1] - wo);
+          const double f = (q < ncol_r) ? plane[wo + q] : 0.0;
+          a0 = fma(w[mu][0], f, a0); a1 = fma(w[mu][1], f, a1); a2 = fma(w[mu][2], f, a2); a3 = fma(w[mu][3], f, a3);
+        }
+      }
+      if (cc >= m0) tile[tid][cc - m0] = a0;
+      a0 = a1; a1 = a2; a2 = a3; a3 = 0.0;
+    }
+  } else {
+    for (int j = 0; j < mcnt; ++j) tile[tid][j] = 0.0;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int qq = warp; qq < RQ; qq += RQ / 32) {
+    if (q0 + qq < g.ncolp && lane < mcnt)
+      Bv[((long long)zb * g.ncolp + q0 + qq) * M + m0 + lane] = tile[qq][lane];
+  }
+}
+
 void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride, double* B,
                   long long B_vstride) {
   ProfScope prof_scope_(c, "fwd_r");
-  dim3 grid((g.ncolp + RQ - 1) / RQ, g.bz, nvars);
-  SB_LAUNCH(k_fwd_r, grid, dim3(RQ), 0, c.stream, g, in, in_vstride, B, B_vstride);
+  static const bool v1 = std::getenv("SB_RADIAL_V1") != nullptr;   // A/B switch
+  if (v1) {
+    dim3 grid((g.ncolp + RQ - 1) / RQ, g.bz, nvars);
+    SB_LAUNCH(k_fwd_r, grid, dim3(RQ), 0, c.stream, g, in, in_vstride, B, B_vstride);
+  } else {
+    dim3 grid((g.ncolp + RQ - 1) / RQ, (g.b_rDim + RM - 1) / RM, g.bz * nvars);
+    SB_LAUNCH(k_fwd_r2, grid, dim3(RQ), 0, c.stream, g, nvars, in, in_vstride, B, B_vstride);
+  }
   SB_CHECK_LAUNCH();
   count(c);
 }
@@ -753,13 +814,73 @@ __global__ void __launch_bounds__(RQ) k_inv_r(DevGrid t, DevGrid p, const double
   }
 }
 
+// chunked version: thread = (spline column, 32 consecutive cells); the 35 coefficients it needs arrive
+// through a transposed shared-memory tile, the 9 outputs per cell leave coalesced along the ring.
+__global__ void __launch_bounds__(RQ) k_inv_r2(DevGrid t, DevGrid p, int nvars, const double* __restrict__ A, long long A_vs,
+                                               double* __restrict__ out, long long out_fs, long long out_vs,
+                                               int out_is_phys, int var0) {
+  __shared__ double tile[RQ][RM + 5];          // odd row stride: the per-thread column walk is conflict-free
+  __shared__ long long s_wo[3 * RM + 1];
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * RQ, q = q0 + tid;
+  const int c0 = blockIdx.y * RM;              // first cell of the chunk
+  const int zb = blockIdx.z / nvars, v = blockIdx.z - zb * nvars;
+  const int nc = t.num_cells, Mp = p.b_rDim, cofs = t.coefOffset - p.coefOffset;
+  const int ccnt = (nc - c0 < RM) ? nc - c0 : RM;
+  for (int i = tid; i <= 3 * ccnt; i += RQ) s_wo[i] = t.ring_woff[3 * c0 + i];
+  __syncthreads();
+  const int ncol_max = (int)(s_wo[3 * ccnt] - s_wo[3 * ccnt - 1]);
+  if (q0 >= ncol_max) return;                  // no ring of this chunk carries these columns
+  const double* Av = A + (long long)v * A_vs;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int need = ccnt + 3;
+  for (int qq = warp; qq < RQ; qq += RQ / 32) {
+    const bool ok = q0 + qq < t.ncolp;
+    const double* src = Av + ((long long)zb * p.ncolp + q0 + qq) * Mp + cofs + c0;
+    tile[qq][lane] = (ok && lane < need) ? src[lane] : 0.0;
+    if (lane < 4) tile[qq][32 + lane] = (ok && 32 + lane < need) ? src[32 + lane] : 0.0;
+  }
+  __syncthreads();
+  if (q >= t.ncolp) return;
+  double a0 = tile[tid][0], a1 = tile[tid][1], a2 = tile[tid][2], a3;
+  for (int c = 0; c < ccnt; ++c) {
+    a3 = tile[tid][c + 3];
+#pragma unroll
+    for (int mu = 0; mu < 3; ++mu) {
+      const long long wo = s_wo[3 * c + mu];
+      const int ncol_r = (int)(s_wo[3 * c + mu + 1] - wo);
+      if (q < ncol_r) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double s = t.phi[d][mu][0] * a0;
+          s = fma(t.phi[d][mu][1], a1, s);
+          s = fma(t.phi[d][mu][2], a2, s);
+          s = fma(t.phi[d][mu][3], a3, s);
+          if (out_is_phys)
+            out[((long long)d * t.V + var0 + v) * t.N + 3 * (c0 + c) + mu] = s;
+          else
+            out[(long long)d * out_fs + (long long)v * out_vs + (long long)zb * t.W + wo + q] = s;
+        }
+      }
+    }
+    a0 = a1; a1 = a2; a2 = a3;
+  }
+}
+
 void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch, int nvars, const double* A,
                   long long A_vstride, double* out, long long out_fstride, long long out_vstride, int out_is_phys,
                   int var0) {
   ProfScope prof_scope_(c, "inv_r");
-  dim3 grid((tile.ncolp + RQ - 1) / RQ, tile.bz, nvars);
-  SB_LAUNCH(k_inv_r, grid, dim3(RQ), 0, c.stream, tile, patch, A, A_vstride, out, out_fstride, out_vstride,
-            out_is_phys, var0);
+  static const bool v1 = std::getenv("SB_RADIAL_V1") != nullptr;   // A/B switch
+  if (v1) {
+    dim3 grid((tile.ncolp + RQ - 1) / RQ, tile.bz, nvars);
+    SB_LAUNCH(k_inv_r, grid, dim3(RQ), 0, c.stream, tile, patch, A, A_vstride, out, out_fstride, out_vstride,
+              out_is_phys, var0);
+  } else {
+    dim3 grid((tile.ncolp + RQ - 1) / RQ, (tile.num_cells + RM - 1) / RM, tile.bz * nvars);
+    SB_LAUNCH(k_inv_r2, grid, dim3(RQ), 0, c.stream, tile, patch, nvars, A, A_vstride, out, out_fstride, out_vstride,
+              out_is_phys, var0);
+  }
   SB_CHECK_LAUNCH();
   count(c);
 }
@@ -827,6 +948,104 @@ __global__ void k_spline_solve(DevSplineFactor f, int ncols, int qc, const doubl
   }
 }
 
+// streaming version: thread = column, but only a [128 columns][32 coefficients] tile lives in shared memory.
+// Forward substitution walks the tiles upward writing y to A, back substitution walks them downward
+// (A is read back: 4S instead of 2S of traffic, but 10x more columns in flight per SM than the
+// whole-column kernel above, whose 172 KB of shared memory allowed 64 columns per SM).
+#define SSQ 128
+__global__ void __launch_bounds__(SSQ) k_spline_solve2(DevSplineFactor f, int ncols, int chol_in_smem,
+                                                       const double* __restrict__ B, double* __restrict__ A) {
+  __shared__ double tile[SSQ][33];
+  SB_DYN_SMEM(double, s_chol);
+  const int M = f.M, n = f.nfree, rL = f.rL, rR = f.rR;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c0 = (long long)blockIdx.x * SSQ;
+  const int nq = (int)((ncols - c0 < SSQ) ? ncols - c0 : SSQ);
+  const bool valid = tid < nq;
+  const double* chol = f.chol;
+  if (chol_in_smem) {
+    for (int i = tid; i < 4 * n; i += SSQ) s_chol[i] = f.chol[i];
+    chol = s_chol;
+  }
+  const int ntile = (M + 31) / 32;
+  const int last = M - 1 - rR;                 // last free index
+  double bM1 = 0.0, bM2 = 0.0, bl0 = 0.0, bl1 = 0.0;
+  if (valid) {
+    bM1 = B[(c0 + tid) * M + M - 1];
+    if (M >= 2) bM2 = B[(c0 + tid) * M + M - 2];
+  }
+  // ---------------- fold + forward substitution  L y = Gamma b
+  double y1 = 0, y2 = 0, y3 = 0;
+  for (int t = 0; t < ntile; ++t) {
+    const int m0 = t * 32, cnt = (M - m0 < 32) ? M - m0 : 32;
+    __syncthreads();
+    for (int qq = warp; qq < SSQ; qq += SSQ / 32)
+      if (qq < nq && lane < cnt) tile[qq][lane] = B[(c0 + qq) * M + m0 + lane];
+    __syncthreads();
+    if (valid) {
+      for (int j = 0; j < cnt; ++j) {
+        const int i = m0 + j;
+        double s = tile[tid][j];
+        if (i < rL) { if (i == 0) bl0 = s; else if (i == 1) bl1 = s; continue; }
+        if (i > last) continue;
+        const int fi = i - rL;
+        if (rL == 1) { if (fi == 0) s += f.foldL[0] * bl0; else if (fi == 1) s += f.foldL[1] * bl0; }
+        else if (rL == 2) { if (fi == 0) s += f.foldL[0] * bl0 + f.foldL[1] * bl1; }
+        if (rR == 1) { if (i == M - 2) s += f.foldR[0] * bM1; else if (i == M - 3) s += f.foldR[1] * bM1; }
+        else if (rR == 2) { if (i == M - 3) s += f.foldR[0] * bM1 + f.foldR[1] * bM2; }
+        const double* l = chol + 4 * fi;
+        s = fma(-l[1], y1, s); s = fma(-l[2], y2, s); s = fma(-l[3], y3, s);
+        s *= l[0];
+        tile[tid][j] = s;
+        y3 = y2; y2 = y1; y1 = s;
+      }
+    }
+    __syncthreads();
+    for (int qq = warp; qq < SSQ; qq += SSQ / 32)
+      if (qq < nq && lane < cnt) A[(c0 + qq) * M + m0 + lane] = tile[qq][lane];
+  }
+  // ---------------- back substitution  L^T x = y, unfold a = Gamma^T x
+  double x1 = 0, x2 = 0, x3 = 0, xa = 0, xb = 0;      // xa = x[n-1], xb = x[n-2]
+  for (int t = ntile - 1; t >= 0; --t) {
+    const int m0 = t * 32, cnt = (M - m0 < 32) ? M - m0 : 32;
+    __syncthreads();
+    for (int qq = warp; qq < SSQ; qq += SSQ / 32)
+      if (qq < nq && lane < cnt) tile[qq][lane] = A[(c0 + qq) * M + m0 + lane];
+    __syncthreads();
+    if (valid) {
+      for (int j = cnt - 1; j >= 0; --j) {
+        const int i = m0 + j;
+        if (i > last || i < rL) continue;
+        const int fi = i - rL;
+        double s = tile[tid][j];
+        if (fi + 1 < n) s = fma(-chol[4 * (fi + 1) + 1], x1, s);
+        if (fi + 2 < n) s = fma(-chol[4 * (fi + 2) + 2], x2, s);
+        if (fi + 3 < n) s = fma(-chol[4 * (fi + 3) + 3], x3, s);
+        s *= chol[4 * fi];
+        tile[tid][j] = s;
+        if (fi == n - 1) xa = s;
+        if (fi == n - 2) xb = s;
+        x3 = x2; x2 = x1; x1 = s;
+      }
+      if (t == 0) {   // x1 = x[0], x2 = x[1] here
+        if (rL == 1) tile[tid][0] = f.foldL[0] * x1 + f.foldL[1] * x2;
+        else if (rL == 2) { tile[tid][0] = f.foldL[0] * x1; tile[tid][1] = f.foldL[1] * x1; }
+        else if (rL == 3) { tile[tid][0] = 0.0; tile[tid][1] = 0.0; tile[tid][2] = 0.0; }
+      }
+    }
+    __syncthreads();
+    for (int qq = warp; qq < SSQ; qq += SSQ / 32)
+      if (qq < nq && lane < cnt) A[(c0 + qq) * M + m0 + lane] = tile[qq][lane];
+  }
+  __syncthreads();
+  if (valid) {        // right-edge unfold: the tiles above stored stale values there
+    double* a = A + (c0 + tid) * M;
+    if (rR == 1) a[M - 1] = f.foldR[0] * xa + f.foldR[1] * xb;
+    else if (rR == 2) { a[M - 1] = f.foldR[0] * xa; a[M - 2] = f.foldR[1] * xa; }
+    else if (rR == 3) { a[M - 1] = 0.0; a[M - 2] = 0.0; a[M - 3] = 0.0; }
+  }
+}
+
 __global__ void k_spline_dense(DevSplineFactor f, int ncols, const double* __restrict__ B, double* __restrict__ A) {
   const int M = f.M;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -850,6 +1069,11 @@ void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFa
     if (f.periodic) {
       long long tot = (long long)ncols * f.M;
       SB_LAUNCH(k_spline_dense, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, c.stream, f, ncols, Bv, Av);
+    } else if (!std::getenv("SB_RADIAL_V1") && f.nfree >= 3) {
+      const int in_smem = (size_t)4 * f.nfree * 8 <= 96 * 1024;
+      size_t smem = in_smem ? (size_t)4 * f.nfree * 8 : 0;
+      opt_in_smem(k_spline_solve2, smem);
+      SB_LAUNCH(k_spline_solve2, dim3((ncols + SSQ - 1) / SSQ), dim3(SSQ), smem, c.stream, f, ncols, in_smem, Bv, Av);
     } else {
       int Ms = f.M | 1;
       int qc = 64;

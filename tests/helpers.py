@@ -43,6 +43,19 @@ def transform_cases():
                                         BCL={"a": B.R0, "b": B.R1T0, "c": B.R1T2, "d": B.R2T10, "e": B.R3},
                                         BCR={"a": B.R1T1, "b": B.R2T20, "c": B.R0, "d": B.R1T0, "e": B.R3},
                                         vars={"a": 1, "b": 2, "c": 3, "d": 4, "e": 5}),
+        # b_rDim = 103 > 3 tiles of 32: streaming banded solve / chunked radial kernels across tile seams
+        "R_100cells_bcs": G.GridParameters(geometry="R", xmin=0, xmax=10, num_cells=100,
+                                           BCL={"a": B.R0, "b": B.R1T0, "c": B.R1T2, "d": B.R2T10, "e": B.R3, "g": B.R1T1},
+                                           BCR={"a": B.R1T1, "b": B.R2T20, "c": B.R0, "d": B.R1T0, "e": B.R3, "g": B.R2T10},
+                                           vars={"a": 1, "b": 2, "c": 3, "d": 4, "e": 5, "g": 6}),
+        "R_61cells_bcs": G.GridParameters(geometry="R", xmin=0, xmax=10, num_cells=61,
+                                          BCL={"a": B.R3, "b": B.R2T20}, BCR={"a": B.R2T20, "b": B.R1T1}, vars={"a": 1, "b": 2}),
+        # b_rDim = 66 / 65: the right-edge BC fold straddles the last two 32-coefficient tiles
+        "R_63cells_bcs": G.GridParameters(geometry="R", xmin=0, xmax=10, num_cells=63,
+                                          BCL={"a": B.R1T0, "b": B.R0, "c": B.R1T1}, BCR={"a": B.R2T10, "b": B.R1T2, "c": B.R3},
+                                          vars={"a": 1, "b": 2, "c": 3}),
+        "R_62cells_bcs": G.GridParameters(geometry="R", xmin=0, xmax=10, num_cells=62,
+                                          BCL={"a": B.R2T20, "b": B.R1T1}, BCR={"a": B.R2T20, "b": B.R1T0}, vars={"a": 1, "b": 2}),
         "RL": G.GridParameters(geometry="RL", xmin=0, xmax=10, num_cells=6, BCL={"h": B.R1T1, "u": B.R1T0},
                                BCR={"h": B.R0, "u": B.R1T1}, vars={"h": 1, "u": 2}),
         "RL_tile": G.GridParameters(geometry="RL", xmin=3, xmax=7, num_cells=4, vars={"h": 1}, spectralIndexL=4),
