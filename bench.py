@@ -173,6 +173,8 @@ def workload_config(ngpus, cells_per_tile):
     return {"workload": "C4 RLZ LinearAdvectionRLZ" if ngpus == 1 else "C5 RLZ radius-scaled, one C4-sized tile per GPU",
             "geometry": "RLZ", "num_cells": total_cells, "zDim": ZDIM, "b_zDim": 43, "vars": NVARS,
             "equation_set": "LinearAdvectionRLZ", "tiles": ngpus, "ts": TS,
+            "exchange": ("none (one tile)" if ngpus == 1 else
+                         "z-mode planes of the spline solve dealt over ranks; NCCL send/recv of tile-sized slabs, no collective"),
             "l2": "working set >> 126 MB L2 (physical 21.7 GB/GPU); no flush needed",
             "units": "C4-equivalent (128.9 M-point) tile-timesteps, summed over ranks"}
 

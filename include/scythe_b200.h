@@ -201,6 +201,21 @@ int64_t sb_model_launch_count(sb_model_t m);
 /* ncclGetUniqueId -> 128 bytes to ship to the other ranks (the reference ships RemoteChannels the
  * same way, src/semiimplicit.jl:205-219) */
 int sb_comm_unique_id(void* out128);
+/* ---- plane-distributed splineTransform! (SURVEY 8e option B) --------------------------------
+ * The reference replicates the whole-patch solve on every worker (src/semiimplicit.jl:285) after
+ * summing the tiles' B through one SharedArray (:323-329).  Across GPUs that is an all-reduce of the
+ * whole patch; instead the (z-mode, wavenumber) columns are dealt out by z-mode plane.  After
+ * sb_model_colsolve_init, sb_model_advance_tiles / sb_model_tendency leave B tile-local, the caller
+ * (or sb_model_exchange with the library's own communicator) moves the message buffers named by
+ * sb_model_colsolve_buffer, sb_model_colsolve_solve overlap-adds + solves + packs on the owner, and the
+ * tiles evaluate their own slice of A.  what: 0 send-B (local tile -> owner peer), 1 recv-B (tile ->
+ * me), 2 send-A (me -> tile), 3 recv-A (owner peer -> local tile), 4 my solved planes, 5 owner
+ * peer's planes inside the replicated patch A (only needed for output).  Buffers are per variable v. */
+int sb_model_colsolve_init(sb_model_t m, int32_t rank, int32_t nranks);
+int sb_model_colsolve_planes(sb_model_t m, int32_t* z0 /* [nranks+1] */, int32_t n);
+int sb_model_colsolve_buffer(sb_model_t m, int32_t what, int32_t tile, int32_t v, int32_t peer, void** ptr, int64_t* count);
+int sb_model_colsolve_solve(sb_model_t m);
+int sb_model_colsolve_publish(sb_model_t m);
 int sb_model_comm_init(sb_model_t m, const void* id128, int32_t rank, int32_t nranks);
 
 /* ---- timing on the handle's stream (CUDA events) ------------------------------------------ */

@@ -88,6 +88,12 @@ PROTOTYPES = {
     "sb_model_sync": (C.c_int, [model_t]),
     "sb_model_launch_count": (C.c_int64, [model_t]),
     "sb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "sb_model_colsolve_init": (C.c_int, [model_t, C.c_int32, C.c_int32]),
+    "sb_model_colsolve_planes": (C.c_int, [model_t, c_i32p, C.c_int32]),
+    "sb_model_colsolve_buffer": (C.c_int, [model_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_int64)]),
+    "sb_model_colsolve_solve": (C.c_int, [model_t]),
+    "sb_model_colsolve_publish": (C.c_int, [model_t]),
     "sb_model_comm_init": (C.c_int, [model_t, C.c_void_p, C.c_int32, C.c_int32]),
     "sb_timer_start": (C.c_int, [grid_t]),
     "sb_timer_stop": (C.c_int, [grid_t, C.POINTER(C.c_float)]),

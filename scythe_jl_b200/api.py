@@ -399,9 +399,16 @@ class Model:
             g.resident = True
             self.tiles.append(g)
         self.t = 0
-        self.exchange = exchange or os.environ.get("SB_EXCHANGE", "torch")
+        # exchange: "columns" = plane-distributed spline solve, messages moved by torch.distributed P2P
+        #           "columns-native" = same, messages moved by the library's own NCCL communicator
+        #           "torch" / "native" = all-reduce of the whole shared B + replicated solve (the reference's scheme)
+        self.exchange = exchange or os.environ.get("SB_EXCHANGE", "columns" if (self.dist is not None and self.world > 1) else "torch")
         self._shared_tensor = None
-        if self.dist is not None and self.world > 1 and self.exchange == "native":
+        self._views = {}
+        self.columns = self.exchange in ("columns", "columns-native")
+        if self.columns:
+            self.lib.check(self.lib.sb_model_colsolve_init(self.handle, self.rank, self.world))
+        if self.dist is not None and self.world > 1 and self.exchange in ("native", "columns-native"):
             self._init_native_comm()
 
     # -- multi-process plumbing -------------------------------------------------------
@@ -418,21 +425,71 @@ class Model:
         uid = (C.c_ubyte * 128)(*t.cpu().tolist())
         self.lib.check(self.lib.sb_model_comm_init(self.handle, uid, self.rank, self.world))
 
+    def _as_tensor(self, ptr: int, n: int):
+        """zero-copy torch view of a library buffer (device memory; host memory in the CPU emulation build)"""
+        import torch
+        if self.dist.get_backend() == "nccl":
+            class _Wrap:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+            if n == 0:
+                return torch.empty(0, dtype=torch.float64, device=f"cuda:{torch.cuda.current_device()}")
+            return torch.as_tensor(_Wrap(), device=f"cuda:{torch.cuda.current_device()}")
+        if n == 0:
+            return torch.empty(0, dtype=torch.float64)
+        buf = (C.c_double * n).from_address(ptr)
+        return torch.from_numpy(np.ctypeslib.as_array(buf))
+
     def _shared_as_tensor(self):
         """torch view of the device-resident shared B buffer (zero copy)."""
         if self._shared_tensor is None:
-            import torch
             ptr, n = C.c_void_p(), C.c_int64()
             self.lib.check(self.lib.sb_grid_device_ptr(self.patch.handle, 1, C.byref(ptr), C.byref(n)))
-            if self.dist.get_backend() == "nccl":
-                class _Wrap:
-                    __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f8", "data": (ptr.value, False),
-                                                "version": 2}
-                self._shared_tensor = torch.as_tensor(_Wrap(), device=f"cuda:{torch.cuda.current_device()}")
-            else:  # CPU emulation build under gloo: the "device" buffer is host memory
-                buf = (C.c_double * n.value).from_address(ptr.value)
-                self._shared_tensor = torch.from_numpy(np.ctypeslib.as_array(buf))
+            self._shared_tensor = self._as_tensor(ptr.value, n.value)
         return self._shared_tensor
+
+    def _msg(self, what: int, tile: int, v: int, peer: int):
+        key = (what, tile, v, peer)
+        if key not in self._views:
+            ptr, n = C.c_void_p(), C.c_int64()
+            self.lib.check(self.lib.sb_model_colsolve_buffer(self.handle, what, tile, v, peer, C.byref(ptr), C.byref(n)))
+            self._views[key] = self._as_tensor(ptr.value, n.value)
+        return self._views[key]
+
+    def _p2p(self, direction: int):
+        """one message set of the plane-distributed solve: 0 = tiles' B chunks to the plane owners,
+        1 = solved chunks back (torch.distributed batch_isend_irecv = one NCCL group)."""
+        dist, V, per = self.dist, self.patch.V, self.num_tiles // self.world
+        ops = []
+        for t in range(self.num_tiles):
+            owner = t // per
+            for v in range(V):
+                if owner == self.rank:
+                    for k in range(self.world):
+                        if k == self.rank:
+                            continue
+                        buf = self._msg(3 if direction else 0, t, v, k)
+                        if buf.numel() == 0:
+                            continue
+                        ops.append(dist.P2POp(dist.irecv if direction else dist.isend, buf, k))
+                else:
+                    buf = self._msg(2 if direction else 1, t, v, self.rank)
+                    if buf.numel() == 0:
+                        continue
+                    ops.append(dist.P2POp(dist.isend if direction else dist.irecv, buf, owner))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _gather_patch_A(self):
+        """output only: every owner's solved planes -> the replicated patch A"""
+        self.lib.check(self.lib.sb_model_colsolve_publish(self.handle))
+        if self.dist is None or self.world == 1:
+            return
+        for k in range(self.world):
+            for v in range(self.patch.V):
+                buf = self._msg(5, 0, v, k)
+                if buf.numel():
+                    self.dist.broadcast(buf, src=k)
 
     # -- reference driver ---------------------------------------------------------------
     def initialize(self, ic: np.ndarray):
@@ -446,9 +503,13 @@ class Model:
         if self.dist is None or self.world == 1:
             self.lib.check(self.lib.sb_model_step(self.handle, self.t))
             return
+        if self.exchange == "columns-native":
+            self.lib.check(self.lib.sb_model_step(self.handle, self.t))
+            return
         self.lib.check(self.lib.sb_model_advance_tiles(self.handle, self.t))
         self._exchange()
-        self.lib.check(self.lib.sb_model_spline_transform(self.handle))
+        if not self.columns:
+            self.lib.check(self.lib.sb_model_spline_transform(self.handle))
 
     def run(self, nsteps: int):
         if self.dist is None or self.world == 1:
@@ -460,6 +521,8 @@ class Model:
 
     def output(self, to_host: bool = True) -> np.ndarray | None:
         """patch.spectral <- A; tileTransform!(patch); checkCFL  (src/semiimplicit.jl:289-291)."""
+        if self.columns:
+            self._gather_patch_A()
         if to_host:
             out = np.empty((self.patch.N, self.patch.V, self.patch.D), order="F")
             rc = self.lib.sb_model_output(self.handle, _ptr(out))
@@ -491,15 +554,19 @@ class Model:
     def _exchange(self):
         if self.dist is None or self.world == 1:
             return
-        if self.exchange == "native":
+        if self.exchange in ("native", "columns-native"):
             self.lib.check(self.lib.sb_model_exchange(self.handle))
+        elif self.columns:
+            self._p2p(0)
+            self.lib.check(self.lib.sb_model_colsolve_solve(self.handle))
+            self._p2p(1)
         else:
             self.dist.all_reduce(self._shared_as_tensor())
 
     def cycle(self):
         """One model_loop iteration entered at calcTendency (see sb_model_cycle)."""
         self.t += 1
-        if self.dist is None or self.world == 1 or self.exchange == "native":
+        if self.dist is None or self.world == 1 or self.exchange in ("native", "columns-native"):
             self.lib.check(self.lib.sb_model_cycle(self.handle, self.t))
             return
         self.lib.check(self.lib.sb_model_tendency(self.handle))
@@ -515,8 +582,12 @@ class Model:
         for i, ic in enumerate(tile_ics):
             self.set_state(i, ic)
         self.lib.check(self.lib.sb_model_tendency(self.handle))
-        self._exchange()
-        self.lib.check(self.lib.sb_model_spline_transform(self.handle))
+        if self.world == 1 and self.columns:
+            self.lib.check(self.lib.sb_model_colsolve_solve(self.handle))
+        else:
+            self._exchange()
+        if not self.columns:
+            self.lib.check(self.lib.sb_model_spline_transform(self.handle))
         self.t = 0
 
     def profile(self, on: bool):

@@ -559,6 +559,10 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, void*) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -575,6 +579,10 @@ static void nccl_load() {
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void**, int, Uid, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, void*))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, void*))dlsym(g_nccl.lib, "ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, void*))dlsym(g_nccl.lib, "ncclRecv");
+  g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) throw std::runtime_error("NCCL symbols missing");
@@ -617,6 +625,21 @@ struct sb_model {
   void* comm = nullptr;
   int rank = 0, nranks = 1;
   long long extra_launches = 0;
+  // ---- distributed spline solve by z-mode planes (sb_model_colsolve_*)
+  struct ColSolve {
+    bool on = false;
+    int rank = 0, nranks = 1;
+    std::vector<int> z0;                    // [nranks+1] plane ranges
+    std::vector<DevGrid> tdg;               // [ntiles] tile descriptors (host copies, device tables of the patch not needed)
+    std::vector<int> tile_owner;            // [ntiles] rank that owns tile t
+    std::vector<long long> recv_off;        // [ntiles] offset of tile t's chunk [V][nz][ncolp_t][M_t] in recvB / sendA
+    double* recvB = nullptr;                // chunks of every tile for my planes
+    double* sendA = nullptr;                // solved coefficients, packed per tile in the same shape
+    double* slabB = nullptr;                // [V][nz][ncolp_P][M_P]
+    double* slabA = nullptr;
+    DevGrid slab{};                         // patch descriptor restricted to my planes
+    int nz() const { return z0[rank + 1] - z0[rank]; }
+  } cs;
 };
 
 static int var_index(const sb_model* M, const char* name) {
@@ -812,6 +835,8 @@ static void model_initialize(sb_model* M, const double* ic_host) {
   grid_forward(P, P->physical, nullptr);      // spectralTransform!(patch)   :135
   grid_spline(P, P->spectralB);               // gridTransform!(patch)       :136  (A-solve ...
   grid_inverse(P, P);                         //                                   ... + evaluate)
+  if (M->cs.on)                               // plane-distributed solve: every local tile keeps its own slice of A
+    for (auto& T : M->tiles) launch_extract(P->ctx(), P->dg, T.grid->dg, P->spectralA, T.grid->spectralA);
   CU(cudaStreamSynchronize(P->stream));
   if ((size_t)P->dg.N * P->dg.V * P->dg.D * sizeof(double) > ((size_t)4 << 30)) P->release_physical();
 }
@@ -821,7 +846,7 @@ static void tiles_physics(sb_model* M, int64_t t) {
   sb_grid* P = M->patch;
   for (auto& T : M->tiles) {
     sb_grid* G = T.grid;
-    grid_inverse(P, G);                                     // tileTransform!  :305
+    grid_inverse(M->cs.on ? G : P, G);                      // tileTransform!  :305 (plane-distributed solve: A arrives tile-local)
     ModelArrays a{};
     a.phys = G->physical; a.var_np1 = T.var_np1;
     a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
@@ -837,6 +862,10 @@ static void tiles_physics(sb_model* M, int64_t t) {
 // second half: calcTendency (K1) + own block / halo into the shared B buffer
 static void tiles_tendency(sb_model* M) {
   sb_grid* P = M->patch;
+  if (M->cs.on) {   // tile B stays tile-local; the z-mode-plane owners assemble and solve (sb_model_colsolve_solve)
+    for (auto& T : M->tiles) grid_forward(T.grid, T.var_np1, T.grid->physical);
+    return;
+  }
   CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
   sb_grid* prev = nullptr;
   for (auto& T : M->tiles) {
@@ -853,18 +882,200 @@ static void model_advance_tiles(sb_model* M, int64_t t) {
   tiles_tendency(M);
 }
 
+static void model_exchange(sb_model* M);
+
+static void model_step(sb_model* M, int64_t t) {
+  model_advance_tiles(M, t);
+  model_exchange(M);
+  if (!M->cs.on) grid_spline(M->patch, M->patch->spectralB);  // splineTransform! :285
+}
+
+
+// ====================================================================================== plane-distributed K2
+// The global spline solve couples all radii but not the (z-mode, wavenumber) columns, so the columns
+// are dealt out by z-mode plane: rank k owns planes [z0[k], z0[k+1]).  Every tile sends each owner the
+// contiguous [planes][columns][coefficients] slab of its B (no packing: zb is the slowest index), the
+// owner overlap-adds the tiles in the reference order (own block, then the lower neighbour's 3-coefficient
+// halo, src/semiimplicit.jl:323-329), solves its planes once, and returns to every tile exactly the
+// coefficients that tile evaluates.  Per rank this moves ~2 x (N-1)/N of ONE tile's spectrum instead of
+// all-reducing the whole patch, and the solve is no longer replicated (SURVEY 8e option B).
+static DevGrid plane_view(const DevGrid& g, int nz) {
+  DevGrid d = g;
+  d.bz = nz;
+  d.S = (long long)nz * g.b_rDim * g.ncolp;
+  return d;
+}
+
+static void colsolve_init(sb_model* M, int rank, int nranks) {
+  auto& cs = M->cs;
+  const DevGrid& p = M->patch->dg;
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw std::invalid_argument("bad rank");
+  if (M->ntiles % nranks) throw std::invalid_argument("tiles must divide evenly over ranks");
+  cs.rank = rank; cs.nranks = nranks;
+  cs.z0.resize(nranks + 1);
+  for (int k = 0; k <= nranks; ++k) cs.z0[k] = (int)((long long)p.bz * k / nranks);
+  const int per = M->ntiles / nranks, nz = cs.nz();
+  cs.tdg.resize(M->ntiles); cs.tile_owner.resize(M->ntiles); cs.recv_off.resize(M->ntiles + 1);
+  long long off = 0;
+  for (int t = 0; t < M->ntiles; ++t) {
+    DevGrid d = p;                        // only the scalar members are used by k_assemble / k_extract
+    d.num_cells = (int)M->tile_params[5 * t + 2];
+    d.rDim = 3 * d.num_cells; d.b_rDim = d.num_cells + 3;
+    d.coefOffset = (int)M->tile_params[5 * t + 3] - 1;
+    d.patchOffsetL = 3 * d.coefOffset;
+    d.kDim = p.has_l ? d.rDim + d.patchOffsetL : 0;
+    d.ncolp = 1 + 2 * d.kDim;
+    d.S = (long long)p.bz * d.b_rDim * d.ncolp;
+    cs.tdg[t] = d;
+    cs.tile_owner[t] = t / per;
+    cs.recv_off[t] = off;
+    off += (long long)p.V * nz * d.ncolp * d.b_rDim;
+  }
+  cs.recv_off[M->ntiles] = off;
+  cs.slab = plane_view(p, nz);
+  cs.recvB = dev_zeros(off, M->stream); M->owned.push_back(cs.recvB);
+  cs.sendA = dev_zeros(off, M->stream); M->owned.push_back(cs.sendA);
+  cs.slabB = dev_zeros(cs.slab.S * p.V, M->stream); M->owned.push_back(cs.slabB);
+  cs.slabA = dev_zeros(cs.slab.S * p.V, M->stream); M->owned.push_back(cs.slabA);
+  cs.on = true;
+}
+
+// pointer / element count of one message buffer.  what: 0 = B chunk of local tile `tile` (global index) for
+// owner `peer`; 1 = where tile `tile`'s B chunk lands on this owner; 2 = solved chunk to return to `tile`;
+// 3 = where owner `peer`'s planes land in local tile `tile`'s A; 4 = my solved slab; 5 = owner `peer`'s slab
+// inside the replicated patch A (output only).  All per variable v.
+static void colsolve_buffer(sb_model* M, int what, int tile, int v, int peer, void** ptr, long long* count) {
+  auto& cs = M->cs;
+  if (!cs.on) throw std::invalid_argument("sb_model_colsolve_init has not been called");
+  const DevGrid& p = M->patch->dg;
+  if (v < 0 || v >= p.V) throw std::invalid_argument("bad variable");
+  auto local_tile = [&](int t) -> sb_grid* {
+    if (t < M->tile_first || t >= M->tile_first + M->tile_count) throw std::invalid_argument("tile is not local");
+    return M->tiles[t - M->tile_first].grid;
+  };
+  const int nz = cs.nz();
+  if (what == 0 || what == 3) {
+    if (peer < 0 || peer >= cs.nranks || tile < 0 || tile >= M->ntiles) throw std::invalid_argument("bad peer/tile");
+    sb_grid* G = local_tile(tile);
+    const DevGrid& d = G->dg;
+    const long long plane = (long long)d.ncolp * d.b_rDim;
+    double* base = (what == 0 ? G->spectralB : G->spectralA) + (long long)v * d.S + cs.z0[peer] * plane;
+    *ptr = base; *count = (cs.z0[peer + 1] - cs.z0[peer]) * plane;
+  } else if (what == 1 || what == 2) {
+    if (tile < 0 || tile >= M->ntiles) throw std::invalid_argument("bad tile");
+    const DevGrid& d = cs.tdg[tile];
+    const long long per_v = (long long)nz * d.ncolp * d.b_rDim;
+    *ptr = (what == 1 ? cs.recvB : cs.sendA) + cs.recv_off[tile] + v * per_v; *count = per_v;
+  } else if (what == 4) {
+    *ptr = cs.slabA + (long long)v * cs.slab.S; *count = cs.slab.S;
+  } else if (what == 5) {
+    if (peer < 0 || peer >= cs.nranks) throw std::invalid_argument("bad peer");
+    const long long plane = (long long)p.ncolp * p.b_rDim;
+    *ptr = M->patch->spectralA + (long long)v * p.S + cs.z0[peer] * plane; *count = (cs.z0[peer + 1] - cs.z0[peer]) * plane;
+  } else {
+    throw std::invalid_argument("what must be 0..5");
+  }
+}
+
+// messages that stay on this rank: device copies on the model stream
+static void colsolve_local(sb_model* M, int direction /*0: B chunks in, 1: A chunks out*/) {
+  auto& cs = M->cs;
+  const DevGrid& p = M->patch->dg;
+  if (cs.nz() == 0) return;
+  for (int t = M->tile_first; t < M->tile_first + M->tile_count; ++t)
+    for (int v = 0; v < p.V; ++v) {
+      void *a, *b; long long na, nb;
+      colsolve_buffer(M, direction ? 3 : 0, t, v, cs.rank, &a, &na);
+      colsolve_buffer(M, direction ? 2 : 1, t, v, cs.rank, &b, &nb);
+      if (na != nb) throw std::runtime_error("colsolve: chunk size mismatch");
+      if (direction) CU(cudaMemcpyAsync(a, b, (size_t)na * sizeof(double), cudaMemcpyDeviceToDevice, M->stream));
+      else CU(cudaMemcpyAsync(b, a, (size_t)na * sizeof(double), cudaMemcpyDeviceToDevice, M->stream));
+    }
+}
+
+// owner side: overlap-add the tiles' chunks, solve my planes, pack what each tile needs
+static void colsolve_solve(sb_model* M) {
+  auto& cs = M->cs;
+  if (!cs.on) throw std::invalid_argument("sb_model_colsolve_init has not been called");
+  sb_grid* P = M->patch;
+  const DevGrid& p = P->dg;
+  const int nz = cs.nz();
+  if (nz == 0) return;                  // fewer planes than ranks (grids without a vertical dimension): nothing to own
+  colsolve_local(M, 0);
+  CU(cudaMemsetAsync(cs.slabB, 0, (size_t)cs.slab.S * p.V * sizeof(double), M->stream));
+  LaunchCtx c = P->ctx();
+  for (int t = 0; t < M->ntiles; ++t) {
+    DevGrid tv = plane_view(cs.tdg[t], nz);
+    if (t > 0) {
+      DevGrid pv = plane_view(cs.tdg[t - 1], nz);
+      launch_assemble(c, cs.slab, tv, cs.recvB + cs.recv_off[t], &pv, cs.recvB + cs.recv_off[t - 1], 0, cs.slabB);
+    } else {
+      launch_assemble(c, cs.slab, tv, cs.recvB + cs.recv_off[t], nullptr, nullptr, 0, cs.slabB);
+    }
+  }
+  launch_spline_solve(c, cs.slab, nullptr, P->hfactors, cs.slabB, cs.slabA);
+  for (int t = 0; t < M->ntiles; ++t) launch_extract(c, cs.slab, plane_view(cs.tdg[t], nz), cs.slabA, cs.sendA + cs.recv_off[t]);
+  colsolve_local(M, 1);
+}
+
+// output only: my solved planes into the replicated patch A (the other owners' planes arrive by broadcast)
+static void colsolve_publish(sb_model* M) {
+  auto& cs = M->cs;
+  const DevGrid& p = M->patch->dg;
+  if (cs.nz() == 0) return;
+  for (int v = 0; v < p.V; ++v) {
+    void *a, *b; long long na, nb;
+    colsolve_buffer(M, 4, 0, v, cs.rank, &a, &na);
+    colsolve_buffer(M, 5, 0, v, cs.rank, &b, &nb);
+    CU(cudaMemcpyAsync(b, a, (size_t)na * sizeof(double), cudaMemcpyDeviceToDevice, M->stream));
+  }
+}
+
+
+// native (library-owned NCCL communicator) exchange of one message set: dir 0 = B chunks to the plane owners,
+// dir 1 = solved chunks back to the tiles.  One ncclGroup = one fused launch over NVLink.
+static void colsolve_p2p(sb_model* M, int dir) {
+  auto& cs = M->cs;
+  if (cs.nranks <= 1) return;
+  if (!M->comm || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart) throw CommError("NCCL point-to-point is not available");
+  const int V = M->patch->dg.V;
+  NC(g_nccl.GroupStart());
+  for (int t = 0; t < M->ntiles; ++t) {
+    const bool mine = cs.tile_owner[t] == cs.rank;
+    for (int v = 0; v < V; ++v) {
+      void* ptr; long long n;
+      if (mine) {          // I hold tile t: talk to every other plane owner
+        for (int k = 0; k < cs.nranks; ++k) {
+          if (k == cs.rank) continue;
+          colsolve_buffer(M, dir ? 3 : 0, t, v, k, &ptr, &n);
+          if (n == 0) continue;
+          if (dir) NC(g_nccl.Recv(ptr, (size_t)n, /*ncclFloat64*/ 8, k, M->comm, (void*)M->stream));
+          else NC(g_nccl.Send(ptr, (size_t)n, 8, k, M->comm, (void*)M->stream));
+        }
+      } else {             // tile t lives elsewhere: its chunk of my planes
+        colsolve_buffer(M, dir ? 2 : 1, t, v, cs.rank, &ptr, &n);
+        if (n == 0) continue;
+        if (dir) NC(g_nccl.Send(ptr, (size_t)n, 8, cs.tile_owner[t], M->comm, (void*)M->stream));
+        else NC(g_nccl.Recv(ptr, (size_t)n, 8, cs.tile_owner[t], M->comm, (void*)M->stream));
+      }
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  ++M->extra_launches;
+}
+
 static void model_exchange(sb_model* M) {
+  if (M->cs.on) {
+    colsolve_p2p(M, 0);
+    colsolve_solve(M);
+    colsolve_p2p(M, 1);
+    return;
+  }
   if (M->nranks <= 1) return;
   sb_grid* P = M->patch;
   NC(g_nccl.AllReduce(P->spectralB, P->spectralB, (size_t)P->dg.S * P->dg.V, /*ncclFloat64*/ 8, /*ncclSum*/ 0, M->comm,
                       (void*)P->stream));
   ++M->extra_launches;
-}
-
-static void model_step(sb_model* M, int64_t t) {
-  model_advance_tiles(M, t);
-  model_exchange(M);
-  grid_spline(M->patch, M->patch->spectralB);  // splineTransform! :285
 }
 
 // ====================================================================================== C ABI
@@ -1048,6 +1259,7 @@ int sb_model_output(sb_model_t m, double* host) {
   return guarded([&] {
     if (!m) throw std::invalid_argument("NULL model");
     sb_grid* P = m->patch;
+    if (m->cs.on) colsolve_publish(m);   // (other owners' planes: broadcast by the caller beforehand)
     grid_inverse(P, P);
     check_cfl(P, nullptr, nullptr);
     if (host) {
@@ -1085,7 +1297,7 @@ int sb_model_cycle(sb_model_t m, int64_t t) {
     if (!m || t < 1) return fail(SB_EINVAL, "bad argument");
     tiles_tendency(m);
     model_exchange(m);
-    grid_spline(m->patch, m->patch->spectralB);
+    if (!m->cs.on) grid_spline(m->patch, m->patch->spectralB);
     tiles_physics(m, t);
     return SB_OK;
   } catch (const CommError& e) { return fail(SB_ECOMM, e.what());
@@ -1132,6 +1344,31 @@ int64_t sb_model_launch_count(sb_model_t m) {
   long long n = m->patch->launches + m->extra_launches;
   for (auto& t : m->tiles) n += t.grid->launches;
   return n;
+}
+
+
+int sb_model_colsolve_init(sb_model_t m, int32_t rank, int32_t nranks) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); colsolve_init(m, rank, nranks); });
+}
+int sb_model_colsolve_buffer(sb_model_t m, int32_t what, int32_t tile, int32_t v, int32_t peer, void** ptr, int64_t* count) {
+  return guarded([&] {
+    if (!m || !ptr || !count) throw std::invalid_argument("NULL argument");
+    long long n = 0;
+    colsolve_buffer(m, what, tile, v, peer, ptr, &n);
+    *count = n;
+  });
+}
+int sb_model_colsolve_planes(sb_model_t m, int32_t* z0, int32_t n) {
+  return guarded([&] {
+    if (!m || !z0 || !m->cs.on || n < m->cs.nranks + 1) throw std::invalid_argument("bad argument");
+    for (int k = 0; k <= m->cs.nranks; ++k) z0[k] = m->cs.z0[k];
+  });
+}
+int sb_model_colsolve_solve(sb_model_t m) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); colsolve_solve(m); });
+}
+int sb_model_colsolve_publish(sb_model_t m) {
+  return guarded([&] { if (!m || !m->cs.on) throw std::invalid_argument("bad argument"); colsolve_publish(m); });
 }
 
 int sb_comm_unique_id(void* out128) {

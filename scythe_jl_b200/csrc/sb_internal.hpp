@@ -175,6 +175,7 @@ void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFa
                          const std::vector<DevSplineFactor>& hfactors, const double* B, double* A);
 void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* tileB,
                      const DevGrid* prev, const double* prevB, int last, double* shared);
+void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA);
 void launch_copy(const LaunchCtx& c, double* dst, const double* src, long long n);
 void launch_nan_scan(const LaunchCtx& c, const double* phys, long long N, int V, long long* result);
 

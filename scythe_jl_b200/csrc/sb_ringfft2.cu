@@ -42,6 +42,11 @@ struct RCfg {
                                                    (CH_SMEM ? L / 2 : 0));
 };
 
+#ifndef SB_PRO_BATCH
+#define SB_PRO_BATCH 2
+#endif
+constexpr int PB = SB_PRO_BATCH;   // spectrum elements whose loads are in flight together in the inverse prologue
+
 template <int T>
 __device__ __forceinline__ void team_sync(int team) {
   if (T >= 64) sb_bar_sync(1 + team, T);
@@ -183,14 +188,28 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
         const double* sp = in + (long long)fin * in_fs + (long long)v_ * in_vs + (long long)zb * g.W + woff;
         const double2* Ph = PQ + (size_t)(2 * half) * m;
         const double2* Qh = Ph + m;
+        // loads are unconditional (clamped indices) and issued four elements at a time, so that one L2
+        // round trip covers a whole batch instead of one per `k < m` branch
 #pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) {
-          const int k = n1 * T + tl;
-          double2 u = make_double2(0.0, 0.0);
-          if (k < m) {
+        for (int h4 = 0; h4 < 8 / PB; ++h4) {
+          double cx[PB], cy[PB], qx[PB], qy[PB];
+          double2 Pk[PB], Qk[PB];
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int k0 = (h4 * PB + j) * T + tl;
+            const int k = k0 < m ? k0 : m - 1;
             const int km = k ? m - k : 0;
-            const double2 ck = k ? make_double2(sp[2 * k - 1], sp[2 * k]) : make_double2(sp[0], 0.0);
-            const double2 cq = km ? make_double2(sp[2 * km - 1], sp[2 * km]) : make_double2(sp[0], 0.0);
+            cx[j] = sp[k ? 2 * k - 1 : 0]; cy[j] = sp[2 * k];
+            qx[j] = sp[km ? 2 * km - 1 : 0]; qy[j] = sp[2 * km];
+            Pk[j] = Ph[k]; Qk[j] = Qh[k];
+          }
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int k0 = (h4 * PB + j) * T + tl;
+            const int k = k0 < m ? k0 : m - 1;
+            const int km = k ? m - k : 0;
+            const double2 ck = make_double2(cx[j], k ? cy[j] : 0.0);
+            const double2 cq = make_double2(qx[j], km ? qy[j] : 0.0);
             // derivative factor D(q): 1 | i q | -q^2 ;  X = conj(c_k D_k), Y = c_km D_km
             double2 X, Y;
             if (f < 3) {
@@ -205,9 +224,9 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
               X = make_double2(sk * ck.x, -sk * ck.y);
               Y = make_double2(sq * cq.x, sq * cq.y);
             }
-            u = cm(X, Ph[k]) + cm(Y, Qh[k]);
+            const double2 u = cm(X, Pk[j]) + cm(Y, Qk[j]);
+            v[h4 * PB + j] = k0 < m ? u : make_double2(0.0, 0.0);
           }
-          v[n1] = u;
         }
       }
       conv2<LOG2L>(v, buf, tw0, twr, FHt, tl, team, active);
@@ -284,16 +303,18 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l2(DevGrid g, const LWork* __res
       if (active) {
         const double* rp = src + (long long)(wk.row0 + row) * n + 2 * half;
         double* mp = mir ? mir + (long long)(wk.row0 + row) * n + 2 * half : nullptr;
+        double2 x[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {   // unconditional (clamped) loads: one round trip for the whole row slice
+          const int a0 = n1 * T + tl, a = a0 < m ? a0 : m - 1;
+          x[n1] = *reinterpret_cast<const double2*>(rp + 4 * a);
+        }
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
-          const int a = n1 * T + tl;
-          double2 y = make_double2(0.0, 0.0);
-          if (a < m) {
-            const double2 x = *reinterpret_cast<const double2*>(rp + 4 * a);
-            if (mp) *reinterpret_cast<double2*>(mp + 4 * a) = x;
-            y = cm(x, chirp[a]);
-          }
-          v[n1] = y;
+          const int a0 = n1 * T + tl, a = a0 < m ? a0 : m - 1;
+          if (mp && a0 < m) *reinterpret_cast<double2*>(mp + 4 * a) = x[n1];
+          const double2 y = cm(x[n1], chirp[a]);
+          v[n1] = a0 < m ? y : make_double2(0.0, 0.0);
         }
       }
       conv2<LOG2L>(v, buf, tw0, twr, FHt, tl, team, active);

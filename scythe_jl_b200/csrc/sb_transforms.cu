@@ -1118,6 +1118,27 @@ void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& ti
   count(c);
 }
 
+// inverse of k_assemble without the halo: the coefficients tile t evaluates, cut out of the solved patch planes
+__global__ void k_extract(DevGrid p, DevGrid t, const double* __restrict__ A, double* __restrict__ tileA) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_v = t.S;
+  if (idx >= per_v * t.V) return;
+  const int v = (int)(idx / per_v);
+  long long rem = idx - (long long)v * per_v;
+  const int m = (int)(rem % t.b_rDim);
+  rem /= t.b_rDim;
+  const int pcol = (int)(rem % t.ncolp), zb = (int)(rem / t.ncolp);
+  tileA[idx] = A[(long long)v * p.S + ((long long)zb * p.ncolp + pcol) * p.b_rDim + (t.coefOffset - p.coefOffset) + m];
+}
+
+void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA) {
+  ProfScope prof_scope_(c, "extract");
+  long long tot = tile.S * tile.V;
+  SB_LAUNCH(k_extract, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, c.stream, patch, tile, A, tileA);
+  SB_CHECK_LAUNCH();
+  count(c);
+}
+
 __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];

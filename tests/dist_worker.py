@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
-def main(case_name, out_path, lib_path, ntiles):
+def main(case_name, out_path, lib_path, ntiles, exchange="columns"):
     import scythe_jl_b200 as S  # noqa: F401
     from helpers import model_cases, pkg_model
     from oracle import grids as G
@@ -22,7 +22,7 @@ def main(case_name, out_path, lib_path, ntiles):
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = _lib.load(lib_path)
     case = model_cases()[case_name]
-    m = pkg_model(case, int(ntiles), lib, distributed=True)
+    m = pkg_model(case, int(ntiles), lib, distributed=True, exchange=exchange)
     assert m.tile_count == int(ntiles) // world and m.tile_first == rank * m.tile_count
     # each rank only ever sees its own slice of the initial state
     patch = G.createGrid(case["gp"])
@@ -39,4 +39,4 @@ def main(case_name, out_path, lib_path, ntiles):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:5])
+    main(*sys.argv[1:6])

@@ -213,12 +213,12 @@ def pkg_model(case, ntiles, lib, **kw):
     return S.Model(mp, num_tiles=ntiles, ref_state=sref, lib=lib, **kw)
 
 
-def check_model(case, lib):
+def check_model(case, lib, **kw):
     """N steps on `tiles` tiles: final tile state (var_np1, expdot history) vs the oracle."""
     errs = []
     for nt in case["tiles"]:
         orun = run_oracle(case, nt)
-        m = pkg_model(case, nt, lib)
+        m = pkg_model(case, nt, lib, **kw)
         m.initialize(case["ic"])
         m.run(case["n"])
         for i, mt in enumerate(orun.mtiles):

@@ -15,13 +15,15 @@ from helpers import STATE_TOL, model_cases, pkg_model, run_oracle, slot_errs
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.parametrize("case_name,ntiles", [("LinearAdvection1D", 2), ("LinearAdvectionRLZ", 2), ("LinearAdvectionRZ", 4)])
-def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, emu_lib, tmp_path):
+@pytest.mark.parametrize("case_name,ntiles,exchange", [("LinearAdvection1D", 2, "torch"), ("LinearAdvection1D", 2, "columns"),
+                                                       ("LinearAdvectionRLZ", 2, "columns"), ("LinearAdvectionRZ", 4, "columns"),
+                                                       ("LinearAdvectionRZ", 4, "torch")])
+def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, emu_lib, tmp_path):
     out = tmp_path / "out"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 2000), OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", env["MASTER_PORT"], str(ROOT / "tests" / "dist_worker.py"), case_name, str(out),
-           str(emu_lib.path), str(ntiles)]
+           str(emu_lib.path), str(ntiles), exchange]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     o0, o1 = np.load(f"{out}.rank0.npy"), np.load(f"{out}.rank1.npy")

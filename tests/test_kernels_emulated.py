@@ -25,3 +25,13 @@ def test_timestep_matches_oracle(name, emu_lib):
     case["tiles"] = case["tiles"][-1:]   # the multi-tile variant only (CPU time)
     case["n"] = min(case["n"], 3)
     assert check_model(case, emu_lib) <= STATE_TOL
+
+
+@pytest.mark.parametrize("name,ntiles", [("LinearAdvection1D", 3), ("LinearAdvectionRLZ", 2), ("Euler_test_semiimplicit", 2)])
+def test_plane_distributed_solve_single_process(name, ntiles, emu_lib):
+    """exchange="columns": B stays tile-local, the z-mode-plane owner overlap-adds, solves and hands every tile
+    its own slice of A (here one process owns every plane) -- same answer as the shared-array scheme."""
+    case = dict(M_CASES[name])
+    case["tiles"] = (ntiles,)
+    case["n"] = min(case["n"], 3)
+    assert check_model(case, emu_lib, exchange="columns") <= STATE_TOL
