@@ -77,6 +77,7 @@ struct sb_grid {
   std::vector<DevSplineFactor> hfactors;
   std::vector<void*> owned;   // device allocations freed at destroy
   double* physical = nullptr;
+  const double* slot0_src = nullptr;   // calcTendency's `physical .= var_np1` (src/semiimplicit.jl:731) deferred until slot 0 is read
   double* spectralB = nullptr;
   double* spectralA = nullptr;
   double* scratch = nullptr;
@@ -110,6 +111,11 @@ struct sb_grid {
 
   void ensure_physical() {
     if (!physical) physical = dev_zeros(dg.N * dg.V * dg.D, stream);
+  }
+  void materialize_slot0() {
+    if (slot0_src && physical)
+      CU(cudaMemcpyAsync(physical, slot0_src, (size_t)dg.N * dg.V * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    slot0_src = nullptr;
   }
   void release_physical() {
     if (physical) { CU(cudaStreamSynchronize(stream)); cudaFree(physical); physical = nullptr; }
@@ -384,6 +390,7 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
   if (t.coefOffset < p.coefOffset || t.coefOffset + t.b_rDim > p.coefOffset + p.b_rDim)
     throw std::invalid_argument("tile is not inside the patch");
   T->ensure_physical();
+  T->slot0_src = nullptr;                 // every slot is rewritten below
   LaunchCtx c = T->ctx();
   if (!t.has_l && !t.has_z) {
     launch_inv_r(c, t, p, t.V, P->spectralA, p.S, T->physical, 0, 0, 1, 0);
@@ -535,6 +542,7 @@ static void calc_tile_sizes(const sb_grid_params* gp, int ntiles, double* out) {
 
 static void check_cfl(sb_grid* G, int32_t* var, int64_t* index) {
   if (!G->physical) throw std::invalid_argument("grid has no physical array");
+  G->materialize_slot0();
   long long init = 0x7fffffffffffffffLL;
   CU(cudaMemcpyAsync(G->d_nan, &init, sizeof(init), cudaMemcpyHostToDevice, G->stream));
   launch_nan_scan(G->ctx(), G->physical, G->dg.N, G->dg.V, G->d_nan);
@@ -863,14 +871,15 @@ static void tiles_physics(sb_model* M, int64_t t) {
 static void tiles_tendency(sb_model* M) {
   sb_grid* P = M->patch;
   if (M->cs.on) {   // tile B stays tile-local; the z-mode-plane owners assemble and solve (sb_model_colsolve_solve)
-    for (auto& T : M->tiles) grid_forward(T.grid, T.var_np1, T.grid->physical);
+    for (auto& T : M->tiles) { grid_forward(T.grid, T.var_np1, nullptr); T.grid->slot0_src = T.var_np1; }
     return;
   }
   CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
   sb_grid* prev = nullptr;
   for (auto& T : M->tiles) {
     sb_grid* G = T.grid;
-    grid_forward(G, T.var_np1, G->physical);                // calcTendency    :728-735
+    grid_forward(G, T.var_np1, nullptr);                    // calcTendency    :728-735 (slot-0 copy deferred)
+    G->slot0_src = T.var_np1;
     launch_assemble(G->ctx(), P->dg, G->dg, G->spectralB, prev ? &prev->dg : nullptr, prev ? prev->spectralB : nullptr, 0,
                     P->spectralB);                         // :320-329
     prev = G;
@@ -1128,6 +1137,7 @@ int sb_grid_set_physical(sb_grid_t g, const double* host, int32_t slot0, int32_t
   return guarded([&] {
     check_slots(g, host, slot0, nslots);
     g->ensure_physical();
+    if (slot0 == 0) g->slot0_src = nullptr;
     CU(cudaMemcpyAsync(g->physical + g->slot_stride() * slot0, host, (size_t)g->slot_stride() * nslots * sizeof(double),
                        cudaMemcpyHostToDevice, g->stream));
     CU(cudaStreamSynchronize(g->stream));
@@ -1137,6 +1147,7 @@ int sb_grid_get_physical(sb_grid_t g, double* host, int32_t slot0, int32_t nslot
   return guarded([&] {
     check_slots(g, host, slot0, nslots);
     g->ensure_physical();
+    if (slot0 == 0) g->materialize_slot0();
     CU(cudaMemcpyAsync(host, g->physical + g->slot_stride() * slot0, (size_t)g->slot_stride() * nslots * sizeof(double),
                        cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
@@ -1159,7 +1170,12 @@ int sb_grid_get_spectral(sb_grid_t g, int32_t which, double* host) {
   });
 }
 int sb_spectral_transform(sb_grid_t g) {
-  return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); g->ensure_physical(); grid_forward(g, g->physical, nullptr); });
+  return guarded([&] {
+    if (!g) throw std::invalid_argument("NULL grid");
+    g->ensure_physical();
+    g->materialize_slot0();
+    grid_forward(g, g->physical, nullptr);
+  });
 }
 int sb_grid_transform(sb_grid_t g) {
   return guarded([&] { if (!g) throw std::invalid_argument("NULL grid"); grid_spline(g, g->spectralB); grid_inverse(g, g); });
@@ -1201,7 +1217,7 @@ int sb_grid_device_ptr(sb_grid_t g, int32_t which, void** ptr, int64_t* n) {
   return guarded([&] {
     if (!g || !ptr) throw std::invalid_argument("NULL argument");
     switch (which) {
-      case 0: g->ensure_physical(); *ptr = g->physical; if (n) *n = g->dg.N * g->dg.V * g->dg.D; break;
+      case 0: g->ensure_physical(); g->materialize_slot0(); *ptr = g->physical; if (n) *n = g->dg.N * g->dg.V * g->dg.D; break;
       case 1: *ptr = g->spectralB; if (n) *n = g->dg.S * g->dg.V; break;
       case 2: *ptr = g->spectralA; if (n) *n = g->dg.S * g->dg.V; break;
       default: throw std::invalid_argument("which must be 0, 1 or 2");

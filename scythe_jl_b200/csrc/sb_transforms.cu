@@ -1072,7 +1072,10 @@ void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFa
     } else if (!std::getenv("SB_RADIAL_V1") && f.nfree >= 3) {
       const int in_smem = (size_t)4 * f.nfree * 8 <= 96 * 1024;
       size_t smem = in_smem ? (size_t)4 * f.nfree * 8 : 0;
-      opt_in_smem(k_spline_solve2, smem);
+      if (smem > 8 * 1024) {   // static tile (33 KB) + table may exceed the 48 KB default
+        cudaError_t e = cudaFuncSetAttribute(k_spline_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+      }
       SB_LAUNCH(k_spline_solve2, dim3((ncols + SSQ - 1) / SSQ), dim3(SSQ), smem, c.stream, f, ncols, in_smem, Bv, Av);
     } else {
       int Ms = f.M | 1;

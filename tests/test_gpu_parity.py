@@ -59,6 +59,25 @@ def test_rz_north_star_config(gpu_lib):
     assert eB <= TRANSFORM_TOL and max(eP) <= TRANSFORM_TOL, (eB, eP)
 
 
+def test_long_radial_columns(gpu_lib):
+    """b_rDim = 1203 (the C5 weak-scaling patch is 948): streaming banded solve with a 38 KB Cholesky table."""
+    gp = G.GridParameters(geometry="R", xmin=0, xmax=1e6, num_cells=1200,
+                          BCL={"a": spl.R1T1, "b": spl.R1T0, "c": spl.R0}, BCR={"a": spl.R0, "b": spl.R2T10, "c": spl.R3},
+                          vars={"a": 1, "b": 2, "c": 3})
+    eB, eP = check_transforms(gp, gpu_lib, seed=17)
+    assert eB <= TRANSFORM_TOL and max(eP) <= TRANSFORM_TOL, (eB, eP)
+
+
+def test_plane_distributed_solve_matches_shared_array_scheme(gpu_lib):
+    """exchange="columns" (one process owning every z-mode plane) == the reference's shared-array scheme."""
+    case = dict(M_CASES["LinearAdvectionRLZ"])
+    case["tiles"] = (2,)
+    assert check_model(case, gpu_lib, exchange="columns") <= STATE_TOL
+    case = dict(M_CASES["Oneway_ShallowWater_HeightResolvedBL"])
+    case["tiles"] = (2,)
+    assert check_model(case, gpu_lib, exchange="columns") <= STATE_TOL
+
+
 def test_tiles_equal_single_tile_and_oracle_on_larger_rl(gpu_lib):
     """N-tile == 1-tile (overlap-add of the 3 seam coefficients) at a size with uneven tiles."""
     case = dict(M_CASES["Oneway_ShallowWater_Slab"])
