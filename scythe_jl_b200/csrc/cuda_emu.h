@@ -39,6 +39,8 @@ struct dim3 {
 struct uint3 { unsigned x, y, z; };
 struct double2 { double x, y; };
 struct alignas(16) double4 { double x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 

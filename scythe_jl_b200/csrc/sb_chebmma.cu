@@ -55,30 +55,43 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k_inv_z_mma(DevGrid g, const ZT
   const int z0 = zt * 8 + 2 * q;                 // this lane's pair of levels (z0, z0+1) and mirror (zDim-2-z0, +1)
   const int nwork = ntiles * nvars;
   constexpr int CPR = 256 / CB, CE = CB / 8;     // copies per 32-column row, doubles per copy
-  auto issue = [&](int w, double* dst) {
+  // per input row (field f, mode zb): {f, zb, offset of the row in the smem tile}; built once, so the copy
+  // loop is a table look-up + two multiply-adds instead of two integer divisions per 16 bytes
+  int4* rowtab = reinterpret_cast<int4*>(a + 2 * bufsz);
+  const int nrow = nfields * bz;
+  for (int r = tid; r < nrow; r += ZM_THREADS) {
+    const int f = r / bz, zb = r - f * bz;
+    rowtab[r] = make_int4(f, zb, ((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS, 0);
+  }
+  __syncthreads();
+  auto issue = [&](int w, const ZTile& ztile, double* dst) {
     const int v = w / ntiles;
-    const ZTile ztile = tiles[w - v * ntiles];
     const double* src = in + (long long)v * in_vs + ztile.out_base;
-    const int total = nfields * bz * CPR;
+    const int total = nrow * CPR;
     for (int c = tid; c < total; c += ZM_THREADS) {
       const int row = c / CPR, col = (c - row * CPR) * CE;
-      const int f = row / bz, zb = row - f * bz;
+      const int4 rt = rowtab[row];
       if (col < ztile.ncols) {
-        const double* sp = src + (long long)f * in_fs + (long long)zb * ztile.out_stride + col;
-        double* dp = dst + ((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS + col;
+        const double* sp = src + (long long)rt.x * in_fs + (long long)rt.y * ztile.out_stride + col;
+        double* dp = dst + rt.z + col;
         if (CB == 16) sb_cp_async16(dp, sp); else sb_cp_async8(dp, sp);
       }
     }
     sb_cp_commit();
   };
+  // the next tile's descriptor is fetched before the barrier, so its L2 round trip overlaps the wait
+  const int G = gridDim.x;
   int w = blockIdx.x, cur = 0;
-  if (w < nwork) issue(w, a);
-  for (; w < nwork; w += gridDim.x) {
+  ZTile zt0 = tiles[(w < nwork ? w : 0) % ntiles], zt1;
+  if (w < nwork) issue(w, zt0, a);
+  for (; w < nwork; w += G) {
+    zt1 = tiles[(w + G < nwork ? w + G : w) % ntiles];
     sb_cp_wait<0>();
     __syncthreads();            // tile w has landed; everybody is done with the other buffer
-    if (w + (int)gridDim.x < nwork) issue(w + gridDim.x, a + (cur ^ 1) * bufsz);
+    if (w + G < nwork) issue(w + G, zt1, a + (cur ^ 1) * bufsz);
     const int v = w / ntiles;
-    const ZTile ztile = tiles[w - v * ntiles];
+    const ZTile ztile = zt0;
+    zt0 = zt1;
     const double* ab = a + cur * bufsz;
     double* const pv = phys + (long long)(var0 + v) * g.N;
     for (int ct = cg; ct < 4; ct += ncg) {
@@ -155,7 +168,7 @@ void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
                       int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
                       const double* parB) {
   ProfScope prof_scope_(c, "inv_z");
-  const size_t smem = (size_t)2 * nfields * 2 * ZM_KK * ZM_CS * sizeof(double);
+  const size_t smem = (size_t)2 * nfields * 2 * ZM_KK * ZM_CS * sizeof(double) + (size_t)nfields * g.bz * 16;
   // 16-byte async copies need every [mode] row of every tile 16-byte aligned
   const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0 && in_vstride % 2 == 0 && (g.has_l || g.rDim % 2 == 0);
   auto kern = al16 ? k_inv_z_mma<16> : k_inv_z_mma<8>;
@@ -184,7 +197,7 @@ void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
 #define FZ_US 68                // level stride of the u tile (== 4 mod 16, 16-byte aligned rows)
 #define FZ_THREADS 256
 
-__global__ void __launch_bounds__(FZ_THREADS) k_fwd_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles, int nvars,
+__global__ void __launch_bounds__(FZ_THREADS, 3) k_fwd_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles, int nvars,
                                                           const double* __restrict__ in, long long in_vs,
                                                           double* __restrict__ mirror, long long mirror_vs,
                                                           double* __restrict__ out, long long out_vs,
@@ -200,32 +213,36 @@ __global__ void __launch_bounds__(FZ_THREADS) k_fwd_z_mma(DevGrid g, const ZTile
 #pragma unroll
     for (int kt = 0; kt < 8; ++kt) Bf[nt][kt] = fwdB[(((par * 3 + nt) * 8 + kt) * 32) + lane];
   const int nwork = ntiles * nvars;
-  const int cpc = zDim >> 1;     // 16-byte copies per column
-  auto issue = [&](int w, double* dst) {
+  const int lcpc = (zDim == 64) ? 5 : (zDim == 32 ? 4 : 3), cpc = 1 << lcpc;     // 16-byte copies per column (2^lcpc)
+  auto issue = [&](int w, const ZTile& zt, double* dst) {
     const int v = w / ntiles;
-    const ZTile zt = tiles[w - v * ntiles];
     const double* src = in + (long long)v * in_vs + (long long)zt.hcol0 * zDim;
-    const int total = zt.ncols * cpc;
+    const int total = zt.ncols << lcpc;
     for (int c = tid; c < total; c += FZ_THREADS) {
-      const int col = c / cpc, z = (c - col * cpc) * 2;
+      const int col = c >> lcpc, z = (c & (cpc - 1)) * 2;
       sb_cp_async16(dst + col * FZ_US + z, src + (long long)col * zDim + z);
     }
     sb_cp_commit();
   };
+  const int G = gridDim.x;
+  auto desc = [&](int w) { return w < nwork ? tiles[w % ntiles] : ZTile{}; };
   int w = blockIdx.x, cur = 0;
-  if (w < nwork) issue(w, u);
-  for (; w < nwork; w += gridDim.x) {
+  ZTile zt0 = desc(w), zt1 = desc(w + G), zt2;
+  if (w < nwork) issue(w, zt0, u);
+  for (; w < nwork; w += G) {
+    zt2 = desc(w + 2 * G);       // descriptor prefetch: keeps the L2 round trip off the barrier -> copy path
     sb_cp_wait<0>();
     __syncthreads();
-    if (w + (int)gridDim.x < nwork) issue(w + gridDim.x, u + (cur ^ 1) * 32 * FZ_US);
+    if (w + G < nwork) issue(w + G, zt1, u + (cur ^ 1) * 32 * FZ_US);
     const int v = w / ntiles;
-    const ZTile zt = tiles[w - v * ntiles];
+    const ZTile zt = zt0;
+    zt0 = zt1; zt1 = zt2;
     const double* ub = u + cur * 32 * FZ_US;
     if (mirror) {
       double* mv = mirror + (long long)v * mirror_vs + (long long)zt.hcol0 * zDim;
-      const int total = zt.ncols * cpc;
+      const int total = zt.ncols << lcpc;
       for (int c = tid; c < total; c += FZ_THREADS) {
-        const int col = c / cpc, z = (c - col * cpc) * 2;
+        const int col = c >> lcpc, z = (c & (cpc - 1)) * 2;
         *reinterpret_cast<double2*>(mv + (long long)col * zDim + z) = *reinterpret_cast<const double2*>(ub + col * FZ_US + z);
       }
     }
