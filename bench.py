@@ -307,10 +307,25 @@ def run_ours(args):
                         "frac": ((nbytes / 1e9) / (ms / 1e3) / peak) if ms > 0 else None}
     kern_ms = {k: v["ms"] / args.steps for k, v in prof.items()}
     top = max(detail, key=lambda k: detail[k]["ms_per_step"])
+    # measured DRAM traffic / FP64-pipe activity of the same step from the committed ncu pass (profiles/), if present
+    traffic, ncu_note = None, None
+    prof_file = ROOT / "profiles" / "r1g_step_kernels.json"
+    if prof_file.exists() and world == 1 and cells_tile == C4_CELLS:
+        pk = json.loads(prof_file.read_text())["one_step"]
+        sel = {"K3": ("k_inv_r", "k_inv_l", "k_inv_z"), "K1": ("k_fwd_z", "k_fwd_l", "k_fwd_r"), "K2": ("k_spline",),
+               "K4": ("k_pointwise",)}[top[:2]]
+        rows = [v for k, v in pk.items() if any(s_ in k for s_ in sel)]
+        traffic = 1e9 * sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows)
+        fft = [v for k, v in pk.items() if "k_inv_l2" in k]
+        ncu_note = {"file": "profiles/r1g_step_kernels.json",
+                    "k_inv_l2_fp64_pipe_pct": sum(r["fp64_pipe_pct"] * r["ms"] for r in fft) / max(sum(r["ms"] for r in fft), 1e-9),
+                    "k_inv_l2_share_of_step_under_ncu": sum(r["share"] for r in fft),
+                    "note": "the ring FFT inside K3 is FP64-pipe bound (Bluestein), not HBM bound; measured FP64 peak "
+                            "36.7 TFLOP/s DFMA = DMMA (profiles/fp64_peak_b200.json)"}
     roof = {"bound": "hbm", "kernel": top, "achieved": detail[top]["achieved_GBps"], "peak": peak, "unit": "GB/s",
-            "frac": detail[top]["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": detail[top]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": detail[top]["algorithmic_GB"] * 1e9,
-            "share_of_step": detail[top]["ms_per_step"] / ms_step}
+            "share_of_step": detail[top]["ms_per_step"] / ms_step, "ncu": ncu_note}
     step_bytes = 8.0 * V * (2 * N * D + 6 * N + 4 * Sg)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

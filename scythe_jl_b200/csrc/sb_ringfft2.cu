@@ -74,8 +74,12 @@ __device__ __forceinline__ void conv2(double2 (&v)[16], double2* buf, const doub
     if (p > 0) {
       team_sync<T>(team);
       if (active) {
+        // butterfly order (0,4,8,12, 1,5,9,13, ...): the first radix-4 can start after four loads
 #pragma unroll
-        for (int n = 0; n < 16; ++n) v[n] = buf[base + n * Ms + ((n * Ms) >> 4)];
+        for (int i = 0; i < 16; ++i) {
+          const int n = (i >> 2) + 4 * (i & 3);
+          v[n] = buf[base + n * Ms + ((n * Ms) >> 4)];
+        }
       }
     }
     if (active) {
@@ -106,11 +110,13 @@ __device__ __forceinline__ void conv2(double2 (&v)[16], double2* buf, const doub
     const int b = tl / Ms, j = tl - b * Ms, base = padi(b * Lb + j);
     team_sync<T>(team);
     if (active) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = buf[base + k * Ms + ((k * Ms) >> 4)];
       const double2* tw = (p == 0 ? tw0 : twr + (p == 1 ? 0 : 15 * (L >> 8))) + j;
 #pragma unroll
-      for (int k = 1; k < 16; ++k) v[k] = cmc(v[k], tw[(k - 1) * Ms]);
+      for (int i = 0; i < 16; ++i) {       // butterfly order, data and twiddle fetched together
+        const int k = (i >> 2) + 4 * (i & 3);
+        const double2 x = buf[base + k * Ms + ((k * Ms) >> 4)];
+        v[k] = k ? cmc(x, tw[(k - 1) * Ms]) : x;
+      }
       fft16<true>(v);
       if (p > 0) {
 #pragma unroll
