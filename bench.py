@@ -37,7 +37,7 @@ TS, KDIFF = 2.0, 500.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=0, help="override radial cells per GPU tile (debug)")
@@ -131,7 +131,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm (oracle = the reference restated)
-def cpu_baseline(steps=2, warmup=1, cells=24, workers=None):
+def cpu_baseline(steps=2, warmup=1, cells=64, workers=None):
     """Oracle ModelRun on a bounded sample of the same workload, all host threads, scaled by points."""
     from oracle import grids as G
     from oracle import model as M
@@ -158,7 +158,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, dt = cpu_baseline(steps=max(args.steps, 1), warmup=min(max(args.warmup, 1), 2))
+    cb, dt = cpu_baseline(steps=max(min(args.steps, 3), 1), warmup=1)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"] * 1.0, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -233,12 +233,12 @@ def run_ours(args):
         return float(t.item())
 
     # warm-up, then K timed steps with per-kernel event profiling on
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # nvidia-smi needs ~0.3 s to produce its first sample: start it before the warm-up
     for _ in range(args.warmup):
         m.step()
     l0 = m.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     m.profile(True)
     total_ms = timed(m.step, args.steps)
     m.profile(False)
@@ -280,6 +280,11 @@ def run_ours(args):
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "what": "end-to-end host-buffer stepping is measured at N=1 only"}
 
+    per_rank = None
+    if distributed:   # every rank's per-kernel time: the step is as slow as the slowest tile
+        mine = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -330,7 +335,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world, cells_tile), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "roofline": roof, "roofline_detail": detail, "kernel_ms_per_step": kern_ms,
+            "gpu_launches": int(launches), "per_rank_kernel_ms": per_rank, "roofline": roof, "roofline_detail": detail, "kernel_ms_per_step": kern_ms,
             "timestep_algorithmic_GB": step_bytes / 1e9,
             "timestep_frac_of_hbm_roofline": (step_bytes / 1e9) / (ms_step / 1e3) / peak,
             "transforms_per_s": {"spectralTransform_K1": 1e3 / k1_ms, "gridTransform_K2K3": 1e3 / k23_ms,
