@@ -90,6 +90,7 @@ struct sb_grid {
   std::vector<const LWork*> d_fwork, d_iwork;
   std::vector<std::vector<LWork>> fwork2, iwork2;     // v2 persistent ring-FFT items (bigger row ranges)
   std::vector<const LWork*> d_fwork2, d_iwork2;
+  double* d_fft3_scratch = nullptr;                    // parking area of the composite-length forward FFT
   std::vector<const double*> d_tw, d_twp;
   RingPlan* d_plans = nullptr;
   double* d_blob = nullptr;
@@ -320,6 +321,10 @@ static void build_grid(sb_grid* G) {
         for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork2[cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
       }
     }
+    size_t f3 = 0;
+    for (auto& cl : G->classes)
+      if (cl.R == 3) f3 = std::max(f3, fft3_scratch_doubles(cl.L));
+    if (f3) { G->d_fft3_scratch = dev_zeros((long long)f3, G->stream); G->owned.push_back(G->d_fft3_scratch); }
     for (size_t c = 0; c < G->classes.size(); ++c) {
       G->d_fwork2.push_back(G->up(G->fwork2[c]));
       G->d_iwork2.push_back(G->up(G->iwork2[c]));
@@ -358,10 +363,10 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
     if (d.has_l && d.has_z) {
       grid_fwd_z(G, nv, inv, mir, SZ, szN);
       launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, SZ, szN,
-                   1, nullptr, 0, SL, slN, &G->fwork2, G->d_fwork2.data());
+                   1, nullptr, 0, SL, slN, &G->fwork2, G->d_fwork2.data(), G->d_fft3_scratch);
     } else if (d.has_l) {
       launch_fwd_l(c, d, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, nv, inv, d.N,
-                   0, mir, d.N, SL, slN, &G->fwork2, G->d_fwork2.data());
+                   0, mir, d.N, SL, slN, &G->fwork2, G->d_fwork2.data(), G->d_fft3_scratch);
     } else {
       grid_fwd_z(G, nv, inv, mir, SL, slN);
     }

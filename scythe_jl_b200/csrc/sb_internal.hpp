@@ -40,8 +40,9 @@ bool lu_factor(std::vector<double>& A, std::vector<int>& piv, int n);
 void lu_solve(const std::vector<double>& LU, const std::vector<int>& piv, int n, double* b);
 bool invert(std::vector<double>& A, int n);
 
-struct FftClass {            // one power-of-two convolution length
+struct FftClass {            // one convolution length: 2^a, or 3 * 2^a (radix-3 split over three sub-FFT teams)
   int L = 0, log2L = 0;
+  int R = 1, L2 = 0;         // L = R * L2, L2 a power of two
   std::vector<double> tw;    // [L] complex: exp(-2 pi i t / L)
   bool fast = false;         // L in 256..8192: register-resident radix-16 kernel (sb_ringfft.cu)
   std::vector<double> twp;   // fast: per-pass twiddle tables
@@ -137,7 +138,8 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   const double* const* tw, const double* const* twp, const RingPlan* plans, const double* blob, int nvars,
                   const double* in, long long in_vstride, int in_is_z, double* mirror, long long mirror_vstride,
                   double* out, long long out_vstride,
-                  const std::vector<std::vector<LWork>>* hostwork2 = nullptr, const LWork* const* work2 = nullptr);
+                  const std::vector<std::vector<LWork>>* hostwork2 = nullptr, const LWork* const* work2 = nullptr,
+                  double* fft3_scratch = nullptr);
 void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes,
                   const double* const* tw, const double* const* twp, const RingPlan* plans, const double* blob, int nvars,
@@ -145,6 +147,15 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   double* out, long long out_fstride, long long out_vstride, int out_is_phys, int var0,
                   const std::vector<std::vector<LWork>>* hostwork2 = nullptr, const LWork* const* work2 = nullptr);
 // v2 persistent ring FFT (sb_ringfft2.cu)
+bool fft3_enabled();                          // composite lengths L = 3 * 2^a available (A/B switch SB_FFT3=0)
+void fft3_class_tables(int L2, std::vector<double>& tab);   // appended to the class twiddles: TWB1[T] TWB2[T] C1[16] C2[16]
+size_t fft3_scratch_doubles(int L);           // forward kernel's parking area (per launch)
+void launch_inv_l3(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
+                   double* out, long long out_fs, long long out_vs, int out_is_phys, int var0);
+void launch_fwd_l3(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs, double* scratch);
 bool fft2_supported(int L, bool forward);
 int fft2_rows_per_item(int L, bool forward);
 void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,

@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -388,6 +389,18 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
       if (classes[i].L == L) return (int)i;
     FftClass c;
     c.L = L;
+    if (L % 3 == 0) {          // composite: three sub-FFTs of length L/3 (sb_ringfft2.cu k_*_l3)
+      c.R = 3; c.L2 = L / 3;
+      while ((1 << c.log2L) < c.L2) ++c.log2L;
+      c.fast = true;
+      fast_class_twiddles(c.L2, c.twp, c.twoff);
+      std::vector<double> extra;
+      fft3_class_tables(c.L2, extra);
+      c.twp.insert(c.twp.end(), extra.begin(), extra.end());
+      classes.push_back(std::move(c));
+      return (int)classes.size() - 1;
+    }
+    c.L2 = L;
     while ((1 << c.log2L) < L) ++c.log2L;
     c.tw.resize((size_t)2 * L);
     for (int t = 0; t < L; ++t) {
@@ -406,6 +419,11 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
     p.m = p.n / 4;
     int L = 4;
     while (L < 2 * p.m - 1) L *= 2;
+    // smooth lengths: 3/4 of the power of two is enough when 2m-1 <= 3 * 2^(a-2).  Measured on B200: 6144 beats 8192
+    // by 1.4x and 3072 beats 4096 slightly; 1536 only ties 2048 (three short sub-FFTs lose the pruning and
+    // the radix-8 final pass), so the default threshold is L >= 4096 (SB_FFT3_MINL overrides).
+    static const int minL = std::getenv("SB_FFT3_MINL") ? std::atoi(std::getenv("SB_FFT3_MINL")) : 4096;
+    if (fft3_enabled() && fast_class_supported(L) && L >= minL && L >= 2048 && L <= 8192 && 2 * p.m - 1 <= 3 * (L / 4)) L = 3 * (L / 4);
     p.L = L;
     p.cls = class_of(L);
     p.off = (long long)blob.size();
@@ -432,7 +450,29 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
       if (j > 0) { h[2 * (L - j)] = chirp[2 * j]; h[2 * (L - j) + 1] = -chirp[2 * j + 1]; }
     }
     const double invL = 1.0 / L;
-    if (classes[p.cls].fast) {
+    if (classes[p.cls].R == 3) {
+      // H[3k+r] = DFT_{L2}( (h[j] + w3^r h[j+L2] + w3^2r h[j+2 L2]) W_L^{jr} )[k]; each r kept in DIF16 order, [r][e][tl]
+      const int L2 = L / 3, T = L2 / 16;
+      typedef std::complex<long double> cld;
+      std::vector<double> hs((size_t)2 * L2);
+      for (int rr = 0; rr < 3; ++rr) {
+        for (int j = 0; j < L2; ++j) {
+          cld acc(0.0L, 0.0L);
+          for (int q = 0; q < 3; ++q) {
+            const cld hv((long double)h[2 * (j + q * L2)], (long double)h[2 * (j + q * L2) + 1]);
+            acc += hv * std::polar(1.0L, -2.0L * kPiL * (long double)((rr * q) % 3) / 3.0L);
+          }
+          acc *= std::polar(1.0L, -2.0L * kPiL * (long double)(((long long)j * rr) % L) / (long double)L);
+          hs[2 * j] = (double)acc.real(); hs[2 * j + 1] = (double)acc.imag();
+        }
+        host_fft_dif16(hs.data(), L2);
+        for (int tl = 0; tl < T; ++tl)
+          for (int e = 0; e < 16; ++e) {
+            FH[2 * ((size_t)rr * L2 + e * T + tl)] = hs[2 * (tl * 16 + e)] * invL;
+            FH[2 * ((size_t)rr * L2 + e * T + tl) + 1] = hs[2 * (tl * 16 + e) + 1] * invL;
+          }
+      }
+    } else if (classes[p.cls].fast) {
       // fast kernel: DIF16 order, laid out [e][tl] so that thread tl reads element tl*16+e coalesced
       host_fft_dif16(h.data(), L);
       const int T = L / 16;

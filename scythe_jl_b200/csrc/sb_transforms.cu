@@ -499,12 +499,19 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   const LWork* const* work, const std::vector<FftClass>& classes, const double* const* tw,
                   const double* const* twp, const RingPlan* plans, const double* blob, int nvars, const double* in,
                   long long in_vstride, int /*in_is_z*/, double* mirror, long long mirror_vstride, double* out,
-                  long long out_vstride, const std::vector<std::vector<LWork>>* hostwork2, const LWork* const* work2) {
+                  long long out_vstride, const std::vector<std::vector<LWork>>* hostwork2, const LWork* const* work2,
+                  double* fft3_scratch) {
   ProfScope prof_scope_(c, "fwd_l");
   for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
     int nwork = (int)hostwork[ci].size();
     if (!nwork) continue;
     int L = classes[ci].L;
+    if (classes[ci].R == 3) {
+      if (!hostwork2 || (*hostwork2)[ci].empty() || !fft3_scratch) throw std::runtime_error("composite FFT class without a v2 work list");
+      launch_fwd_l3(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+                    mirror_vstride, out, out_vstride, fft3_scratch);
+      continue;
+    }
     if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty()) {
       launch_fwd_l2(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
                     mirror_vstride, out, out_vstride);
@@ -620,6 +627,12 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     int nwork = (int)hostwork[ci].size();
     if (!nwork) continue;
     int L = classes[ci].L;
+    if (classes[ci].R == 3) {
+      if (!hostwork2 || (*hostwork2)[ci].empty()) throw std::runtime_error("composite FFT class without a v2 work list");
+      launch_inv_l3(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+                    out, out_fstride, out_vstride, out_is_phys, var0);
+      continue;
+    }
     if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty()) {
       launch_inv_l2(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
                     out, out_fstride, out_vstride, out_is_phys, var0);

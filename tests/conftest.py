@@ -9,6 +9,10 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 
+# exercise the composite (3 x 2^a) Bluestein lengths from L = 1536 up in the tests (the product default starts at 3072)
+os.environ.setdefault("SB_FFT3_MINL", "2048")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

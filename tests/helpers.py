@@ -73,6 +73,10 @@ def transform_cases():
         "RL_24cells_fft2": G.GridParameters(geometry="RL", xmin=0, xmax=24, num_cells=24, BCL={"h": B.R1T1}, vars={"h": 1}),
         "RLZ_22cells_fft2": G.GridParameters(geometry="RLZ", xmin=0, xmax=22, num_cells=22, zmin=0, zmax=5, zDim=8,
                                              BCL={"h": B.R1T1}, vars={"h": 1}),
+        # outer-tile rings with 512 < m <= 768: composite Bluestein length L = 1536 = 3 x 512 (three-team radix-3 split)
+        "RL_tile_fft3": G.GridParameters(geometry="RL", xmin=171, xmax=174, num_cells=3, vars={"h": 1, "u": 2}, spectralIndexL=172),
+        "RLZ_tile_fft3": G.GridParameters(geometry="RLZ", xmin=171, xmax=173, num_cells=2, zmin=0, zmax=5, zDim=8,
+                                          vars={"h": 1}, spectralIndexL=172),
         "RZ_z32_nobc": G.GridParameters(geometry="RZ", xmin=0, xmax=10, num_cells=13, zmin=0, zmax=5, zDim=32,
                                         vars={"s": 1, "w": 2}),
     }

@@ -59,6 +59,21 @@ def test_rz_north_star_config(gpu_lib):
     assert eB <= TRANSFORM_TOL and max(eP) <= TRANSFORM_TOL, (eB, eP)
 
 
+@pytest.mark.parametrize("sil,expect_L", [(172, 1536), (343, 3072), (690, 6144), (1000, 8192)])
+def test_outer_tile_rings_composite_bluestein_lengths(sil, expect_L, gpu_lib):
+    """Outer radial tiles of a multi-GPU patch (rings of up to 12,000 points): every convolution-length class,
+    including the composite 3 x 2^a ones, against the oracle (expect_L documents the class the rings fall into)."""
+    gp = G.GridParameters(geometry="RL", xmin=float(sil - 1), xmax=float(sil + 1), num_cells=2, vars={"h": 1, "u": 2},
+                          spectralIndexL=sil)
+    eB, eP = check_transforms(gp, gpu_lib, seed=sil)
+    assert eB <= TRANSFORM_TOL, eB
+    assert max(eP[:4]) <= TRANSFORM_TOL and eP[4] <= 1e-9, eP     # d2/dlambda2 of white noise: round-off x kDim^2
+    gz = G.GridParameters(geometry="RLZ", xmin=float(sil - 1), xmax=float(sil), num_cells=1, zmin=0, zmax=1e4, zDim=16,
+                          vars={"h": 1}, spectralIndexL=sil)
+    eB, eP = check_transforms(gz, gpu_lib, seed=sil + 1)
+    assert eB <= TRANSFORM_TOL and max(eP[:4]) <= TRANSFORM_TOL and max(eP[5:]) <= TRANSFORM_TOL and eP[4] <= 1e-9, (eB, eP)
+
+
 def test_long_radial_columns(gpu_lib):
     """b_rDim = 1203 (the C5 weak-scaling patch is 948): streaming banded solve with a 38 KB Cholesky table."""
     gp = G.GridParameters(geometry="R", xmin=0, xmax=1e6, num_cells=1200,
