@@ -675,7 +675,7 @@ int fft2_rows_per_item(int L, bool forward) {
   }
   const int T = L / 16, nteams = 512 / T;
   const int wave = forward ? (nteams / 2) : (nteams > 1 ? nteams / 2 : 1);   // rows in flight per CTA
-  return 8 * (wave < 1 ? 1 : wave);
+  return (forward ? 8 : 16) * (wave < 1 ? 1 : wave);
 }
 
 template <int LOG2L>
