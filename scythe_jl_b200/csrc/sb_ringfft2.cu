@@ -37,7 +37,10 @@ struct RCfg {
   static constexpr int TWRP = (TWR + 1) & ~1;
   static constexpr bool FH_SMEM = LOG2L <= 12;
   static constexpr bool CH_SMEM = LOG2L <= 11;
-  static constexpr bool TW0_SMEM = LOG2L <= 11;
+#ifndef SB_TW0_SMEM_MAX
+#define SB_TW0_SMEM_MAX 11
+#endif
+  static constexpr bool TW0_SMEM = LOG2L <= SB_TW0_SMEM_MAX;
   static constexpr size_t SMEM = sizeof(double2) * ((size_t)NTEAMS * LP + TWRP + (TW0_SMEM ? TW0 : 0) + (FH_SMEM ? L : 0) +
                                                    (CH_SMEM ? L / 2 : 0));
 };
