@@ -79,6 +79,7 @@ struct sb_grid {
   double* physical = nullptr;
   const double* slot0_src = nullptr;   // calcTendency's `physical .= var_np1` (src/semiimplicit.jl:731) deferred until slot 0 is read
   double* spectralB = nullptr;
+  bool owns_B = true;                  // false: spectralB aliases the patch's shared B (single-tile model)
   double* spectralA = nullptr;
   double* scratch = nullptr;
   long long scratch_doubles = 0;
@@ -496,7 +497,7 @@ static void grid_free(sb_grid* G) {
   cudaSetDevice(G->device);
   cudaStreamSynchronize(G->stream);
   for (void* p : G->owned) cudaFree(p);
-  cudaFree(G->physical); cudaFree(G->spectralB); cudaFree(G->spectralA); cudaFree(G->scratch); cudaFree(G->d_nan);
+  cudaFree(G->physical); if (G->owns_B) cudaFree(G->spectralB); cudaFree(G->spectralA); cudaFree(G->scratch); cudaFree(G->d_nan);
   if (G->ev0) cudaEventDestroy(G->ev0);
   if (G->ev1) cudaEventDestroy(G->ev1);
   delete G;
@@ -816,6 +817,11 @@ static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first
     tp.BCR = r0.data();
     TileState ts;
     ts.grid = grid_new(&tp, device, stream);
+    if (ntiles == 1) {   // one tile == the patch: its B *is* the shared B (no clear / assemble pass per step)
+      CU(cudaFree(ts.grid->spectralB));
+      ts.grid->spectralB = M->patch->spectralB;
+      ts.grid->owns_B = false;
+    }
     ts.grid->ensure_physical();
     const long long n = ts.grid->dg.N * V;
     ts.var_np1 = dev_zeros(n, M->stream);
@@ -877,6 +883,12 @@ static void tiles_tendency(sb_model* M) {
   sb_grid* P = M->patch;
   if (M->cs.on) {   // tile B stays tile-local; the z-mode-plane owners assemble and solve (sb_model_colsolve_solve)
     for (auto& T : M->tiles) { grid_forward(T.grid, T.var_np1, nullptr); T.grid->slot0_src = T.var_np1; }
+    return;
+  }
+  if (M->ntiles == 1 && !M->tiles[0].grid->owns_B) {   // the tile writes the shared B directly
+    TileState& T = M->tiles[0];
+    grid_forward(T.grid, T.var_np1, nullptr);
+    T.grid->slot0_src = T.var_np1;
     return;
   }
   CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
