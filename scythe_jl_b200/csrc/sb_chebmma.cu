@@ -17,26 +17,29 @@
 #include "sb_internal.hpp"
 
 #include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace sb {
 
 #define ZM_KT 6                 // k-tiles (of 4 modes) per parity  -> b_zDim <= 48
 #define ZM_KK (4 * ZM_KT)       // modes per parity held in smem
-#define ZM_CS 36                // column stride of the smem tile: 32 columns + 4 pad (== 4 mod 16: the
-                                // half-warp fragment load q*CS + i, q,i = 0..3 touches 16 distinct banks)
-#define ZM_THREADS 512
+// column stride of the smem tile = COLS + 4 (== 4 mod 16: the half-warp fragment load q*CS + i, q,i = 0..3
+// touches 16 distinct banks)
 
-// One persistent CTA per SM, 16 warps = (4 level tiles) x (4 column groups); the [mode][column] tile of the
-// NEXT work item streams into the second smem buffer with cp.async (LDGSTS) while the tensor cores
-// work on the current one.  CB = bytes per async copy (16 when every row is 16-byte aligned, else 8).
-template <int CB>
-__global__ void __launch_bounds__(ZM_THREADS, 1) k_inv_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles,
+// Persistent CTAs, warps = (4 level tiles) x (COLS/8 column groups); the [mode][column] tile of the NEXT work
+// item streams into the second smem buffer with cp.async (LDGSTS) while the tensor cores work on the
+// current one.  CB = bytes per async copy (16 when every row is 16-byte aligned, else 8).  COLS = 32: one
+// 512-thread CTA per SM; COLS = 16: two 256-thread CTAs per SM that drift out of phase, so one CTA's copy
+// issue / barrier overlaps the other's DMMA burst (each 32-column ZTile is split in two).
+template <int CB, int COLS>
+__global__ void __launch_bounds__(COLS * 16, 32 / COLS) k_inv_z_mma(DevGrid g, const ZTile* __restrict__ tiles, int ntiles,
                                                              int nvars, int var0, int nfields,
                                                              const double* __restrict__ in, long long in_fs,
                                                              long long in_vs, double* __restrict__ phys,
                                                              const double* __restrict__ parB) {
   SB_DYN_SMEM(double, a);       // [2 buffers][nfields][2 parities][ZM_KK][ZM_CS]
+  constexpr int ZM_CS = COLS + 4, ZM_THREADS = COLS * 16, SPLIT = 32 / COLS;
   const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = (ZM_THREADS / 32) / nzt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = lane & 3, i = lane >> 2;
@@ -53,8 +56,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k_inv_z_mma(DevGrid g, const ZT
   __syncthreads();
   const long long slotN = (long long)g.V * g.N;
   const int z0 = zt * 8 + 2 * q;                 // this lane's pair of levels (z0, z0+1) and mirror (zDim-2-z0, +1)
-  const int nwork = ntiles * nvars;
-  constexpr int CPR = 256 / CB, CE = CB / 8;     // copies per 32-column row, doubles per copy
+  const int nsub = ntiles * SPLIT;               // sub-tiles of COLS columns
+  const int nwork = nsub * nvars;
+  constexpr int CPR = COLS * 8 / CB, CE = CB / 8;     // copies per row, doubles per copy
   // per input row (field f, mode zb): {f, zb, offset of the row in the smem tile}; built once, so the copy
   // loop is a table look-up + two multiply-adds instead of two integer divisions per 16 bytes
   int4* rowtab = reinterpret_cast<int4*>(a + 2 * bufsz);
@@ -64,8 +68,16 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k_inv_z_mma(DevGrid g, const ZT
     rowtab[r] = make_int4(f, zb, ((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS, 0);
   }
   __syncthreads();
+  auto desc = [&](int w) {       // COLS-column sub-tile of a 32-column ZTile
+    const int s_ = w % nsub;
+    ZTile t = tiles[s_ / SPLIT];
+    const int off = (s_ % SPLIT) * COLS;
+    t.hcol0 += off; t.out_base += off;
+    t.ncols = t.ncols - off < COLS ? t.ncols - off : COLS;   // may be <= 0: empty sub-tile
+    return t;
+  };
   auto issue = [&](int w, const ZTile& ztile, double* dst) {
-    const int v = w / ntiles;
+    const int v = w / nsub;
     const double* src = in + (long long)v * in_vs + ztile.out_base;
     const int total = nrow * CPR;
     for (int c = tid; c < total; c += ZM_THREADS) {
@@ -82,19 +94,19 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) k_inv_z_mma(DevGrid g, const ZT
   // the next tile's descriptor is fetched before the barrier, so its L2 round trip overlaps the wait
   const int G = gridDim.x;
   int w = blockIdx.x, cur = 0;
-  ZTile zt0 = tiles[(w < nwork ? w : 0) % ntiles], zt1;
+  ZTile zt0 = desc(w < nwork ? w : 0), zt1;
   if (w < nwork) issue(w, zt0, a);
   for (; w < nwork; w += G) {
-    zt1 = tiles[(w + G < nwork ? w + G : w) % ntiles];
+    zt1 = desc(w + G < nwork ? w + G : w);
     sb_cp_wait<0>();
     __syncthreads();            // tile w has landed; everybody is done with the other buffer
     if (w + G < nwork) issue(w + G, zt1, a + (cur ^ 1) * bufsz);
-    const int v = w / ntiles;
+    const int v = w / nsub;
     const ZTile ztile = zt0;
     zt0 = zt1;
     const double* ab = a + cur * bufsz;
     double* const pv = phys + (long long)(var0 + v) * g.N;
-    for (int ct = cg; ct < 4; ct += ncg) {
+    for (int ct = cg; ct < COLS / 8; ct += ncg) {
       const int c = ct * 8 + i;
       const bool live = c < ztile.ncols;
       double* const o = pv + ((long long)ztile.hcol0 + c) * zDim;
@@ -164,27 +176,37 @@ void build_inv_z_mma_tables(int zDim, int bz, const double* T0, const double* T1
           }
 }
 
+template <int CB, int COLS>
+static void launch_inv_z_mma_t(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
+                               int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
+                               const double* parB) {
+  const size_t smem = (size_t)2 * nfields * 2 * ZM_KK * (COLS + 4) * sizeof(double) + (size_t)nfields * g.bz * 16;
+  cudaError_t e = cudaFuncSetAttribute(k_inv_z_mma<CB, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int nwork = ntiles * (32 / COLS) * nvars;
+  const int cap = 148 * (32 / COLS);
+  const int gx = nwork < cap ? nwork : cap;
+  SB_LAUNCH((k_inv_z_mma<CB, COLS>), dim3(gx), dim3(COLS * 16), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
+            in_fstride, in_vstride, phys, parB);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_z_mma launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
 void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, int nvars, int var0,
                       int nfields, const double* in, long long in_fstride, long long in_vstride, double* phys,
                       const double* parB) {
   ProfScope prof_scope_(c, "inv_z");
-  const size_t smem = (size_t)2 * nfields * 2 * ZM_KK * ZM_CS * sizeof(double) + (size_t)nfields * g.bz * 16;
   // 16-byte async copies need every [mode] row of every tile 16-byte aligned
   const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0 && in_vstride % 2 == 0 && (g.has_l || g.rDim % 2 == 0);
-  auto kern = al16 ? k_inv_z_mma<16> : k_inv_z_mma<8>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int nwork = ntiles * nvars;
-  const int gx = nwork < 148 ? nwork : 148;
-  if (al16)
-    SB_LAUNCH(k_inv_z_mma<16>, dim3(gx), dim3(ZM_THREADS), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
-              in_fstride, in_vstride, phys, parB);
-  else
-    SB_LAUNCH(k_inv_z_mma<8>, dim3(gx), dim3(ZM_THREADS), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
-              in_fstride, in_vstride, phys, parB);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_z_mma launch: ") + cudaGetErrorString(e));
-  if (c.launches) ++*c.launches;
+  static const bool wide = std::getenv("SB_INVZ_COLS") && std::atoi(std::getenv("SB_INVZ_COLS")) == 32;   // A/B switch
+  if (wide) {
+    if (al16) launch_inv_z_mma_t<16, 32>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
+    else launch_inv_z_mma_t<8, 32>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
+  } else {
+    if (al16) launch_inv_z_mma_t<16, 16>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
+    else launch_inv_z_mma_t<8, 16>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
+  }
 }
 
 // =====================================================================================
