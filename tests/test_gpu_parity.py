@@ -154,6 +154,65 @@ def test_north_star_horizontal_grid_matches_oracle(gpu_lib):
     assert max(eP[:4]) <= TRANSFORM_TOL and eP[4] <= 1e-10, eP
 
 
+def test_c4_full_size_vertical_exactness(gpu_lib):
+    """BASELINE.json's full C4 grid (334 cells, rings 8..4012 points, 64 levels, N = 128,897,280 points, one
+    variable): u = p(z), a degree-5 polynomial, must come back from spectralTransform!/gridTransform! with
+    u_z = p'(z), u_zz = p''(z) and zero radial / azimuthal derivatives at EVERY point -- constants pass the
+    spline filter and wavenumber 0 passes every ring's Bluestein plan exactly (all convolution-length classes,
+    the DMMA Chebyshev analysis/synthesis and the streaming spline solve at the size bench.py times)."""
+    zmax = 2.0e4
+    gp = S.GridParameters(geometry="RLZ", xmin=0, xmax=1e6, num_cells=334, zmin=0, zmax=zmax, zDim=64, vars={"u": 1})
+    g = S.createGrid(gp, lib=gpu_lib)
+    assert g.N == 128_897_280 and g.S == 29_054_455
+    zl = 0.5 * zmax * (1.0 - np.cos(np.pi * np.arange(64) / 63))
+    x = 2.0 * zl / zmax - 1.0                                   # [-1, 1]
+    c = np.array([0.3, -1.1, 0.7, 0.45, -0.6, 0.25])            # p(x) = sum c_k x^k
+    p0 = np.polyval(c[::-1], x)
+    p1 = np.polyval(np.polyder(c[::-1]), x) * (2.0 / zmax)
+    p2 = np.polyval(np.polyder(c[::-1], 2), x) * (2.0 / zmax) ** 2
+    ncol = g.N // 64
+    g.physical[:, 0, 0] = np.tile(p0, ncol)
+    S.spectralTransform(g)
+    S.gridTransform(g)
+    ph = g.physical[:, 0, :].reshape(ncol, 64, 7)
+    s0, s1, s2 = np.abs(p0).max(), np.abs(p1).max(), np.abs(p2).max()
+    assert np.abs(ph[:, :, 0] - p0).max() <= 1e-11 * s0
+    assert np.abs(ph[:, :, 5] - p1).max() <= 1e-10 * s1
+    assert np.abs(ph[:, :, 6] - p2).max() <= 1e-9 * s2          # second Chebyshev derivative amplifies round-off by ~zDim^4
+    dx = 1e6 / 334
+    assert np.abs(ph[:, :, 1]).max() <= 1e-9 * s0 / dx and np.abs(ph[:, :, 2]).max() <= 1e-8 * s0 / dx ** 2
+    assert np.abs(ph[:, :, 3]).max() <= 1e-10 * s0 and np.abs(ph[:, :, 4]).max() <= 1e-7 * s0
+    g.close()
+
+
+def test_c4_full_size_two_tiles_equal_one_tile(gpu_lib):
+    """bench.py's workload (C4, LinearAdvectionRLZ, synthetic vortex): two steps on one tile and on two radial
+    tiles with the plane-distributed solve must give the same state (seam overlap-add of the 3 shared spline
+    coefficients, tile-local evaluation of A) at the full 128.9 M-point size."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench as B
+    gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=B.XMAX, num_cells=B.C4_CELLS, zmin=0.0, zmax=B.ZMAX, zDim=B.ZDIM,
+                          vars={"h": 1, "u": 2, "v": 3})
+    mp = S.ModelParameters(ts=B.TS, integration_time=B.TS * 10, equation_set="LinearAdvectionRLZ", grid_params=gp,
+                           physical_params={"K": B.KDIFF})
+    DX = B.XMAX / B.C4_CELLS
+    finals = {}
+    for nt, ex in ((1, "torch"), (2, "columns")):
+        m = S.Model(mp, num_tiles=nt, lib=gpu_lib, exchange=ex)
+        tp = m.tile_params
+        ics = [B.synthetic_state(tp[0, t], DX, int(tp[2, t]), (int(tp[3, t]) - 1) * 3, B.ZDIM, B.ZMAX) for t in range(nt)]
+        m.initialize_tiles(ics)
+        m.run(2)
+        finals[nt] = np.concatenate([m.state(t, "var_np1") for t in range(nt)], axis=0)
+        m.close()
+    assert finals[1].shape == finals[2].shape == (128_897_280, 3)
+    for v in range(3):
+        assert rel_err(finals[2][:, v], finals[1][:, v]) <= 1e-11
+    assert np.isfinite(finals[1]).all() and np.abs(finals[1][:, 0]).max() > 1.0
+
+
 def test_linearity_rlz(gpu_lib):
     gp = S.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=30, zmin=0, zmax=1e4, zDim=64, vars={"a": 1, "b": 2, "c": 3})
     g = S.createGrid(gp, lib=gpu_lib)
