@@ -175,9 +175,11 @@ int sb_model_output(sb_model_t m, double* host_physical);
 /* ModelTile state arrays of local tile i <-> host [N_tile,V]:
  * which = 0 var_np1, 1 expdot_n, 2 expdot_nm1, 3 expdot_nm2, 4 impdot_n, 5 impdot_nm1, 6 impdot_nm2 */
 int sb_model_get_state(sb_model_t m, int32_t tile, int32_t which, double* host);
-/* var_np1 of local tile i <- host [N_tile,V] (which must be 0).  Restart / host-driven stepping:
- * the reference restarts from an output file the same way (physical_out_*.csv as the next
- * initial_conditions, notebooks/Cha_Bell_WCD2024_initialization.ipynb:196). */
+/* state of local tile i <- host [N_tile,V]: which = 0 var_np1, 2/3 expdot_nm1/nm2, 5/6 impdot_nm1/nm2 (the
+ * numbering of sb_model_get_state; 1 and 4 are transient).  Restart / host-driven stepping: the reference
+ * restarts from an output file (physical_out_*.csv as the next initial_conditions,
+ * notebooks/Cha_Bell_WCD2024_initialization.ipynb:196) and re-enters the Euler/AB2 start-up because the
+ * AB3 history of src/semiimplicit.jl:685-695 is not saved; setting the history too makes a restart exact. */
 int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* host);
 /* calcTendency for every local tile (src/semiimplicit.jl:728-735: physical[:,:,1] <- var_np1,
  * spectralTransform!) followed by the own-block / halo assembly into the shared B buffer (:320-329).

@@ -1317,9 +1317,14 @@ int sb_model_get_state(sb_model_t m, int32_t tile, int32_t which, double* host) 
 }
 int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* host) {
   return guarded([&] {
-    if (!m || !host || tile < 0 || tile >= (int)m->tiles.size() || which != 0) throw std::invalid_argument("bad argument");
+    if (!m || !host || tile < 0 || tile >= (int)m->tiles.size() || which < 0 || which > 6 || which == 1 || which == 4)
+      throw std::invalid_argument("bad argument (which: 0 var_np1, 2/3 expdot_nm1/nm2, 5/6 impdot_nm1/nm2)");
     TileState& T = m->tiles[tile];
-    CU(cudaMemcpyAsync(T.var_np1, host, (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    // history as sb_model_get_state reports it after a step: nm1 = buffer 1, nm2 = buffer 2 of the rotation
+    double* dst = which == 0 ? T.var_np1 : (which <= 3 ? T.expd[which - 1] : T.impd[which - 4]);
+    if (!dst) throw std::invalid_argument("state array not allocated (semi-implicit off)");
+    CU(cudaMemcpyAsync(dst, host, (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
   });
 }
 int sb_model_tendency(sb_model_t m) {
