@@ -213,6 +213,46 @@ def test_c4_full_size_two_tiles_equal_one_tile(gpu_lib):
     assert np.isfinite(finals[1]).all() and np.abs(finals[1][:, 0]).max() > 1.0
 
 
+def test_notebook_run_through_integrate_model_and_csv(gpu_lib, tmp_path):
+    """The reference's only end-to-end known answer (notebooks/LinearAdvection_example.ipynb: R grid, 100 cells,
+    PERIODIC, 2 workers, 2000 steps of 0.05 s, output every 50 s) through the driver a Scythe user calls:
+    initial conditions from a CSV (read_physical_grid, src/semiimplicit.jl:134), integrate_model
+    (src/Scythe.jl:37-62), physical_out_<t>.csv files named as src/io.jl:5 does.  Checked against the notebook's
+    printed values (sanity band) and against the oracle's run of the same model (<= 1e-9)."""
+    import json
+    from pathlib import Path
+    from oracle import model as OM
+    gold = json.loads((Path(__file__).parent / "golden" / "linear_advection_notebook.json").read_text())
+    gp = S.GridParameters(geometry="R", xmin=-50.0, xmax=50.0, num_cells=100, BCL={"u": S.CubicBSpline.PERIODIC},
+                          BCR={"u": S.CubicBSpline.PERIODIC}, vars={"u": 1})
+    g = S.createGrid(gp, lib=gpu_lib)
+    x = S.getGridpoints(g)
+    g.close()
+    ic_csv = tmp_path / "gaussian_ic.csv"
+    np.savetxt(ic_csv, np.stack([x, np.exp(-(x / 20.0) ** 2)], 1), delimiter=",", header="r,u", comments="", fmt="%.17g")
+    mp = S.ModelParameters(ts=0.05, integration_time=100.0, output_interval=50.0, equation_set="LinearAdvection1D",
+                           initial_conditions=str(ic_csv), output_dir=str(tmp_path / "out"), grid_params=gp,
+                           physical_params={"c_0": 1.0, "K": 0.0})
+    final = S.integrate_model(mp, num_tiles=2, write=True, lib=gpu_lib)
+    files = sorted(p.name for p in (tmp_path / "out").iterdir())
+    assert files == ["physical_out_0.0.csv", "physical_out_100.0.csv", "physical_out_50.0.csv"]
+    csv = np.loadtxt(tmp_path / "out" / "physical_out_100.0.csv", delimiter=",", skiprows=1)
+    assert np.array_equal(csv[:, 0], x) and np.array_equal(csv[:, 1], final[:, 0, 0])
+    uf = final[:, 0, 0]
+    got = np.concatenate([uf[:13], uf[-12:]])
+    band = np.array(gold["final_u_first13"] + gold["final_u_last12"])
+    assert np.abs(got / band - 1).max() < 5e-3
+    u0 = np.loadtxt(tmp_path / "out" / "physical_out_0.0.csv", delimiter=",", skiprows=1)[:, 1]
+    assert abs(np.sqrt(((u0 - uf) ** 2).sum()) / gold["l2_norm"] - 1) < 0.05
+    ogp = G.GridParameters(geometry="R", xmin=-50.0, xmax=50.0, num_cells=100, BCL={"u": spl.PERIODIC},
+                           BCR={"u": spl.PERIODIC}, vars={"u": 1})
+    omp = OM.ModelParameters(ts=0.05, integration_time=100.0, output_interval=50.0, equation_set="LinearAdvection1D",
+                             grid_params=ogp, physical_params={"c_0": 1.0, "K": 0.0})
+    run = OM.ModelRun(omp, 2, np.exp(-(x / 20.0) ** 2)[:, None])
+    run.run(2000)
+    assert rel_err(uf, run.output_patch()[:, 0, 0]) <= STATE_TOL
+
+
 def test_linearity_rlz(gpu_lib):
     gp = S.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=30, zmin=0, zmax=1e4, zDim=64, vars={"a": 1, "b": 2, "c": 3})
     g = S.createGrid(gp, lib=gpu_lib)

@@ -57,3 +57,29 @@ def test_checkpoint_restart_is_exact(name, ntiles, exchange, emu_lib, tmp_path):
         for k in ("var_np1", "expdot_nm1", "expdot_nm2"):
             assert np.array_equal(a.state(i, k), b.state(i, k)), (i, k)
     a.close(); b.close()
+
+
+def test_integrate_model_driver_and_csv_files(emu_lib, tmp_path):
+    """integrate_model (src/Scythe.jl:37-62): CSV initial conditions in, physical_out_<t>.csv out at the output
+    cadence of model_loop (src/semiimplicit.jl:288-293), file names as src/io.jl:5; final state == oracle."""
+    import numpy as np
+    import scythe_jl_b200 as S
+    from helpers import run_oracle, rel_err
+    case = dict(M_CASES["LinearAdvection1D"])
+    from helpers import to_pkg
+    gp = to_pkg(case["gp"])
+    g = S.createGrid(gp, lib=emu_lib)
+    x = S.getGridpoints(g)
+    g.close()
+    ic = tmp_path / "ic.csv"
+    np.savetxt(ic, np.stack([x, case["ic"][:, 0]], 1), delimiter=",", header="r,u", comments="", fmt="%.17g")
+    mp = S.ModelParameters(ts=case["ts"], integration_time=case["ts"] * 6, output_interval=case["ts"] * 3,
+                           equation_set=case["eq"], initial_conditions=str(ic), output_dir=str(tmp_path / "out"),
+                           grid_params=gp, physical_params=case["prm"])
+    final = S.integrate_model(mp, num_tiles=3, write=True, lib=emu_lib)
+    names = sorted(p.name for p in (tmp_path / "out").iterdir())
+    assert names == ["physical_out_0.0.csv", "physical_out_0.15.csv", "physical_out_0.3.csv"]
+    case["n"] = 6
+    assert rel_err(final[:, 0, 0], run_oracle(case, 3).output_patch()[:, 0, 0]) <= STATE_TOL
+    with pytest.raises(S.ScytheError):
+        S.integrate_model(mp, num_tiles=0, lib=emu_lib)      # "Need to add at least 1 worker process" (src/Scythe.jl:39-41)
