@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=0, help="override radial cells per GPU tile (debug)")
+    ap.add_argument("--equation-set", default="LinearAdvectionRLZ",
+                    choices=["LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL"],
+                    help="C4 step to time: the transform-dominated linear set (headline) or the 6-variable TC boundary-layer set")
+    ap.add_argument("--no-tcbl", action="store_true", help="skip the secondary C4 run of the TC boundary-layer equation set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -76,6 +80,19 @@ def synthetic_state(xmin, DX, num_cells, patch_offset, zDim, zmax, out=None):
     out[:, 0] = (hh[:, None] * zh[None, :]).reshape(-1)
     out[:, 1] = (uu[:, None] * zw[None, :]).reshape(-1)
     out[:, 2] = (vv[:, None] * zw[None, :]).reshape(-1)
+    return out
+
+
+def synthetic_state_tcbl(xmin, DX, num_cells, patch_offset, zDim, zmax):
+    """h, ug, vg as synthetic_state; boundary-layer winds ub, vb relax to the gradient wind above ~1 km; wb = 0."""
+    base = synthetic_state(xmin, DX, num_cells, patch_offset, zDim, zmax)
+    z = 0.5 * zmax * (1.0 - np.cos(np.pi * np.arange(zDim) / (zDim - 1)))
+    prof = np.tile(1.0 - np.exp(-(z + 50.0) / 300.0), base.shape[0] // zDim)
+    out = np.empty((base.shape[0], 6), order="F")
+    out[:, :3] = base
+    out[:, 3] = base[:, 1] * prof - 0.2 * base[:, 2] * (1.0 - prof)
+    out[:, 4] = base[:, 2] * prof
+    out[:, 5] = 0.0
     return out
 
 
@@ -168,11 +185,11 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(ngpus, cells_per_tile):
+def workload_config(ngpus, cells_per_tile, eq="LinearAdvectionRLZ", nvars=3):
     total_cells = int(round(cells_per_tile * math.sqrt(ngpus)))
-    return {"workload": "C4 RLZ LinearAdvectionRLZ" if ngpus == 1 else "C5 RLZ radius-scaled, one C4-sized tile per GPU",
-            "geometry": "RLZ", "num_cells": total_cells, "zDim": ZDIM, "b_zDim": 43, "vars": NVARS,
-            "equation_set": "LinearAdvectionRLZ", "tiles": ngpus, "ts": TS,
+    return {"workload": f"C4 RLZ {eq}" if ngpus == 1 else "C5 RLZ radius-scaled, one C4-sized tile per GPU",
+            "geometry": "RLZ", "num_cells": total_cells, "zDim": ZDIM, "b_zDim": 43, "vars": nvars,
+            "equation_set": eq, "tiles": ngpus, "ts": TS,
             "exchange": ("none (one tile)" if ngpus == 1 else
                          "z-mode planes of the spline solve dealt over ranks; NCCL send/recv of tile-sized slabs, no collective"),
             "l2": "working set >> 126 MB L2 (physical 21.7 GB/GPU); no flush needed",
@@ -198,14 +215,26 @@ def run_ours(args):
     cells_tile = args.cells or C4_CELLS
     total_cells = int(round(cells_tile * math.sqrt(ntiles)))
     DX = XMAX / C4_CELLS
-    gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * total_cells, num_cells=total_cells, zmin=0.0, zmax=ZMAX,
-                          zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
-    mp = S.ModelParameters(ts=TS, integration_time=TS * 1000, equation_set="LinearAdvectionRLZ", grid_params=gp,
-                           physical_params={"K": KDIFF})
+    tcbl = args.equation_set != "LinearAdvectionRLZ"
+    global NVARS
+    if tcbl:
+        NVARS = 6
+        names = ["h", "u", "v", "ub", "vb", "wb"]
+        gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * total_cells, num_cells=total_cells, zmin=0.0, zmax=ZMAX,
+                              zDim=ZDIM, vars={n: i + 1 for i, n in enumerate(names)},
+                              BCL={"h": S.CubicBSpline.R1T1, "u": S.CubicBSpline.R1T0, "v": S.CubicBSpline.R1T0,
+                                   "ub": S.CubicBSpline.R1T0, "vb": S.CubicBSpline.R1T0, "wb": S.CubicBSpline.R1T1})
+        mp = S.ModelParameters(ts=0.5, integration_time=500.0, equation_set=args.equation_set, grid_params=gp,
+                               physical_params=dict(g=9.81, Kh=1500.0, Cd=2.4e-3, Hfree=2000.0, f=5e-5, Um=3.0, Vm=-2.0))
+    else:
+        gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * total_cells, num_cells=total_cells, zmin=0.0, zmax=ZMAX,
+                              zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
+        mp = S.ModelParameters(ts=TS, integration_time=TS * 1000, equation_set="LinearAdvectionRLZ", grid_params=gp,
+                               physical_params={"K": KDIFF})
     m = S.Model(mp, num_tiles=ntiles, device=local_rank, distributed=distributed)
     tp = m.tile_params
     tcells, tsil = int(tp[2, m.tile_first]), int(tp[3, m.tile_first])
-    ic = synthetic_state(tp[0, m.tile_first], DX, tcells, (tsil - 1) * 3, ZDIM, ZMAX)
+    ic = (synthetic_state_tcbl if tcbl else synthetic_state)(tp[0, m.tile_first], DX, tcells, (tsil - 1) * 3, ZDIM, ZMAX)
     m.initialize_tiles([ic])
     m.sync()
     tile = m.tiles[0]
@@ -302,7 +331,7 @@ def run_ours(args):
         "K3 tileTransform! (inv_r+inv_l+inv_z)": (["inv_r", "inv_l", "inv_z"], 8.0 * V * (Sg + N * D)),
         "K1 spectralTransform! (fwd_z+fwd_l+fwd_r)": (["fwd_z", "fwd_l", "fwd_r"], 8.0 * V * (N + Sg)),
         "K2 splineTransform! (spline_solve)": (["spline_solve"], 8.0 * V * 2 * Sp),
-        "K4 equation set + AB3 (LinearAdvectionRLZ)": (["equation_set"], 8.0 * N * (5 + 2 + 6 + 6)),
+        f"K4 equation set + AB3 ({args.equation_set})": (["equation_set"], 8.0 * N * ((5 + 2 + 6 + 6) if not tcbl else (26 + 10 + 13))),
     }
     detail = {}
     for name, (ks, nbytes) in groups.items():
@@ -315,7 +344,7 @@ def run_ours(args):
     # measured DRAM traffic / FP64-pipe activity of the same step from the committed ncu pass (profiles/), if present
     traffic, ncu_note = None, None
     prof_file = ROOT / "profiles" / "r1g_step_kernels.json"
-    if prof_file.exists() and world == 1 and cells_tile == C4_CELLS:
+    if prof_file.exists() and world == 1 and cells_tile == C4_CELLS and not tcbl:
         pk = json.loads(prof_file.read_text())["one_step"]
         sel = {"K3": ("k_inv_r", "k_inv_l", "k_inv_z"), "K1": ("k_fwd_z", "k_fwd_l", "k_fwd_r"), "K2": ("k_spline",),
                "K4": ("k_pointwise",)}[top[:2]]
@@ -334,12 +363,26 @@ def run_ours(args):
     step_bytes = 8.0 * V * (2 * N * D + 6 * N + 4 * Sg)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world, cells_tile), "clocks": clocks, "e2e": e2e,
+            "data": "synthetic", "config": workload_config(world, cells_tile, args.equation_set, NVARS), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "per_rank_kernel_ms": per_rank, "roofline": roof, "roofline_detail": detail, "kernel_ms_per_step": kern_ms,
             "timestep_algorithmic_GB": step_bytes / 1e9,
             "timestep_frac_of_hbm_roofline": (step_bytes / 1e9) / (ms_step / 1e3) / peak,
             "transforms_per_s": {"spectralTransform_K1": 1e3 / k1_ms, "gridTransform_K2K3": 1e3 / k23_ms,
                                  "K1_ms": k1_ms, "K2K3_ms": k23_ms, "vars": V}}
+    if world == 1 and not tcbl and not args.no_tcbl and not args.cells:
+        # secondary number (north_star item 4): the same C4 grid stepped with the 6-variable height-resolved TC
+        # boundary-layer set, in a fresh process once this model's 60 GB are released
+        m.close()
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--equation-set", "Oneway_ShallowWater_HeightResolvedBL",
+                                "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"], capture_output=True,
+                               text=True, timeout=600)
+            t2 = json.loads(r.stdout.strip().splitlines()[-1])
+            line["tcbl"] = {"equation_set": "Oneway_ShallowWater_HeightResolvedBL", "vars": 6, "value": t2["value"], "unit": UNIT,
+                            "ms_per_step": t2["ms_per_step"], "kernel_ms_per_step": t2["kernel_ms_per_step"],
+                            "timestep_frac_of_hbm_roofline": t2["timestep_frac_of_hbm_roofline"]}
+        except Exception as e:  # the headline line must still print
+            line["tcbl"] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"], _ = cpu_baseline()
     else:

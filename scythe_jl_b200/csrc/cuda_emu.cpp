@@ -12,6 +12,7 @@ thread_local int t_lin;
 std::barrier<>* g_block_barrier = nullptr;
 std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
 double g_warp_buf[64][32];
+double g_warp_buf2[64][32];
 unsigned char* g_dyn_smem = nullptr;
 
 static std::mutex g_named_mu;

@@ -51,6 +51,7 @@ extern thread_local int t_lin;            // linear thread id in block
 extern std::barrier<>* g_block_barrier;
 extern std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
 extern double g_warp_buf[64][32];
+extern double g_warp_buf2[64][32];
 extern unsigned char* g_dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 }  // namespace sbemu
@@ -134,14 +135,16 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 // FP64 tensor-core MMA m8n8k4 (row.col): A[i][k] from lane i*4+k, B[k][j] from lane j*4+k,
 // D[i][2q..2q+1] in lane i*4+q
 static inline void sb_dmma(double& d0, double& d1, double a, double b) {
-  const int lane = sbemu::t_lin % 32, i = lane / 4, q = lane % 4;
+  const int w = sbemu::t_lin / 32, lane = sbemu::t_lin % 32, i = lane / 4, q = lane % 4;
+  sbemu::g_warp_buf[w][lane] = a;
+  sbemu::g_warp_buf2[w][lane] = b;
+  sbemu::g_warp_barriers[w]->arrive_and_wait();
   for (int k = 0; k < 4; ++k) {
-    double aik = __shfl_sync(0xffffffffu, a, i * 4 + k);
-    double b0 = __shfl_sync(0xffffffffu, b, (2 * q) * 4 + k);
-    double b1 = __shfl_sync(0xffffffffu, b, (2 * q + 1) * 4 + k);
-    d0 += aik * b0;
-    d1 += aik * b1;
+    const double aik = sbemu::g_warp_buf[w][i * 4 + k];
+    d0 += aik * sbemu::g_warp_buf2[w][(2 * q) * 4 + k];
+    d1 += aik * sbemu::g_warp_buf2[w][(2 * q + 1) * 4 + k];
   }
+  sbemu::g_warp_barriers[w]->arrive_and_wait();
 }
 // asynchronous global->shared copies (LDGSTS): the emulation copies at once
 static inline void sb_cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }

@@ -633,6 +633,7 @@ struct sb_model {
   std::vector<TileState> tiles;
   std::vector<void*> owned;
   double* d_colops = nullptr;
+  double* d_colfrag = nullptr;
   double* d_refstate = nullptr;
   double* d_sicols = nullptr;
   std::vector<double> ref_host;  // [3][3][zDim]
@@ -736,6 +737,13 @@ static void build_column_ops(sb_model* M) {
     composite(ct.T1, IG, tmp); transpose_into(tmp, ops.data() + nn);
     composite(ct.Tint, IG, tmp); transpose_into(tmp, ops.data() + 2 * nn);
     M->d_colops = dev_upload(ops); M->owned.push_back(M->d_colops);
+    if (nz % 8 == 0 && nz <= 64) {   // tensor-core column operators (k_heightresolved_bl2)
+      std::vector<double> frag, f2;
+      build_colop_fragments(nz, ops.data() + 2 * nn, frag);
+      build_colop_fragments(nz, ops.data() + nn, f2);
+      frag.insert(frag.end(), f2.begin(), f2.end());
+      M->d_colfrag = dev_upload(frag); M->owned.push_back(M->d_colfrag);
+    }
   }
   if (M->eq == EQ_Euler_test) {
     M->d_refstate = dev_upload(M->ref_host); M->owned.push_back(M->d_refstate);
@@ -870,7 +878,7 @@ static void tiles_physics(sb_model* M, int64_t t) {
     a.phys = G->physical; a.var_np1 = T.var_np1;
     a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
     a.imp_n = T.impd[0]; a.imp_nm1 = T.impd[1]; a.imp_nm2 = T.impd[2];
-    a.colops = M->d_colops; a.refstate = M->d_refstate; a.sicols = M->d_sicols;
+    a.colops = M->d_colops; a.colfrag = M->d_colfrag; a.refstate = M->d_refstate; a.sicols = M->d_sicols;
     launch_equation_set(G->ctx(), M->eq, G->dg, M->ep, a, (int)std::min<int64_t>(t, 3));  // :308-314
     // history rotation (:685-695): nm2 <- nm1 <- n ; the old nm2 buffer becomes next step's n
     std::rotate(T.expd, T.expd + 2, T.expd + 3);

@@ -213,10 +213,12 @@ struct ModelArrays {
   double* imp_nm1;
   double* imp_nm2;
   const double* colops;   // [4][zDim][zDim]: CB->CA->{CI, CIx, CIInt} of "h", (spare)
+  const double* colfrag;  // DMMA B fragments of colops 2 (CIInt) and 1 (CIx): [2][zDim/8][zDim/4][32]; null if zDim % 8
   const double* refstate; // [3 profiles][3][zDim] sbar, xibar, mubar (value, dz, dzz)
   const double* helm;     // [2][zDim][zDim] inverse Helmholtz matrices (tau=0.5 ts, 1.25 ts)
   const double* sicols;   // [2 vars (xi,w)][3][zDim][zDim] composite column operators for semi-implicit
 };
+void build_colop_fragments(int nz, const double* Mt /*[k][z]*/, std::vector<double>& out);
 void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p,
                          const ModelArrays& a, int tstep);
 

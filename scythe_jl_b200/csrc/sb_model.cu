@@ -8,6 +8,7 @@
 #include "sb_internal.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -211,6 +212,113 @@ __global__ void k_heightresolved_bl(DevGrid g, EqParams p, ModelArrays a, int t)
   c.advance(5, t, p.ts, wb, 0.0);
 }
 
+
+// ------------------------------------------------------------------------------------
+// tensor-core version: the three 64x64 column operators (integral of the divergence, d/dz of the two
+// vertical fluxes) of 8 columns at a time are [8 x 64].[64 x 64] products on DMMA (mma.sync.m8n8k4.f64):
+// 384 DMMA per 8 columns instead of 3 x 64 x (matrix load + broadcast load + FMA) per point.  block =
+// (zDim levels, 8 columns); warp w: level tile nt = w % (zDim/8); products 1 and 2 share the d/dz operator.
+// colfrag: [2][zDim/8][zDim/4][32] B fragments (host: build_colop_fragments), read through L1.
+#define HB_COLS 8
+__global__ void __launch_bounds__(512, 2) k_heightresolved_bl2(DevGrid g, EqParams p, ModelArrays a, int t, long long ngroups) {
+  SB_DYN_SMEM(double, sm);
+  const int nz = g.zDim, z = threadIdx.x, cl = threadIdx.y;
+  const int xs = nz + 4;                       // row stride of X / O (== 4 mod 16: conflict-free fragment loads)
+  double* X = sm;                              // [3][HB_COLS][xs]
+  double* O = sm + (size_t)3 * HB_COLS * xs;   // [3][HB_COLS][xs]
+  double* sfc = O + (size_t)3 * HB_COLS * xs;  // [HB_COLS][2] storm-motion surface wind of the column
+  const int tid = cl * nz + z, lane = tid & 31, warp = tid >> 5;
+  const int q = lane & 3, li = lane >> 2;
+  const int nnt = nz >> 3, nkt = nz >> 2;
+  // per-thread constants (the level is fixed for the thread's whole life)
+  const double zz = g.zlev[z];
+  const double lmix = 1.0 / ((1.0 / (0.4 * zz)) + (1.0 / 80.0));
+  const double lmix2 = lmix * lmix;
+  const double gg = p.g, Kh = p.Kh, Hfree = p.Hfree, f = p.f;
+  auto product = [&](int m, int mat) {   // O[m] = X[m] . colop[mat]   (this warp's level tile)
+    const int nt = warp % nnt;
+    const double* bf = a.colfrag + ((size_t)(mat * nnt + nt) * nkt) * 32 + lane;
+    const double* xa = X + (m * HB_COLS + li) * xs + q;
+    double d0 = 0.0, d1 = 0.0;
+    for (int kt = 0; kt < nkt; ++kt) sb_dmma(d0, d1, xa[kt * 4], bf[kt * 32]);
+    *reinterpret_cast<double2*>(O + (m * HB_COLS + li) * xs + nt * 8 + 2 * q) = make_double2(d0, d1);
+  };
+  for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const long long col = grp * HB_COLS + cl;
+    const bool live = col < g.hpoints;
+    const long long i = live ? col * nz + z : 0;
+    PointCtx c{g, a, i};
+    const int ring = live ? g.h2r[col] : 0;
+    const double r = g.rad[ring];
+    // one reciprocal per point instead of ~25 FP64 divisions (each a ~25-instruction Newton sequence)
+    const double ri_ = 1.0 / r, ri2 = ri_ * ri_;
+    double h = c.P(0, 0), hr = c.P(0, 1), hl = c.P(0, 3);
+    double ug = c.P(1, 0), ugr = c.P(1, 1), ugl = c.P(1, 3);
+    double vg = c.P(2, 0), vgr = c.P(2, 1), vgl = c.P(2, 3);
+    double ub = c.P(3, 0), ubr = c.P(3, 1), ubrr = c.P(3, 2), ubl = c.P(3, 3), ubll = c.P(3, 4), ubz = c.P(3, 5);
+    double vb = c.P(4, 0), vbr = c.P(4, 1), vbrr = c.P(4, 2), vbl = c.P(4, 3), vbll = c.P(4, 4), vbz = c.P(4, 5);
+    const double Kv = lmix2 * sqrt((ubz * ubz) + (vbz * vbz));
+    X[(0 * HB_COLS + cl) * xs + z] = -((ub * ri_) + ubr + (vbl * ri_));
+    X[(1 * HB_COLS + cl) * xs + z] = ub;
+    X[(2 * HB_COLS + cl) * xs + z] = vb;
+    if (z == 0) {   // storm-motion surface wind rotated by the column's azimuth: once per column
+      const int jring = (int)(col - g.ring_hoff[ring]);
+      const int n = g.ring_n[ring], rix = g.ring_ri[ring];
+      const double dl = 6.283185307179586476925286766559 / n;
+      const double lam = 0.5 * dl * (rix - 1) + dl * jring;
+      double sl, cl_;
+      sincos(lam, &sl, &cl_);
+      sfc[2 * cl] = (p.Um * cl_) + (p.Vm * sl);
+      sfc[2 * cl + 1] = (p.Vm * cl_) - (p.Um * sl);
+    }
+    __syncthreads();
+    // 10 m wind = level 2 of the column
+    const double u10 = X[(1 * HB_COLS + cl) * xs + 1] + sfc[2 * cl], v10 = X[(2 * HB_COLS + cl) * xs + 1] + sfc[2 * cl + 1];
+    if (warp < nnt) product(0, 0);               // wb = CIInt(divergence)
+    const double U10 = sqrt(u10 * u10 + v10 * v10);
+    double Cd = p.Cd;
+    if (U10 < 5.2) Cd = 1.0e-3;
+    else if (U10 < 33.6) Cd = 4.4e-4 * sqrt(U10);
+    __syncthreads();
+    X[(1 * HB_COLS + cl) * xs + z] = (z == 0) ? Cd * U10 * u10 : Kv * ubz;
+    X[(2 * HB_COLS + cl) * xs + z] = (z == 0) ? Cd * U10 * v10 : Kv * vbz;
+    __syncthreads();
+    product(1 + warp / nnt, 1);                  // d/dz of the two vertical fluxes (2 * nnt warps == all warps)
+    __syncthreads();
+    if (live) {
+      const double wb = O[(0 * HB_COLS + cl) * xs + z];
+      const double vdu = O[(1 * HB_COLS + cl) * xs + z], vdv = O[(2 * HB_COLS + cl) * xs + z];
+      c.setP(5, 0, wb);
+      double e0 = ((-vg * hl * ri_) + (-ug * hr)) + (-(Hfree + h) * ((ug * ri_) + ugr + (vgl * ri_)));
+      double e1 = ((-vg * ugl * ri_) + (-ug * ugr)) + (-gg * hr) + (vg * (f + (vg * ri_)));
+      double e2 = ((-vg * vgl * ri_) + (-ug * vgr)) + (-gg * (hl * ri_)) + (-ug * (f + (vg * ri_)));
+      double hdu = Kh * ((ubr * ri_) + ubrr - (ub * ri2) + (ubll * ri2) - (2.0 * vbl * ri2));
+      double hdv = Kh * ((vbr * ri_) + vbrr - (vb * ri2) + (vbll * ri2) + (2.0 * ubl * ri2));
+      double e3 = ((-vb * ubl * ri_) + (-ub * ubr) + (-wb * ubz)) + (-gg * hr) + (vb * (f + (vb * ri_))) + vdu + hdu;
+      double e4 = ((-vb * vbl * ri_) + (-ub * vbr) + (-wb * vbz)) + (-gg * (hl * ri_)) + (-ub * (f + (vb * ri_))) + vdv + hdv;
+      c.advance(0, t, p.ts, h, e0);
+      c.advance(1, t, p.ts, ug, e1);
+      c.advance(2, t, p.ts, vg, e2);
+      c.advance(3, t, p.ts, ub, e3);
+      c.advance(4, t, p.ts, vb, e4);
+      c.advance(5, t, p.ts, wb, 0.0);
+    }
+    // (the next iteration's first writes to X / sfc are ordered behind this iteration's reads by the barriers above:
+    //  X[0..2] were last read before the final barrier; O is rewritten only after the next two barriers)
+  }
+}
+
+// B fragments of a transposed column operator Mt[k][z] (out[z] = sum_k Mt[k][z] x[k]): [zDim/8][zDim/4][32],
+// lane = (level n = lane/4 of the tile, k = lane%4 of the k-tile)
+void build_colop_fragments(int nz, const double* Mt, std::vector<double>& out) {
+  const int nnt = nz / 8, nkt = nz / 4;
+  out.assign((size_t)nnt * nkt * 32, 0.0);
+  for (int nt = 0; nt < nnt; ++nt)
+    for (int kt = 0; kt < nkt; ++kt)
+      for (int lane = 0; lane < 32; ++lane)
+        out[((size_t)nt * nkt + kt) * 32 + lane] = Mt[(size_t)(kt * 4 + lane % 4) * nz + nt * 8 + lane / 4];
+}
+
 // ---- thermodynamic closure for Euler_test (src/thermodynamics.jl:2-17,31-32,67-80,184-269) ----
 #define TH_Rd 287.04
 #define TH_Rv 461.50
@@ -367,6 +475,14 @@ void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqP
     case EQ_Oneway_ShallowWater_Slab: launch_pw<EQ_Oneway_ShallowWater_Slab>(c, g, p, a, tstep); break;
     case EQ_Twoway_ShallowWater_Slab: launch_pw<EQ_Twoway_ShallowWater_Slab>(c, g, p, a, tstep); break;
     case EQ_Oneway_ShallowWater_HeightResolvedBL: {
+      static const bool v1 = std::getenv("SB_TCBL_V1") != nullptr;   // A/B switch
+      if (a.colfrag && !v1 && g.zDim % 8 == 0 && g.zDim <= 64) {
+        long long ngroups = (g.hpoints + HB_COLS - 1) / HB_COLS;
+        long long blocks = ngroups < 148 * 8 ? ngroups : 148 * 8;
+        size_t smem = ((size_t)6 * HB_COLS * (g.zDim + 4) + 2 * HB_COLS) * sizeof(double);
+        SB_LAUNCH(k_heightresolved_bl2, dim3((unsigned)blocks), dim3(g.zDim, HB_COLS), smem, c.stream, g, p, a, tstep, ngroups);
+        break;
+      }
       int cpb = 128 / g.zDim; if (cpb < 1) cpb = 1;
       long long blocks = (g.hpoints + cpb - 1) / cpb;
       size_t smem = (size_t)cpb * 4 * g.zDim * sizeof(double);

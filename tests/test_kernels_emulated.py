@@ -9,7 +9,7 @@ from helpers import STATE_TOL, TRANSFORM_TOL, check_model, check_transforms, mod
 T_CASES = transform_cases()
 M_CASES = model_cases()
 FAST_MODELS = ["LinearAdvection1D", "LinearShallowWater1D", "LinearAdvectionRL_K0", "LinearAdvectionRZ",
-               "Euler_test_semiimplicit", "LinearAdvectionRLZ"]
+               "Euler_test_semiimplicit", "LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL_z16"]
 
 
 @pytest.mark.parametrize("name", sorted(T_CASES))
