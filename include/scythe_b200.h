@@ -199,6 +199,26 @@ int sb_model_sync(sb_model_t m);
 /* number of kernels this model launched since creation (bench.py's gpu_launches) */
 int64_t sb_model_launch_count(sb_model_t m);
 
+/* ---- Chebyshev column API (Springsteel's Chebyshev module as Scythe calls it) ------------------
+ * Chebyshev1D(ChebyshevParameters(zmin, zmax, zDim, bDim, BCB, BCT)) with CBtransform!, CAtransform!,
+ * CItransform!, CIxtransform, CIxxtransform, CIInttransform(col, C0) -- src/semiimplicit.jl:569-574,593,596,
+ * src/shallowWaterModels.jl:424-429,480-482, src/reference_state.jl:97-108,141-155 -- and
+ * Chebyshev.dct_matrix / dct_1st_derivative / dct_2nd_derivative (src/semiimplicit.jl:772-775).
+ * The column transforms are batched on the device: `in` / `out` are host arrays [len x ncols], column-major
+ * (one column of the reference's col.uMish / col.b / col.a per batch entry).  Lengths: CB zDim -> b_zDim,
+ * CA b_zDim -> zDim (zero filled), CI / CIx / CIxx / CIInt zDim -> zDim. */
+typedef struct sb_cheb_params {
+  double zmin, zmax;
+  int64_t zDim;           /* number of Gauss-Lobatto levels */
+  int64_t b_zDim;         /* retained modes; <= 0 -> min(zDim, (2 zDim - 1)/3 + 1) */
+  int32_t BCB, BCT;       /* SB_ZBC_* */
+} sb_cheb_params;
+enum { SB_CHEB_CB = 0, SB_CHEB_CA = 1, SB_CHEB_CI = 2, SB_CHEB_CIX = 3, SB_CHEB_CIXX = 4, SB_CHEB_CIINT = 5 };
+int sb_cheb_mish_points(const sb_cheb_params* cp, double* z /* [zDim] */);
+/* zDim x zDim matrices, column-major (Julia): values / d/dz / d2/dz2 at the mish points of coefficient k */
+int sb_cheb_matrices(const sb_cheb_params* cp, double* dct, double* dct1, double* dct2);
+int sb_cheb_columns(const sb_cheb_params* cp, int32_t op, const double* in, double* out, int64_t ncols, double C0, int device);
+
 /* ---- multi-GPU: NCCL over NVLink, one process per GPU ------------------------------------- */
 /* ncclGetUniqueId -> 128 bytes to ship to the other ranks (the reference ships RemoteChannels the
  * same way, src/semiimplicit.jl:205-219) */

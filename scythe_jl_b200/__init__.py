@@ -4,7 +4,7 @@ time-step hot path behind the reference's API names.  See DESIGN.md / INTEGRATIO
 Importing the package does not load the CUDA library; the first grid/model creation does, and it
 fails loudly if ``libscythe_b200.so`` has not been built (there is no CPU fallback).
 """
-from .api import (Chebyshev, CubicBSpline, DomainError, Grid, GridParameters, Model, ModelParameters,  # noqa: F401
-                  ReferenceState, ScytheError, UnsupportedError, calcTileSizes, checkCFL, createGrid,
+from .api import (Chebyshev, Chebyshev1D, ChebyshevParameters, CubicBSpline, DomainError, Grid, GridParameters, Model, ModelParameters,  # noqa: F401
+                  ReferenceState, ScytheError, UnsupportedError, calcTileSizes, checkCFL, createGrid, dct_1st_derivative, dct_2nd_derivative, dct_matrix,
                   getGridpoints, gridTransform, integrate_model, num_columns, read_physical_grid,
                   spectralTransform, splineTransform, tileTransform, tile_grid_params, write_grid)

@@ -41,6 +41,11 @@ class sb_model_params(C.Structure):
                 ("ref_sbar", c_f64p), ("ref_xibar", c_f64p), ("ref_mubar", c_f64p), ("Pxi_bar", C.c_double)]
 
 
+class sb_cheb_params(C.Structure):
+    _fields_ = [("zmin", C.c_double), ("zmax", C.c_double), ("zDim", C.c_int64), ("b_zDim", C.c_int64),
+                ("BCB", C.c_int32), ("BCT", C.c_int32)]
+
+
 grid_t = C.c_void_p
 model_t = C.c_void_p
 
@@ -87,6 +92,9 @@ PROTOTYPES = {
     "sb_model_profile_report": (C.c_int, [model_t, C.c_char_p, C.c_int64]),
     "sb_model_sync": (C.c_int, [model_t]),
     "sb_model_launch_count": (C.c_int64, [model_t]),
+    "sb_cheb_mish_points": (C.c_int, [C.POINTER(sb_cheb_params), c_f64p]),
+    "sb_cheb_matrices": (C.c_int, [C.POINTER(sb_cheb_params), c_f64p, c_f64p, c_f64p]),
+    "sb_cheb_columns": (C.c_int, [C.POINTER(sb_cheb_params), C.c_int32, c_f64p, c_f64p, C.c_int64, C.c_double, C.c_int]),
     "sb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sb_model_colsolve_init": (C.c_int, [model_t, C.c_int32, C.c_int32]),
     "sb_model_colsolve_planes": (C.c_int, [model_t, c_i32p, C.c_int32]),

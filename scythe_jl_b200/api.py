@@ -75,6 +75,82 @@ class Chebyshev:
 
 
 @dataclass
+class ChebyshevParameters:
+    """Springsteel ChebyshevParameters(zmin, zmax, zDim, bDim, BCB, BCT) (src/reference_state.jl:97-104)."""
+    zmin: float = 0.0
+    zmax: float = 0.0
+    zDim: int = 0
+    bDim: int = 0
+    BCB: dict = field(default_factory=lambda: dict(Chebyshev.R0))
+    BCT: dict = field(default_factory=lambda: dict(Chebyshev.R0))
+
+
+class Chebyshev1D:
+    """One vertical column object of the reference (col.uMish / col.b / col.a); the transforms are functional and
+    batched over axis 1, and run on the device (sb_cheb_columns).  CBtransform!, CAtransform!, CItransform!,
+    CIxtransform, CIxxtransform, CIInttransform: src/semiimplicit.jl:569-574,593,596."""
+
+    def __init__(self, cp: ChebyshevParameters, lib=None, device: int = 0):
+        self.lib = lib or _lib.load()
+        self.device = device
+        self.params = cp
+        bdim = cp.bDim if cp.bDim > 0 else min(cp.zDim, (2 * cp.zDim - 1) // 3 + 1)
+        self.bDim = bdim
+        self._c = _lib.sb_cheb_params(zmin=cp.zmin, zmax=cp.zmax, zDim=cp.zDim, b_zDim=bdim, BCB=Chebyshev.code(cp.BCB),
+                                      BCT=Chebyshev.code(cp.BCT))
+        self.mishPoints = np.empty(cp.zDim)
+        self.lib.check(self.lib.sb_cheb_mish_points(C.byref(self._c), _ptr(self.mishPoints)))
+        self.uMish, self.b, self.a = np.zeros(cp.zDim), np.zeros(bdim), np.zeros(cp.zDim)
+
+    def _op(self, op: int, x: np.ndarray, n_in: int, n_out: int, C0: float = 0.0) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float64)
+        one = x.ndim == 1
+        xin = np.asfortranarray(x.reshape(n_in, -1))
+        out = np.empty((n_out, xin.shape[1]), order="F")
+        self.lib.check(self.lib.sb_cheb_columns(C.byref(self._c), op, _ptr(xin), _ptr(out), xin.shape[1], float(C0), self.device))
+        return out[:, 0].copy() if one else out
+
+    def CBtransform(self, u):
+        return self._op(0, u, self.params.zDim, self.bDim)
+
+    def CAtransform(self, b):
+        return self._op(1, b, self.bDim, self.params.zDim)
+
+    def CItransform(self, a):
+        return self._op(2, a, self.params.zDim, self.params.zDim)
+
+    def CIxtransform(self, a):
+        return self._op(3, a, self.params.zDim, self.params.zDim)
+
+    def CIxxtransform(self, a):
+        return self._op(4, a, self.params.zDim, self.params.zDim)
+
+    def CIInttransform(self, a, C0: float = 0.0):
+        return self._op(5, a, self.params.zDim, self.params.zDim, C0)
+
+
+def _cheb_matrix(which: int, nz: int, length: float, lib=None) -> np.ndarray:
+    lib = lib or _lib.load()
+    cp = _lib.sb_cheb_params(zmin=0.0, zmax=float(length), zDim=nz, b_zDim=nz, BCB=0, BCT=0)
+    mats = [np.empty((nz, nz), order="F") for _ in range(3)]
+    lib.check(lib.sb_cheb_matrices(C.byref(cp), *(_ptr(m) for m in mats)))
+    return mats[which]
+
+
+def dct_matrix(nz: int, lib=None) -> np.ndarray:
+    """Chebyshev.dct_matrix(nz) (src/semiimplicit.jl:772): coefficients -> values at the mish points, row 1 = bottom."""
+    return _cheb_matrix(0, nz, 1.0, lib)
+
+
+def dct_1st_derivative(nz: int, length: float, lib=None) -> np.ndarray:
+    return _cheb_matrix(1, nz, length, lib)
+
+
+def dct_2nd_derivative(nz: int, length: float, lib=None) -> np.ndarray:
+    return _cheb_matrix(2, nz, length, lib)
+
+
+@dataclass
 class GridParameters:
     """src/spectralGrid.jl:20-45; derived fields are properties."""
     geometry: str = "R"

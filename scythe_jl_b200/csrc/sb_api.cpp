@@ -1112,6 +1112,59 @@ static void model_exchange(sb_model* M) {
   ++M->extra_launches;
 }
 
+
+// ====================================================================================== Chebyshev column API
+static ChebTables cheb_tables_of(const sb_cheb_params* cp, int* bz_out) {
+  if (!cp) throw std::invalid_argument("NULL Chebyshev parameters");
+  if (cp->zDim < 4 || !(cp->zmax > cp->zmin)) throw std::invalid_argument("zDim >= 4 and zmax > zmin required");
+  if (cp->BCB < 0 || cp->BCB > 3 || cp->BCT < 0 || cp->BCT > 3) throw std::invalid_argument("bad Chebyshev BC code");
+  const long long def = std::min<long long>(cp->zDim, (2 * cp->zDim - 1) / 3 + 1);
+  const int bz = (int)(cp->b_zDim > 0 ? cp->b_zDim : def);
+  if (bz > cp->zDim) throw std::invalid_argument("b_zDim > zDim");
+  *bz_out = bz;
+  return make_cheb_tables((int)cp->zDim, bz, cp->zmin, cp->zmax);
+}
+
+static void cheb_columns(const sb_cheb_params* cp, int op, const double* in, double* out, long long ncols, double C0, int device) {
+  if (!in || !out || ncols < 0) throw std::invalid_argument("bad argument");
+  require_device();
+  int bz = 0;
+  const ChebTables t = cheb_tables_of(cp, &bz);
+  const int nz = t.nz;
+  std::vector<double> M;
+  int rows = nz, cols = nz;
+  switch (op) {
+    case SB_CHEB_CB: rows = bz; cols = nz; M = t.fwd; break;
+    case SB_CHEB_CA: {   // a = (I + Gamma) b, zero filled to zDim
+      rows = nz; cols = bz;
+      const std::vector<double> IG = cheb_bc_matrix(t, cp->BCB, cp->BCT);
+      M.assign((size_t)nz * bz, 0.0);
+      std::copy(IG.begin(), IG.end(), M.begin());
+      break;
+    }
+    case SB_CHEB_CI: M = t.T0; break;
+    case SB_CHEB_CIX: M = t.T1; break;
+    case SB_CHEB_CIXX: M = t.T2; break;
+    case SB_CHEB_CIINT: M = t.Tint; break;
+    default: throw std::invalid_argument("unknown Chebyshev column operation");
+  }
+  if (ncols == 0) return;
+  CU(cudaSetDevice(device));
+  double *dM = dev_upload(M), *din = nullptr, *dout = nullptr;
+  CU(cudaMalloc((void**)&din, (size_t)cols * ncols * sizeof(double)));
+  CU(cudaMalloc((void**)&dout, (size_t)rows * ncols * sizeof(double)));
+  try {
+    CU(cudaMemcpy(din, in, (size_t)cols * ncols * sizeof(double), cudaMemcpyHostToDevice));
+    LaunchCtx c{nullptr, nullptr, nullptr};
+    launch_column_op(c, dM, rows, cols, din, dout, ncols, op == SB_CHEB_CIINT ? C0 : 0.0);
+    CU(cudaMemcpy(out, dout, (size_t)rows * ncols * sizeof(double), cudaMemcpyDeviceToHost));
+  } catch (...) {
+    cudaFree(dM); cudaFree(din); cudaFree(dout);
+    throw;
+  }
+  cudaFree(dM); cudaFree(din); cudaFree(dout);
+}
+
 // ====================================================================================== C ABI
 extern "C" {
 
@@ -1415,6 +1468,31 @@ int sb_model_colsolve_solve(sb_model_t m) {
 }
 int sb_model_colsolve_publish(sb_model_t m) {
   return guarded([&] { if (!m || !m->cs.on) throw std::invalid_argument("bad argument"); colsolve_publish(m); });
+}
+
+int sb_cheb_mish_points(const sb_cheb_params* cp, double* z) {
+  return guarded([&] {
+    if (!z) throw std::invalid_argument("NULL argument");
+    int bz;
+    const ChebTables t = cheb_tables_of(cp, &bz);
+    std::copy(t.z.begin(), t.z.end(), z);
+  });
+}
+int sb_cheb_matrices(const sb_cheb_params* cp, double* dct, double* dct1, double* dct2) {
+  return guarded([&] {
+    int bz;
+    const ChebTables t = cheb_tables_of(cp, &bz);
+    const int nz = t.nz;
+    double* dst[3] = {dct, dct1, dct2};
+    const std::vector<double>* src[3] = {&t.T0, &t.T1, &t.T2};
+    for (int m = 0; m < 3; ++m)
+      if (dst[m])
+        for (int j = 0; j < nz; ++j)
+          for (int k = 0; k < nz; ++k) dst[m][(size_t)k * nz + j] = (*src[m])[(size_t)j * nz + k];   // column-major
+  });
+}
+int sb_cheb_columns(const sb_cheb_params* cp, int32_t op, const double* in, double* out, int64_t ncols, double C0, int device) {
+  return guarded([&] { cheb_columns(cp, op, in, out, ncols, C0, device); });
 }
 
 int sb_comm_unique_id(void* out128) {

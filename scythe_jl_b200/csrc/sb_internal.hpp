@@ -187,6 +187,8 @@ void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFa
 void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* tileB,
                      const DevGrid* prev, const double* prevB, int last, double* shared);
 void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA);
+void launch_column_op(const LaunchCtx& c, const double* M /*[rows][cols]*/, int rows, int cols, const double* in, double* out,
+                      long long ncols, double C0);
 void launch_copy(const LaunchCtx& c, double* dst, const double* src, long long n);
 void launch_nan_scan(const LaunchCtx& c, const double* phys, long long N, int V, long long* result);
 

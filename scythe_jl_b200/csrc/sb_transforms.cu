@@ -1155,6 +1155,33 @@ void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& til
   count(c);
 }
 
+// batched column operator (Chebyshev column API): out[r][c] = sum_k M[r][k] in[k][c] + C0, column-major batches
+__global__ void k_column_op(const double* __restrict__ M, int rows, int cols, const double* __restrict__ in,
+                            double* __restrict__ out, long long ncols, double C0) {
+  SB_DYN_SMEM(double, x);                // [columns of this block][cols]
+  const int r = threadIdx.x, cl = threadIdx.y;
+  const long long c = (long long)blockIdx.x * blockDim.y + cl;
+  for (int k = r; k < cols; k += blockDim.x)
+    x[cl * cols + k] = c < ncols ? in[c * cols + k] : 0.0;
+  __syncthreads();
+  if (c >= ncols) return;
+  for (int rr = r; rr < rows; rr += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < cols; ++k) s = fma(M[(size_t)rr * cols + k], x[cl * cols + k], s);
+    out[c * rows + rr] = s + C0;
+  }
+}
+
+void launch_column_op(const LaunchCtx& c, const double* M, int rows, int cols, const double* in, double* out,
+                      long long ncols, double C0) {
+  ProfScope prof_scope_(c, "column_op");
+  const int tx = 32, ty = 8;
+  SB_LAUNCH(k_column_op, dim3((unsigned)((ncols + ty - 1) / ty)), dim3(tx, ty), (size_t)ty * cols * sizeof(double), c.stream,
+            M, rows, cols, in, out, ncols, C0);
+  SB_CHECK_LAUNCH();
+  count(c);
+}
+
 __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];

@@ -253,6 +253,13 @@ def test_notebook_run_through_integrate_model_and_csv(gpu_lib, tmp_path):
     assert rel_err(uf, run.output_patch()[:, 0, 0]) <= STATE_TOL
 
 
+@pytest.mark.parametrize("bcb,bct", [("R0", "R0"), ("R1T0", "R1T1"), ("R1T2", "R1T0")])
+def test_chebyshev_column_api(bcb, bct, gpu_lib):
+    from oracle import chebyshev as och
+    from test_kernels_emulated import check_chebyshev_column_api
+    check_chebyshev_column_api(S, och, gpu_lib, bcb, bct, nz=64, ncol=1000)
+
+
 def test_linearity_rlz(gpu_lib):
     gp = S.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=30, zmin=0, zmax=1e4, zDim=64, vars={"a": 1, "b": 2, "c": 3})
     g = S.createGrid(gp, lib=gpu_lib)

@@ -83,3 +83,39 @@ def test_integrate_model_driver_and_csv_files(emu_lib, tmp_path):
     assert rel_err(final[:, 0, 0], run_oracle(case, 3).output_patch()[:, 0, 0]) <= STATE_TOL
     with pytest.raises(S.ScytheError):
         S.integrate_model(mp, num_tiles=0, lib=emu_lib)      # "Need to add at least 1 worker process" (src/Scythe.jl:39-41)
+
+
+@pytest.mark.parametrize("bcb,bct", [("R0", "R0"), ("R1T0", "R1T1"), ("R1T2", "R1T0"), ("R1T1", "R0")])
+def test_chebyshev_column_api_matches_oracle(bcb, bct, emu_lib):
+    """Chebyshev1D column transforms (CB, CA, CI, CIx, CIxx, CIInt) and the dct_* matrices the semi-implicit
+    Helmholtz operator is built from (src/semiimplicit.jl:569-574, 768-781), batched over 37 columns."""
+    import numpy as np
+    import scythe_jl_b200 as S
+    from oracle import chebyshev as och
+    check_chebyshev_column_api(S, och, emu_lib, bcb, bct)
+
+
+def check_chebyshev_column_api(S, och, lib, bcb, bct, nz=24, ncol=37):
+    import numpy as np
+    ocp = och.ChebyshevParameters(0.5, 7.5, nz, 0, getattr(och, bcb), getattr(och, bct))
+    oc = och.Chebyshev1D(ocp)
+    c = S.Chebyshev1D(S.ChebyshevParameters(zmin=0.5, zmax=7.5, zDim=nz, bDim=0, BCB=getattr(S.Chebyshev, bcb),
+                                            BCT=getattr(S.Chebyshev, bct)), lib=lib)
+    assert np.abs(c.mishPoints - oc.mishPoints).max() <= 1e-14 * 7.5
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal((nz, ncol))
+    b, ob = c.CBtransform(u), oc.CBtransform(u)
+    assert b.shape == ob.shape and np.abs(b - ob).max() <= 1e-14
+    a, oa = c.CAtransform(ob), oc.CAtransform(ob)
+    assert a.shape == oa.shape == (nz, ncol) and np.abs(a - oa).max() <= 1e-13
+    for name, tol in (("CItransform", 1e-13), ("CIxtransform", 1e-11), ("CIxxtransform", 1e-9)):
+        got, want = getattr(c, name)(oa), getattr(oc, name)(oa)
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), name
+    got, want = c.CIInttransform(oa, 2.5), oc.CIInttransform(oa, 2.5)
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    assert np.abs(c.CBtransform(u[:, 0]) - ob[:, 0]).max() <= 1e-14          # single column
+    L = 7.0
+    assert np.abs(S.dct_matrix(nz, lib=lib) - och.dct_matrix(nz)).max() <= 1e-13
+    d1, o1 = S.dct_1st_derivative(nz, L, lib=lib), och.dct_1st_derivative(nz, L)
+    d2, o2 = S.dct_2nd_derivative(nz, L, lib=lib), och.dct_2nd_derivative(nz, L)
+    assert np.abs(d1 - o1).max() <= 1e-12 * np.abs(o1).max() and np.abs(d2 - o2).max() <= 1e-12 * np.abs(o2).max()
