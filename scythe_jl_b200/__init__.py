@@ -5,6 +5,6 @@ Importing the package does not load the CUDA library; the first grid/model creat
 fails loudly if ``libscythe_b200.so`` has not been built (there is no CPU fallback).
 """
 from .api import (Chebyshev, Chebyshev1D, ChebyshevParameters, CubicBSpline, DomainError, Grid, GridParameters, Model, ModelParameters,  # noqa: F401
-                  ReferenceState, ScytheError, UnsupportedError, calcTileSizes, checkCFL, createGrid, dct_1st_derivative, dct_2nd_derivative, dct_matrix,
+                  ReferenceState, ScytheError, UnsupportedError, allocateSplineBuffer, calcHaloMap, calcPatchMap, calcTileSizes, checkCFL, createGrid, dct_1st_derivative, dct_2nd_derivative, dct_matrix,
                   getGridpoints, gridTransform, integrate_model, num_columns, read_physical_grid,
                   spectralTransform, splineTransform, tileTransform, tile_grid_params, write_grid)

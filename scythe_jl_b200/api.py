@@ -370,6 +370,41 @@ def calcTileSizes(patch, num_tiles: int, lib=None) -> np.ndarray:
     return out
 
 
+def _block_rows(grid: Grid, ncolp: int, m0: int, m1: int, shift: int = 0) -> np.ndarray:
+    bz = max(grid.b_zDim, 1)
+    gcol = 1 + 2 * grid.kDim
+    zb = np.arange(bz)[:, None, None]
+    p = np.arange(ncolp)[None, :, None]
+    m = np.arange(m0, m1)[None, None, :]
+    return ((zb * gcol + p) * grid.b_rDim + m + shift).reshape(-1)
+
+
+def calcPatchMap(patch: Grid, tile: Grid):
+    """src/semiimplicit.jl:79-81: (BitMatrix over patch.spectral, view into tile.spectral) of the tile's OWNED block
+    (all but its last 3 coefficients of every spline column).  Returned as a boolean [S_patch, V] mask and the
+    matching row indices of tile.spectral (``tile.spectral[rows]`` is the reference's tileView).  The device path
+    never builds these maps (k_assemble / k_extract apply them on the fly); they are here for host code."""
+    off = tile.params.spectralIndexL - patch.params.spectralIndexL
+    tcol = 1 + 2 * tile.kDim
+    mask = np.zeros((patch.S, patch.V), dtype=bool, order="F")
+    mask[_block_rows(patch, tcol, 0, tile.b_rDim - 3, off), :] = True
+    return mask, _block_rows(tile, tcol, 0, tile.b_rDim - 3)
+
+
+def calcHaloMap(patch: Grid, tile: Grid):
+    """src/semiimplicit.jl:84-86: the tile's last 3 coefficients of every spline column = the next tile's first 3."""
+    off = tile.params.spectralIndexL - patch.params.spectralIndexL
+    tcol = 1 + 2 * tile.kDim
+    mask = np.zeros((patch.S, patch.V), dtype=bool, order="F")
+    mask[_block_rows(patch, tcol, tile.b_rDim - 3, tile.b_rDim, off), :] = True
+    return mask, _block_rows(tile, tcol, tile.b_rDim - 3, tile.b_rDim)
+
+
+def allocateSplineBuffer(patch: Grid, tile: Grid):
+    """src/semiimplicit.jl:90: scratch of tileTransform!.  The device keeps its own scratch; nothing to allocate."""
+    return None
+
+
 def tile_grid_params(gp: GridParameters, tile_params: np.ndarray, t: int) -> GridParameters:
     """GridParameters of tile t (0-based), as at src/semiimplicit.jl:155-169."""
     names = gp.var_names()

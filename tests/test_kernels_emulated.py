@@ -119,3 +119,46 @@ def check_chebyshev_column_api(S, och, lib, bcb, bct, nz=24, ncol=37):
     d1, o1 = S.dct_1st_derivative(nz, L, lib=lib), och.dct_1st_derivative(nz, L)
     d2, o2 = S.dct_2nd_derivative(nz, L, lib=lib), och.dct_2nd_derivative(nz, L)
     assert np.abs(d1 - o1).max() <= 1e-12 * np.abs(o1).max() and np.abs(d2 - o2).max() <= 1e-12 * np.abs(o2).max()
+
+
+@pytest.mark.parametrize("name", ["RL", "RLZ", "RZ"])
+def test_patch_and_halo_maps_match_oracle_and_overlap_add(name, emu_lib):
+    """calcPatchMap / calcHaloMap (src/semiimplicit.jl:79-86) as host index maps: the reference's host-side overlap-add  shared[patchMap] = tileView; shared[haloMap(prev)] += haloView  (:323-329)
+    of the tiles' B reproduces the patch's B."""
+    import numpy as np
+    import scythe_jl_b200 as S
+    from helpers import to_pkg
+    from oracle import grids as OG
+    gp = T_CASES[name]
+    gp = OG.GridParameters(**{**gp.__dict__, "num_cells": 9, "xmin": 0.0, "xmax": 9.0})
+    opatch = OG.createGrid(gp)
+    patch = S.createGrid(to_pkg(gp), lib=emu_lib)
+    tp = S.calcTileSizes(patch.params, 3, lib=emu_lib)
+    otp = OG.calcTileSizes(opatch, 3)
+    assert np.array_equal(tp, otp)
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal((patch.N, patch.V))
+    patch.physical[:, :, 0] = u
+    S.spectralTransform(patch)
+    shared = np.zeros_like(patch.spectral)
+    pts = np.concatenate([[0], np.cumsum(tp[4]).astype(np.int64)])
+    prev = None
+    for t in range(3):
+        tile = S.createGrid(S.tile_grid_params(patch.params, tp, t), lib=emu_lib)
+        tile.physical[:, :, 0] = u[pts[t]:pts[t + 1]]
+        S.spectralTransform(tile)
+        pmask, trows = S.calcPatchMap(patch, tile)
+        hmask, hrows = S.calcHaloMap(patch, tile)
+        assert pmask.sum() == trows.size * patch.V and hmask.sum() == hrows.size * patch.V
+        for v in range(patch.V):
+            shared[np.flatnonzero(pmask[:, v]), v] = tile.spectral[trows, v]
+            if prev is not None:
+                shared[np.flatnonzero(prev[0][:, v]), v] += prev[1][:, v]
+        if t == 2:   # the last tile's halo goes to the master (src/semiimplicit.jl:279-282)
+            for v in range(patch.V):
+                shared[np.flatnonzero(hmask[:, v]), v] += tile.spectral[hrows, v]
+        prev = (hmask, tile.spectral[hrows].copy())
+        tile.close()
+    assert np.abs(shared - patch.spectral).max() <= 1e-13 * np.abs(patch.spectral).max()
+    assert S.allocateSplineBuffer(patch, patch) is None
+    patch.close()
