@@ -61,9 +61,21 @@ __device__ __forceinline__ void pair_sync(int pair) {
   else __syncwarp();
 }
 
+// w[k] = w1^k, k = 1..15, by a depth-4 product tree: trades the 15 shared-memory twiddle loads of the second
+// strided pass for 14 complex multiplies.  Measured on B200 (C4): inverse kernel -2.5 %, forward kernel +1 %
+// (shared-memory wavefronts, not FP64 issue, are the tighter resource of the inverse kernel), so only the inverse
+// kernel enables it (TW1C); doing the same for the first pass loses (19.4 vs 18.8 ms).
+__device__ __forceinline__ void twiddle_powers(double2 w1, double2 (&w)[16]) {
+  w[1] = w1;
+  w[2] = cm(w1, w1); w[3] = cm(w[2], w1);
+  w[4] = cm(w[2], w[2]); w[5] = cm(w[4], w1); w[6] = cm(w[4], w[2]); w[7] = cm(w[4], w[3]);
+  w[8] = cm(w[4], w[4]); w[9] = cm(w[8], w1); w[10] = cm(w[8], w[2]); w[11] = cm(w[8], w[3]);
+  w[12] = cm(w[8], w[4]); w[13] = cm(w[8], w[5]); w[14] = cm(w[8], w[6]); w[15] = cm(w[8], w[7]);
+}
+
 // circular convolution with the pre-transformed chirp.  In: v[n1] = element n1*T + tl, n1 < 8 (upper half zero).
 // Out: v[n1] = element n1*T + tl of the result for n1 < 8 (the upper half is not produced).
-template <int LOG2L, bool PRUNE = true>
+template <int LOG2L, bool PRUNE = true, bool TW1C = false>
 __device__ __forceinline__ void conv2(double2 (&v)[16], double2* buf, const double2* __restrict__ tw0,
                                       const double2* __restrict__ twr, const double2* __restrict__ FHt, int tl, int team,
                                       bool active) {
@@ -88,8 +100,15 @@ __device__ __forceinline__ void conv2(double2 (&v)[16], double2* buf, const doub
     if (active) {
       if (p == 0 && PRUNE) fft16_fwd_lo8(v); else fft16<false>(v);
       const double2* tw = (p == 0 ? tw0 : twr + (p == 1 ? 0 : 15 * (L >> 8))) + j;
+      if (TW1C && p == 1) {
+        double2 w[16];
+        twiddle_powers(tw[0], w);
 #pragma unroll
-      for (int k = 1; k < 16; ++k) v[k] = cm(v[k], tw[(k - 1) * Ms]);
+        for (int k = 1; k < 16; ++k) v[k] = cm(v[k], w[k]);
+      } else {
+#pragma unroll
+        for (int k = 1; k < 16; ++k) v[k] = cm(v[k], tw[(k - 1) * Ms]);
+      }
 #pragma unroll
       for (int k = 0; k < 16; ++k) buf[base + k * Ms + ((k * Ms) >> 4)] = v[k];
     }
@@ -114,11 +133,21 @@ __device__ __forceinline__ void conv2(double2 (&v)[16], double2* buf, const doub
     team_sync<T>(team);
     if (active) {
       const double2* tw = (p == 0 ? tw0 : twr + (p == 1 ? 0 : 15 * (L >> 8))) + j;
+      if (TW1C && p == 1) {
+        double2 w[16];
+        twiddle_powers(tw[0], w);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {       // butterfly order, data and twiddle fetched together
-        const int k = (i >> 2) + 4 * (i & 3);
-        const double2 x = buf[base + k * Ms + ((k * Ms) >> 4)];
-        v[k] = k ? cmc(x, tw[(k - 1) * Ms]) : x;
+        for (int k = 0; k < 16; ++k) {
+          const double2 x = buf[base + k * Ms + ((k * Ms) >> 4)];
+          v[k] = k ? cmc(x, w[k]) : x;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {       // butterfly order, data and twiddle fetched together
+          const int k = (i >> 2) + 4 * (i & 3);
+          const double2 x = buf[base + k * Ms + ((k * Ms) >> 4)];
+          v[k] = k ? cmc(x, tw[(k - 1) * Ms]) : x;
+        }
       }
       fft16<true>(v);
       if (p > 0) {
@@ -238,7 +267,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
           }
         }
       }
-      conv2<LOG2L>(v, buf, tw0, twr, FHt, tl, team, active);
+      conv2<LOG2L, true, true>(v, buf, tw0, twr, FHt, tl, team, active);
       if (active) {
         double* orow;
         if (out_is_phys)
