@@ -343,7 +343,7 @@ def run_ours(args):
     top = max(detail, key=lambda k: detail[k]["ms_per_step"])
     # measured DRAM traffic / FP64-pipe activity of the same step from the committed ncu pass (profiles/), if present
     traffic, ncu_note = None, None
-    prof_file = ROOT / "profiles" / "r1g_step_kernels.json"
+    prof_file = ROOT / "profiles" / "r1j_step_kernels.json"
     if prof_file.exists() and world == 1 and cells_tile == C4_CELLS and not tcbl:
         pk = json.loads(prof_file.read_text())["one_step"]
         sel = {"K3": ("k_inv_r", "k_inv_l", "k_inv_z"), "K1": ("k_fwd_z", "k_fwd_l", "k_fwd_r"), "K2": ("k_spline",),
@@ -351,7 +351,7 @@ def run_ours(args):
         rows = [v for k, v in pk.items() if any(s_ in k for s_ in sel)]
         traffic = 1e9 * sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows)
         fft = [v for k, v in pk.items() if "k_inv_l2" in k]
-        ncu_note = {"file": "profiles/r1g_step_kernels.json",
+        ncu_note = {"file": "profiles/r1j_step_kernels.json",
                     "k_inv_l2_fp64_pipe_pct": sum(r["fp64_pipe_pct"] * r["ms"] for r in fft) / max(sum(r["ms"] for r in fft), 1e-9),
                     "k_inv_l2_share_of_step_under_ncu": sum(r["share"] for r in fft),
                     "note": "the ring FFT inside K3 is FP64-pipe bound (Bluestein), not HBM bound; measured FP64 peak "
