@@ -238,6 +238,17 @@ int sb_model_colsolve_planes(sb_model_t m, int32_t* z0 /* [nranks+1] */, int32_t
 int sb_model_colsolve_buffer(sb_model_t m, int32_t what, int32_t tile, int32_t v, int32_t peer, void** ptr, int64_t* count);
 int sb_model_colsolve_solve(sb_model_t m);
 int sb_model_colsolve_publish(sb_model_t m);
+/* Peer-memory form of the same exchange (one process per GPU on one NVSwitch box): instead of messages, the
+ * forward radial kernel stores every B coefficient straight into the receive buffer of the rank that owns its
+ * z-mode plane, and the owner's cut-out kernel stores every tile's slice of A straight into that tile's A -- plain
+ * pointers into the other GPU's memory, mapped with CUDA IPC, so the transfer overlaps the kernels tile by tile over
+ * NVLink.  Each rank exports handles (what = 0: its receive buffer; 1: spectral A of local tile `tile`), ships them
+ * to the others (the reference ships RemoteChannels the same way, src/semiimplicit.jl:205-219), opens the others'
+ * (index = peer rank for what 0, global tile index for what 1) and calls sb_model_p2p_enable.  A step then needs
+ * only two stream-ordered rendezvous (sb_model_exchange with the library's communicator, or the caller's own). */
+int sb_model_ipc_handle(sb_model_t m, int32_t what, int32_t tile, void* out64);
+int sb_model_ipc_open(sb_model_t m, int32_t what, int32_t index, const void* handle64);
+int sb_model_p2p_enable(sb_model_t m);
 int sb_model_comm_init(sb_model_t m, const void* id128, int32_t rank, int32_t nranks);
 
 /* ---- timing on the handle's stream (CUDA events) ------------------------------------------ */

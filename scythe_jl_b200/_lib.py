@@ -102,6 +102,9 @@ PROTOTYPES = {
                                            C.POINTER(C.c_int64)]),
     "sb_model_colsolve_solve": (C.c_int, [model_t]),
     "sb_model_colsolve_publish": (C.c_int, [model_t]),
+    "sb_model_ipc_handle": (C.c_int, [model_t, C.c_int32, C.c_int32, C.c_void_p]),
+    "sb_model_ipc_open": (C.c_int, [model_t, C.c_int32, C.c_int32, C.c_void_p]),
+    "sb_model_p2p_enable": (C.c_int, [model_t]),
     "sb_model_comm_init": (C.c_int, [model_t, C.c_void_p, C.c_int32, C.c_int32]),
     "sb_timer_start": (C.c_int, [grid_t]),
     "sb_timer_stop": (C.c_int, [grid_t, C.POINTER(C.c_float)]),

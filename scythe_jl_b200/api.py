@@ -516,11 +516,16 @@ class Model:
         self.exchange = exchange or os.environ.get("SB_EXCHANGE", "columns" if (self.dist is not None and self.world > 1) else "torch")
         self._shared_tensor = None
         self._views = {}
-        self.columns = self.exchange in ("columns", "columns-native")
+        #           "columns-p2p" / "columns-p2p-native" = same solve, but no messages: the kernels store into the other
+        #           GPUs' buffers through CUDA-IPC peer mappings (NVLink); only two rendezvous per step remain
+        self.columns = self.exchange in ("columns", "columns-native", "columns-p2p", "columns-p2p-native")
+        self.p2p = self.exchange in ("columns-p2p", "columns-p2p-native")
         if self.columns:
             self.lib.check(self.lib.sb_model_colsolve_init(self.handle, self.rank, self.world))
-        if self.dist is not None and self.world > 1 and self.exchange in ("native", "columns-native"):
+        if self.dist is not None and self.world > 1 and self.exchange in ("native", "columns-native", "columns-p2p-native"):
             self._init_native_comm()
+        if self.p2p:
+            self._init_p2p()
 
     # -- multi-process plumbing -------------------------------------------------------
     def _init_native_comm(self):
@@ -535,6 +540,36 @@ class Model:
         self.dist.broadcast(t, 0)
         uid = (C.c_ubyte * 128)(*t.cpu().tolist())
         self.lib.check(self.lib.sb_model_comm_init(self.handle, uid, self.rank, self.world))
+
+    def _init_p2p(self):
+        """exchange CUDA IPC handles of the receive buffers / tile A arrays and map the peers' memory"""
+        lib = self.lib
+        if self.dist is not None and self.world > 1:
+            def handle(what, tile):
+                h = (C.c_ubyte * 64)()
+                lib.check(lib.sb_model_ipc_handle(self.handle, what, tile, h))
+                return bytes(h)
+            mine = (self.rank, handle(0, 0), {t: handle(1, t) for t in range(self.tile_first, self.tile_first + self.tile_count)})
+            everyone = [None] * self.world
+            self.dist.all_gather_object(everyone, mine)
+            for r, hrecv, tiles in everyone:
+                if r == self.rank:
+                    continue
+                lib.check(lib.sb_model_ipc_open(self.handle, 0, r, (C.c_ubyte * 64).from_buffer_copy(hrecv)))
+                for t, h in tiles.items():
+                    lib.check(lib.sb_model_ipc_open(self.handle, 1, t, (C.c_ubyte * 64).from_buffer_copy(h)))
+        lib.check(lib.sb_model_p2p_enable(self.handle))
+        self._bar = None
+
+    def _barrier(self):
+        """stream-ordered rendezvous (a one-element all-reduce on the compute stream)"""
+        if self.dist is None or self.world == 1:
+            return
+        if self._bar is None:
+            import torch
+            dev = f"cuda:{torch.cuda.current_device()}" if self.dist.get_backend() == "nccl" else "cpu"
+            self._bar = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.dist.all_reduce(self._bar)
 
     def _as_tensor(self, ptr: int, n: int):
         """zero-copy torch view of a library buffer (device memory; host memory in the CPU emulation build)"""
@@ -614,7 +649,7 @@ class Model:
         if self.dist is None or self.world == 1:
             self.lib.check(self.lib.sb_model_step(self.handle, self.t))
             return
-        if self.exchange == "columns-native":
+        if self.exchange in ("columns-native", "columns-p2p-native"):
             self.lib.check(self.lib.sb_model_step(self.handle, self.t))
             return
         self.lib.check(self.lib.sb_model_advance_tiles(self.handle, self.t))
@@ -698,8 +733,12 @@ class Model:
     def _exchange(self):
         if self.dist is None or self.world == 1:
             return
-        if self.exchange in ("native", "columns-native"):
+        if self.exchange in ("native", "columns-native", "columns-p2p-native"):
             self.lib.check(self.lib.sb_model_exchange(self.handle))
+        elif self.p2p:
+            self._barrier()
+            self.lib.check(self.lib.sb_model_colsolve_solve(self.handle))
+            self._barrier()
         elif self.columns:
             self._p2p(0)
             self.lib.check(self.lib.sb_model_colsolve_solve(self.handle))
@@ -710,7 +749,7 @@ class Model:
     def cycle(self):
         """One model_loop iteration entered at calcTendency (see sb_model_cycle)."""
         self.t += 1
-        if self.dist is None or self.world == 1 or self.exchange in ("native", "columns-native"):
+        if self.dist is None or self.world == 1 or self.exchange in ("native", "columns-native", "columns-p2p-native"):
             self.lib.check(self.lib.sb_model_cycle(self.handle, self.t))
             return
         self.lib.check(self.lib.sb_model_tendency(self.handle))

@@ -92,6 +92,7 @@ struct sb_grid {
   std::vector<std::vector<LWork>> fwork2, iwork2;     // v2 persistent ring-FFT items (bigger row ranges)
   std::vector<const LWork*> d_fwork2, d_iwork2;
   double* d_fft3_scratch = nullptr;                    // parking area of the composite-length forward FFT
+  const PeerScatter* scatter = nullptr;                // multi-GPU: fwd_r also stores into the plane owners' buffers
   std::vector<const double*> d_tw, d_twp;
   RingPlan* d_plans = nullptr;
   double* d_blob = nullptr;
@@ -350,7 +351,7 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
   LaunchCtx c = G->ctx();
   if (!d.has_l && !d.has_z) {
     if (mirror && mirror != in) launch_copy(c, mirror, in, d.N * d.V);
-    launch_fwd_r(c, d, d.V, in, d.N, G->spectralB, d.S);
+    launch_fwd_r(c, d, d.V, in, d.N, G->spectralB, d.S, G->scatter, 0);
     return;
   }
   G->ensure_scratch();
@@ -371,7 +372,7 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
     } else {
       grid_fwd_z(G, nv, inv, mir, SL, slN);
     }
-    launch_fwd_r(c, d, nv, SL, slN, G->spectralB + (long long)v0 * d.S, d.S);
+    launch_fwd_r(c, d, nv, SL, slN, G->spectralB + (long long)v0 * d.S, d.S, G->scatter, v0);
   }
 }
 
@@ -638,6 +639,7 @@ struct sb_model {
   double* d_sicols = nullptr;
   std::vector<double> ref_host;  // [3][3][zDim]
   void* comm = nullptr;
+  double* d_barrier = nullptr;
   int rank = 0, nranks = 1;
   long long extra_launches = 0;
   // ---- distributed spline solve by z-mode planes (sb_model_colsolve_*)
@@ -653,6 +655,12 @@ struct sb_model {
     double* slabB = nullptr;                // [V][nz][ncolp_P][M_P]
     double* slabA = nullptr;
     DevGrid slab{};                         // patch descriptor restricted to my planes
+    // peer-memory mode (sb_model_p2p_enable): no messages -- fwd_r / extract store into the other GPUs directly
+    bool p2p = false;
+    std::vector<double*> peer_recvB;        // [nranks] base of rank k's recvB (CUDA IPC mapping; own pointer for k == rank)
+    std::vector<double*> peer_tileA;        // [ntiles] spectralA of tile t on the rank that owns it
+    std::vector<PeerScatter> scat;          // [local tiles]
+    std::vector<void*> ipc_opened;
     int nz() const { return z0[rank + 1] - z0[rank]; }
   } cs;
 };
@@ -845,6 +853,9 @@ static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first
 static void model_free(sb_model* M) {
   if (!M) return;
   if (M->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(M->comm);
+#ifndef SB_EMU
+  for (void* p : M->cs.ipc_opened) cudaIpcCloseMemHandle(p);
+#endif
   for (auto& t : M->tiles) {
     grid_free(t.grid);
     cudaFree(t.var_np1);
@@ -1035,7 +1046,7 @@ static void colsolve_solve(sb_model* M) {
   const DevGrid& p = P->dg;
   const int nz = cs.nz();
   if (nz == 0) return;                  // fewer planes than ranks (grids without a vertical dimension): nothing to own
-  colsolve_local(M, 0);
+  if (!cs.p2p) colsolve_local(M, 0);
   CU(cudaMemsetAsync(cs.slabB, 0, (size_t)cs.slab.S * p.V * sizeof(double), M->stream));
   LaunchCtx c = P->ctx();
   for (int t = 0; t < M->ntiles; ++t) {
@@ -1048,6 +1059,13 @@ static void colsolve_solve(sb_model* M) {
     }
   }
   launch_spline_solve(c, cs.slab, nullptr, P->hfactors, cs.slabB, cs.slabA);
+  if (cs.p2p) {     // every tile's slice straight into that tile's A, wherever it lives
+    for (int t = 0; t < M->ntiles; ++t) {
+      const DevGrid& d = cs.tdg[t];
+      launch_extract(c, cs.slab, plane_view(d, nz), cs.slabA, cs.peer_tileA[t] + (long long)cs.z0[cs.rank] * d.ncolp * d.b_rDim, d.S);
+    }
+    return;
+  }
   for (int t = 0; t < M->ntiles; ++t) launch_extract(c, cs.slab, plane_view(cs.tdg[t], nz), cs.slabA, cs.sendA + cs.recv_off[t]);
   colsolve_local(M, 1);
 }
@@ -1098,7 +1116,23 @@ static void colsolve_p2p(sb_model* M, int dir) {
   ++M->extra_launches;
 }
 
+// stream-ordered rendezvous of all ranks: every rank's kernels enqueued before it (and their stores into peer
+// memory) are complete when it returns on the stream
+static void comm_barrier(sb_model* M) {
+  if (M->nranks <= 1) return;
+  if (!M->comm) throw CommError("library communicator not initialised (sb_model_comm_init)");
+  if (!M->d_barrier) throw CommError("no barrier buffer");
+  NC(g_nccl.AllReduce(M->d_barrier, M->d_barrier, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, M->comm, (void*)M->stream));
+  ++M->extra_launches;
+}
+
 static void model_exchange(sb_model* M) {
+  if (M->cs.on && M->cs.p2p) {
+    comm_barrier(M);        // every tile's fwd_r has stored its B into the owners' buffers
+    colsolve_solve(M);
+    comm_barrier(M);        // every owner's extract has stored A into the tiles
+    return;
+  }
   if (M->cs.on) {
     colsolve_p2p(M, 0);
     colsolve_solve(M);
@@ -1112,6 +1146,83 @@ static void model_exchange(sb_model* M) {
   ++M->extra_launches;
 }
 
+
+
+// ---- peer-memory mode: CUDA IPC handles of the buffers other ranks write into
+static void p2p_handle(sb_model* M, int what, int tile, void* out64) {
+  auto& cs = M->cs;
+  if (!cs.on || !out64) throw std::invalid_argument("bad argument");
+#ifdef SB_EMU
+  (void)what; (void)tile;
+  throw Unsupported("CUDA IPC is not available in the CPU emulation build");
+#else
+  void* ptr = nullptr;
+  if (what == 0) ptr = cs.recvB;
+  else if (what == 1) {
+    if (tile < M->tile_first || tile >= M->tile_first + M->tile_count) throw std::invalid_argument("tile is not local");
+    ptr = M->tiles[tile - M->tile_first].grid->spectralA;
+  } else throw std::invalid_argument("what must be 0 or 1");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  CU(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(out64), ptr));
+#endif
+}
+
+static void p2p_open(sb_model* M, int what, int index, const void* handle64) {
+  auto& cs = M->cs;
+  if (!cs.on || !handle64) throw std::invalid_argument("bad argument");
+#ifdef SB_EMU
+  (void)what; (void)index;
+  throw Unsupported("CUDA IPC is not available in the CPU emulation build");
+#else
+  cs.peer_recvB.resize(cs.nranks, nullptr);
+  cs.peer_tileA.resize(M->ntiles, nullptr);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof(h));
+  void* ptr = nullptr;
+  CU(cudaSetDevice(M->device));
+  CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  cs.ipc_opened.push_back(ptr);
+  if (what == 0) {
+    if (index < 0 || index >= cs.nranks) throw std::invalid_argument("bad peer");
+    cs.peer_recvB[index] = (double*)ptr;
+  } else if (what == 1) {
+    if (index < 0 || index >= M->ntiles) throw std::invalid_argument("bad tile");
+    cs.peer_tileA[index] = (double*)ptr;
+  } else throw std::invalid_argument("what must be 0 or 1");
+#endif
+}
+
+static void p2p_enable(sb_model* M) {
+  auto& cs = M->cs;
+  if (!cs.on) throw std::invalid_argument("sb_model_colsolve_init has not been called");
+  if (cs.nranks > SB_MAX_PEERS) throw Unsupported("peer-memory exchange supports at most 8 ranks");
+  const DevGrid& p = M->patch->dg;
+  cs.peer_recvB.resize(cs.nranks, nullptr);
+  cs.peer_tileA.resize(M->ntiles, nullptr);
+  cs.peer_recvB[cs.rank] = cs.recvB;
+  for (int t = M->tile_first; t < M->tile_first + M->tile_count; ++t) cs.peer_tileA[t] = M->tiles[t - M->tile_first].grid->spectralA;
+  for (int k = 0; k < cs.nranks; ++k)
+    if (!cs.peer_recvB[k]) throw std::invalid_argument("peer buffer of rank " + std::to_string(k) + " has not been opened");
+  for (int t = 0; t < M->ntiles; ++t)
+    if (!cs.peer_tileA[t]) throw std::invalid_argument("spectral A of tile " + std::to_string(t) + " has not been opened");
+  cs.scat.assign(M->tile_count, PeerScatter{});
+  for (int i = 0; i < M->tile_count; ++i) {
+    const int t = M->tile_first + i;
+    const DevGrid& d = cs.tdg[t];
+    PeerScatter& ps = cs.scat[i];
+    ps.nranks = cs.nranks;
+    for (int k = 0; k <= cs.nranks; ++k) ps.z0[k] = cs.z0[k];
+    for (int k = 0; k < cs.nranks; ++k) {
+      const long long nzk = cs.z0[k + 1] - cs.z0[k];
+      long long off = 0;     // owner k's receive slots are laid out tile by tile: [t'][V][nz_k][ncolp_t'][M_t']
+      for (int tt = 0; tt < t; ++tt) off += (long long)p.V * nzk * cs.tdg[tt].ncolp * cs.tdg[tt].b_rDim;
+      ps.base[k] = cs.peer_recvB[k] + off;
+      ps.vstride[k] = nzk * d.ncolp * d.b_rDim;
+    }
+    M->tiles[i].grid->scatter = &ps;
+  }
+  cs.p2p = true;
+}
 
 // ====================================================================================== Chebyshev column API
 static ChebTables cheb_tables_of(const sb_cheb_params* cp, int* bz_out) {
@@ -1470,6 +1581,16 @@ int sb_model_colsolve_publish(sb_model_t m) {
   return guarded([&] { if (!m || !m->cs.on) throw std::invalid_argument("bad argument"); colsolve_publish(m); });
 }
 
+int sb_model_ipc_handle(sb_model_t m, int32_t what, int32_t tile, void* out64) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); p2p_handle(m, what, tile, out64); });
+}
+int sb_model_ipc_open(sb_model_t m, int32_t what, int32_t index, const void* handle64) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); p2p_open(m, what, index, handle64); });
+}
+int sb_model_p2p_enable(sb_model_t m) {
+  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); p2p_enable(m); });
+}
+
 int sb_cheb_mish_points(const sb_cheb_params* cp, double* z) {
   return guarded([&] {
     if (!z) throw std::invalid_argument("NULL argument");
@@ -1511,6 +1632,7 @@ int sb_model_comm_init(sb_model_t m, const void* id128, int32_t rank, int32_t nr
     std::memcpy(&id, id128, sizeof(id));
     cudaSetDevice(m->device);
     NC(g_nccl.CommInitRank(&m->comm, nranks, id, rank));
+    if (!m->d_barrier) { m->d_barrier = dev_zeros(8, m->stream); m->owned.push_back(m->d_barrier); }
     m->rank = rank;
     m->nranks = nranks;
     return SB_OK;

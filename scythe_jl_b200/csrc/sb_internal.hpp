@@ -164,8 +164,18 @@ void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
 void launch_fwd_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
                    const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
                    long long mirror_vs, double* out, long long out_vs);
+// peer scatter of the forward radial transform (multi-GPU, plane-distributed solve): besides the tile's own B,
+// every coefficient is stored straight into the buffer of the rank that owns its z-mode plane -- a plain pointer
+// into that GPU's memory, mapped with CUDA IPC, so the transfer rides NVLink from inside the kernel.
+#define SB_MAX_PEERS 8
+struct PeerScatter {
+  int nranks;
+  int z0[SB_MAX_PEERS + 1];          // plane ranges
+  double* base[SB_MAX_PEERS];        // owner k's receive slot of THIS tile (variable 0, its first plane)
+  long long vstride[SB_MAX_PEERS];   // per-variable stride inside owner k's slot = nz_k * ncolp_t * b_rDim_t
+};
 void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride,
-                  double* B, long long B_vstride);
+                  double* B, long long B_vstride, const PeerScatter* scatter = nullptr, int var0 = 0);
 void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch, int nvars,
                   const double* A, long long A_vstride, double* out, long long out_fstride,
                   long long out_vstride, int out_is_phys, int var0);
@@ -186,7 +196,8 @@ void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFa
                          const std::vector<DevSplineFactor>& hfactors, const double* B, double* A);
 void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* tileB,
                      const DevGrid* prev, const double* prevB, int last, double* shared);
-void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA);
+void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA,
+                    long long dst_vstride = 0);
 void launch_column_op(const LaunchCtx& c, const double* M /*[rows][cols]*/, int rows, int cols, const double* in, double* out,
                       long long ncols, double C0);
 void launch_copy(const LaunchCtx& c, double* dst, const double* src, long long n);

@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(RQ) k_fwd_r(DevGrid g, const double* __restric
 // range) are written without touching the input.
 #define RM 32
 __global__ void __launch_bounds__(RQ) k_fwd_r2(DevGrid g, int nvars, const double* __restrict__ in, long long in_vs,
-                                               double* __restrict__ B, long long B_vs) {
+                                               double* __restrict__ B, long long B_vs, PeerScatter ps, int var0) {
   __shared__ double tile[RQ][RM + 1];
   __shared__ long long s_wo[3 * (RM + 3) + 1];
   const int tid = threadIdx.x;
@@ -753,22 +753,34 @@ __global__ void __launch_bounds__(RQ) k_fwd_r2(DevGrid g, int nvars, const doubl
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
+  // plane owner of this block's z-mode (peer scatter): its slot of this tile, in that GPU's memory
+  double* peer = nullptr;
+  if (ps.nranks > 0) {
+    int k = 0;
+    while (k + 1 < ps.nranks && zb >= ps.z0[k + 1]) ++k;
+    peer = ps.base[k] + (long long)(var0 + v) * ps.vstride[k] + (long long)(zb - ps.z0[k]) * g.ncolp * M;
+  }
   for (int qq = warp; qq < RQ; qq += RQ / 32) {
-    if (q0 + qq < g.ncolp && lane < mcnt)
-      Bv[((long long)zb * g.ncolp + q0 + qq) * M + m0 + lane] = tile[qq][lane];
+    if (q0 + qq < g.ncolp && lane < mcnt) {
+      const double val = tile[qq][lane];
+      Bv[((long long)zb * g.ncolp + q0 + qq) * M + m0 + lane] = val;
+      if (peer) peer[(long long)(q0 + qq) * M + m0 + lane] = val;
+    }
   }
 }
 
 void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double* in, long long in_vstride, double* B,
-                  long long B_vstride) {
+                  long long B_vstride, const PeerScatter* scatter, int var0) {
   ProfScope prof_scope_(c, "fwd_r");
   static const bool v1 = std::getenv("SB_RADIAL_V1") != nullptr;   // A/B switch
-  if (v1) {
+  if (v1 && !scatter) {
     dim3 grid((g.ncolp + RQ - 1) / RQ, g.bz, nvars);
     SB_LAUNCH(k_fwd_r, grid, dim3(RQ), 0, c.stream, g, in, in_vstride, B, B_vstride);
   } else {
+    PeerScatter ps{};
+    if (scatter) ps = *scatter;
     dim3 grid((g.ncolp + RQ - 1) / RQ, (g.b_rDim + RM - 1) / RM, g.bz * nvars);
-    SB_LAUNCH(k_fwd_r2, grid, dim3(RQ), 0, c.stream, g, nvars, in, in_vstride, B, B_vstride);
+    SB_LAUNCH(k_fwd_r2, grid, dim3(RQ), 0, c.stream, g, nvars, in, in_vstride, B, B_vstride, ps, var0);
   }
   SB_CHECK_LAUNCH();
   count(c);
@@ -1135,7 +1147,7 @@ void launch_assemble(const LaunchCtx& c, const DevGrid& patch, const DevGrid& ti
 }
 
 // inverse of k_assemble without the halo: the coefficients tile t evaluates, cut out of the solved patch planes
-__global__ void k_extract(DevGrid p, DevGrid t, const double* __restrict__ A, double* __restrict__ tileA) {
+__global__ void k_extract(DevGrid p, DevGrid t, const double* __restrict__ A, double* __restrict__ tileA, long long dst_vs) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_v = t.S;
   if (idx >= per_v * t.V) return;
@@ -1144,13 +1156,16 @@ __global__ void k_extract(DevGrid p, DevGrid t, const double* __restrict__ A, do
   const int m = (int)(rem % t.b_rDim);
   rem /= t.b_rDim;
   const int pcol = (int)(rem % t.ncolp), zb = (int)(rem / t.ncolp);
-  tileA[idx] = A[(long long)v * p.S + ((long long)zb * p.ncolp + pcol) * p.b_rDim + (t.coefOffset - p.coefOffset) + m];
+  // dst_vs != 0: straight into the tile's own A (possibly another GPU's memory), whose variables are S_tile apart
+  const long long o = dst_vs ? (long long)v * dst_vs + (idx - (long long)v * per_v) : idx;
+  tileA[o] = A[(long long)v * p.S + ((long long)zb * p.ncolp + pcol) * p.b_rDim + (t.coefOffset - p.coefOffset) + m];
 }
 
-void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA) {
+void launch_extract(const LaunchCtx& c, const DevGrid& patch, const DevGrid& tile, const double* A, double* tileA,
+                    long long dst_vstride) {
   ProfScope prof_scope_(c, "extract");
   long long tot = tile.S * tile.V;
-  SB_LAUNCH(k_extract, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, c.stream, patch, tile, A, tileA);
+  SB_LAUNCH(k_extract, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, c.stream, patch, tile, A, tileA, dst_vstride);
   SB_CHECK_LAUNCH();
   count(c);
 }

@@ -1,0 +1,52 @@
+"""Manual multi-GPU check (torchrun, NCCL): every exchange mode must give bit-identical patch coefficients.
+    torchrun --nproc-per-node 2 tests/dist_gpu_check.py
+Not collected by pytest (needs >= 2 GPUs); the same host logic is covered on CPU by test_distributed_gloo.py."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    from helpers import model_cases, pkg_model
+    from oracle import grids as G
+    from scythe_jl_b200 import _lib
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lib = _lib.load()
+    outs = {}
+    for name in ("LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL_z16"):
+        case = dict(model_cases()[name])
+        case["n"] = 3
+        ntiles = world
+        patch = G.createGrid(case["gp"])
+        tp = G.calcTileSizes(patch, ntiles)
+        pts = np.concatenate([[0], np.cumsum(tp[4]).astype(np.int64)])
+        for ex in ("torch", "columns", "columns-native", "columns-p2p", "columns-p2p-native"):
+            m = pkg_model(case, ntiles, lib, distributed=True, exchange=ex, device=local)
+            ics = [case["ic"][pts[t]:pts[t + 1]] for t in range(m.tile_first, m.tile_first + m.tile_count)]
+            m.initialize_tiles(ics)
+            m.run(case["n"])
+            outs[(name, ex)] = m.state(0, "var_np1")
+            m.close()
+            dist.barrier()
+        ref = outs[(name, "torch")]
+        for ex in ("columns", "columns-native", "columns-p2p", "columns-p2p-native"):
+            same = np.array_equal(outs[(name, ex)], ref)
+            err = float(np.abs(outs[(name, ex)] - ref).max() / np.abs(ref).max())
+            print(f"rank {rank} {name} {ex}: identical={same} rel_err={err:.2e}", flush=True)
+            assert err <= 1e-12
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

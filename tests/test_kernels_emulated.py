@@ -35,6 +35,10 @@ def test_plane_distributed_solve_single_process(name, ntiles, emu_lib):
     case["tiles"] = (ntiles,)
     case["n"] = min(case["n"], 3)
     assert check_model(case, emu_lib, exchange="columns") <= STATE_TOL
+    if name == "LinearAdvectionRLZ":
+        # peer-memory form (here every "peer" buffer is this process's own): fwd_r scatters into the owner's slots,
+        # the cut-out kernel writes the tiles' A in place
+        assert check_model(case, emu_lib, exchange="columns-p2p") <= STATE_TOL
 
 
 @pytest.mark.parametrize("name,ntiles,exchange", [("LinearAdvectionRLZ", 2, "torch"), ("Euler_test_semiimplicit", 2, "columns")])
