@@ -513,7 +513,11 @@ class Model:
         # exchange: "columns" = plane-distributed spline solve, messages moved by torch.distributed P2P
         #           "columns-native" = same, messages moved by the library's own NCCL communicator
         #           "torch" / "native" = all-reduce of the whole shared B + replicated solve (the reference's scheme)
-        self.exchange = exchange or os.environ.get("SB_EXCHANGE", "columns" if (self.dist is not None and self.world > 1) else "torch")
+        default = "torch"
+        if self.dist is not None and self.world > 1:
+            default = "columns-p2p" if (self.dist.get_backend() == "nccl" and self.world <= 8) else "columns"
+        self.exchange = exchange or os.environ.get("SB_EXCHANGE", default)
+        self._p2p_is_default = exchange is None and "SB_EXCHANGE" not in os.environ
         self._shared_tensor = None
         self._views = {}
         #           "columns-p2p" / "columns-p2p-native" = same solve, but no messages: the kernels store into the other
@@ -525,7 +529,21 @@ class Model:
         if self.dist is not None and self.world > 1 and self.exchange in ("native", "columns-native", "columns-p2p-native"):
             self._init_native_comm()
         if self.p2p:
-            self._init_p2p()
+            ok = True
+            try:
+                self._init_p2p()
+            except ScytheError:
+                if not self._p2p_is_default:
+                    raise
+                ok = False
+            if self.dist is not None and self.world > 1 and self._p2p_is_default:
+                # the peer mappings are an optimisation of the default: if CUDA IPC is unavailable on ANY rank, every
+                # rank drops to the message form of the same exchange (still NCCL over NVLink, same results)
+                import torch
+                flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{torch.cuda.current_device()}")
+                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+                if flag.item() < 1.0:
+                    self.exchange, self.p2p = "columns", False
 
     # -- multi-process plumbing -------------------------------------------------------
     def _init_native_comm(self):
@@ -544,14 +562,20 @@ class Model:
     def _init_p2p(self):
         """exchange CUDA IPC handles of the receive buffers / tile A arrays and map the peers' memory"""
         lib = self.lib
+        self._bar = None
         if self.dist is not None and self.world > 1:
             def handle(what, tile):
                 h = (C.c_ubyte * 64)()
                 lib.check(lib.sb_model_ipc_handle(self.handle, what, tile, h))
                 return bytes(h)
-            mine = (self.rank, handle(0, 0), {t: handle(1, t) for t in range(self.tile_first, self.tile_first + self.tile_count)})
+            try:
+                mine = (self.rank, handle(0, 0), {t: handle(1, t) for t in range(self.tile_first, self.tile_first + self.tile_count)})
+            except ScytheError:
+                mine = (self.rank, None, {})        # still take part in the gather so that nobody hangs
             everyone = [None] * self.world
             self.dist.all_gather_object(everyone, mine)
+            if any(h is None for _, h, _ in everyone):
+                raise ScytheError(_lib.SB_ECUDA, "CUDA IPC handles are not available on every rank")
             for r, hrecv, tiles in everyone:
                 if r == self.rank:
                     continue
@@ -559,7 +583,6 @@ class Model:
                 for t, h in tiles.items():
                     lib.check(lib.sb_model_ipc_open(self.handle, 1, t, (C.c_ubyte * 64).from_buffer_copy(h)))
         lib.check(lib.sb_model_p2p_enable(self.handle))
-        self._bar = None
 
     def _barrier(self):
         """stream-ordered rendezvous (a one-element all-reduce on the compute stream)"""
