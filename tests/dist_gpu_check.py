@@ -24,7 +24,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = _lib.load()
     outs = {}
-    for name in ("LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL_z16"):
+    for name in ("LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL"):
         case = dict(model_cases()[name])
         case["n"] = 3
         ntiles = world

@@ -176,7 +176,7 @@ def model_cases(small=True):
     ic[:, 2] = vbar
     ic[:, 3] = -0.2 * vbar * np.exp(-z / 500)
     ic[:, 4] = vbar * (1 - np.exp(-(z + 50) / 300))
-    gp16 = G.GridParameters(geometry="RLZ", xmin=0, xmax=2e5, num_cells=6, zmin=0, zmax=2e3, zDim=16,
+    gp16 = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=3, zmin=0, zmax=2e3, zDim=16,
                             vars={n: i + 1 for i, n in enumerate(names)},
                             BCL={"h": spl.R1T1, "u": spl.R1T0, "v": spl.R1T0, "ub": spl.R1T0, "vb": spl.R1T0, "wb": spl.R1T1})
     r16, l16, z16 = G.createGrid(gp16).getGridpoints().T
@@ -190,7 +190,7 @@ def model_cases(small=True):
     # 16 levels: the tensor-core (DMMA) column operators of k_heightresolved_bl2
     cases["Oneway_ShallowWater_HeightResolvedBL_z16"] = dict(
         gp=gp16, eq="Oneway_ShallowWater_HeightResolvedBL",
-        prm=dict(g=9.81, Kh=1500.0, Cd=2.4e-3, Hfree=2000.0, f=5e-5, Um=3.0, Vm=-2.0), ts=2.0, n=1, ic=ic16, tiles=(1, 2))
+        prm=dict(g=9.81, Kh=1500.0, Cd=2.4e-3, Hfree=2000.0, f=5e-5, Um=3.0, Vm=-2.0), ts=2.0, n=2, ic=ic16, tiles=(1,))
     cases["Oneway_ShallowWater_HeightResolvedBL"] = dict(
         gp=gp, eq="Oneway_ShallowWater_HeightResolvedBL",
         prm=dict(g=9.81, Kh=1500.0, Cd=2.4e-3, Hfree=2000.0, f=5e-5, Um=3.0, Vm=-2.0), ts=2.0, n=3, ic=ic, tiles=(1, 2))

@@ -16,8 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.parametrize("case_name,ntiles,exchange", [("LinearAdvection1D", 2, "torch"), ("LinearAdvection1D", 2, "columns"),
-                                                       ("LinearAdvectionRLZ", 2, "columns"), ("LinearAdvectionRZ", 4, "columns"),
-                                                       ("LinearAdvectionRZ", 4, "torch")])
+                                                       ("LinearAdvectionRLZ", 2, "columns"), ("LinearAdvectionRZ", 4, "columns")])
 def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, emu_lib, tmp_path):
     out = tmp_path / "out"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 2000), OMP_NUM_THREADS="1")
