@@ -75,6 +75,7 @@ struct sb_grid {
   ChebTables cheb;
   std::vector<SplineFactor> factors;
   std::vector<DevSplineFactor> hfactors;
+  DevSplineFactor* d_factors = nullptr;   // device copy of hfactors ([V]) for the merged spline solve
   std::vector<void*> owned;   // device allocations freed at destroy
   double* physical = nullptr;
   const double* slot0_src = nullptr;   // calcTendency's `physical .= var_np1` (src/semiimplicit.jl:731) deferred until slot 0 is read
@@ -233,6 +234,7 @@ static void build_grid(sb_grid* G) {
   }
   G->hfactors.resize(d.V);
   for (int v = 0; v < d.V; ++v) G->hfactors[v] = df[fidx[v]];
+  G->d_factors = G->up(G->hfactors);
 
   // Chebyshev tables
   if (d.has_z) {
@@ -439,7 +441,7 @@ static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in
 }
 
 static void grid_spline(sb_grid* P, const double* B) {
-  launch_spline_solve(P->ctx(), P->dg, nullptr, P->hfactors, B, P->spectralA);
+  launch_spline_solve(P->ctx(), P->dg, P->d_factors, P->hfactors, B, P->spectralA);
 }
 
 static void fill_gridpoints(sb_grid* G, double* out) {
@@ -1058,7 +1060,7 @@ static void colsolve_solve(sb_model* M) {
       launch_assemble(c, cs.slab, tv, cs.recvB + cs.recv_off[t], nullptr, nullptr, 0, cs.slabB);
     }
   }
-  launch_spline_solve(c, cs.slab, nullptr, P->hfactors, cs.slabB, cs.slabA);
+  launch_spline_solve(c, cs.slab, P->d_factors, P->hfactors, cs.slabB, cs.slabA);
   if (cs.p2p) {     // every tile's slice straight into that tile's A, wherever it lives
     for (int t = 0; t < M->ntiles; ++t) {
       const DevGrid& d = cs.tdg[t];

@@ -13,6 +13,7 @@
 // DFT_m, each evaluated with Bluestein's chirp-z algorithm on a power-of-two FFT held in shared memory.
 #include "sb_internal.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <stdexcept>
 
@@ -978,10 +979,14 @@ __global__ void k_spline_solve(DevSplineFactor f, int ncols, int qc, const doubl
 // (A is read back: 4S instead of 2S of traffic, but 10x more columns in flight per SM than the
 // whole-column kernel above, whose 172 KB of shared memory allowed 64 columns per SM).
 #define SSQ 128
-__global__ void __launch_bounds__(SSQ) k_spline_solve2(DevSplineFactor f, int ncols, int chol_in_smem,
-                                                       const double* __restrict__ B, double* __restrict__ A) {
+__global__ void __launch_bounds__(SSQ) k_spline_solve2(const DevSplineFactor* __restrict__ fs, int ncols, int chol_in_smem,
+                                                       const double* __restrict__ B, double* __restrict__ A, long long vstride) {
   __shared__ double tile[SSQ][33];
   SB_DYN_SMEM(double, s_chol);
+  const DevSplineFactor f = fs[blockIdx.y];        // one launch covers every variable (blockIdx.y), each with its own BCs
+  if (f.periodic || f.nfree < 3) return;           // handled by k_spline_dense / k_spline_solve
+  B += (long long)blockIdx.y * vstride;
+  A += (long long)blockIdx.y * vstride;
   const int M = f.M, n = f.nfree, rL = f.rL, rR = f.rR;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long c0 = (long long)blockIdx.x * SSQ;
@@ -1083,10 +1088,31 @@ __global__ void k_spline_dense(DevSplineFactor f, int ncols, const double* __res
   A[idx] = s;
 }
 
-void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFactor* /*dfactors*/,
+void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFactor* dfactors,
                          const std::vector<DevSplineFactor>& hf, const double* B, double* A) {
   ProfScope prof_scope_(c, "spline_solve");
   const int ncols = g.bz * g.ncolp;
+  static const bool v1 = std::getenv("SB_RADIAL_V1") != nullptr;
+  // streaming kernel: all variables with banded (non-periodic) factors in ONE launch
+  bool merged = false;
+  if (!v1 && dfactors) {
+    int nmax = 0;
+    for (int v = 0; v < g.V; ++v)
+      if (!hf[v].periodic && hf[v].nfree >= 3) nmax = std::max(nmax, hf[v].nfree);
+    if (nmax > 0) {
+      const int in_smem = (size_t)4 * nmax * 8 <= 96 * 1024;
+      size_t smem = in_smem ? (size_t)4 * nmax * 8 : 0;
+      if (smem > 8 * 1024) {   // static tile (33 KB) + table may exceed the 48 KB default
+        cudaError_t e = cudaFuncSetAttribute(k_spline_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+      }
+      SB_LAUNCH(k_spline_solve2, dim3((ncols + SSQ - 1) / SSQ, g.V), dim3(SSQ), smem, c.stream, dfactors, ncols, in_smem, B, A,
+                g.S);
+      SB_CHECK_LAUNCH();
+      count(c);
+      merged = true;
+    }
+  }
   for (int v = 0; v < g.V; ++v) {
     const DevSplineFactor& f = hf[v];
     const double* Bv = B + (long long)v * g.S;
@@ -1094,14 +1120,8 @@ void launch_spline_solve(const LaunchCtx& c, const DevGrid& g, const DevSplineFa
     if (f.periodic) {
       long long tot = (long long)ncols * f.M;
       SB_LAUNCH(k_spline_dense, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, c.stream, f, ncols, Bv, Av);
-    } else if (!std::getenv("SB_RADIAL_V1") && f.nfree >= 3) {
-      const int in_smem = (size_t)4 * f.nfree * 8 <= 96 * 1024;
-      size_t smem = in_smem ? (size_t)4 * f.nfree * 8 : 0;
-      if (smem > 8 * 1024) {   // static tile (33 KB) + table may exceed the 48 KB default
-        cudaError_t e = cudaFuncSetAttribute(k_spline_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-      }
-      SB_LAUNCH(k_spline_solve2, dim3((ncols + SSQ - 1) / SSQ), dim3(SSQ), smem, c.stream, f, ncols, in_smem, Bv, Av);
+    } else if (merged && f.nfree >= 3) {
+      continue;
     } else {
       int Ms = f.M | 1;
       int qc = 64;
