@@ -292,7 +292,7 @@ def run_ours(args):
 
     # end to end through the public API with HOST buffers: pinned state in -> one model_loop cycle -> state out
     e2e = None
-    if not args.no_e2e and not distributed:
+    if not args.no_e2e:
         hin = torch.empty((NVARS, tile.N), dtype=torch.float64, pin_memory=True)
         hout = torch.empty((NVARS, tile.N), dtype=torch.float64, pin_memory=True)
         a_in, a_out = hin.numpy().T, hout.numpy().T      # [N, V] Fortran views
@@ -304,11 +304,10 @@ def run_ours(args):
             m.get_state_into(0, a_out)
         e2e_step()
         e_ms = timed(e2e_step, max(2, min(args.steps, 3))) / max(2, min(args.steps, 3))
-        e2e = {"value": 1e3 / e_ms, "unit": UNIT, "h2d_bytes_per_step": int(a_in.nbytes), "d2h_bytes_per_step": int(a_out.nbytes),
-               "what": "Model.set_state(host pinned [N,V]) -> Model.cycle() -> get_state(host pinned [N,V])"}
-    elif distributed:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "what": "end-to-end host-buffer stepping is measured at N=1 only"}
+        e2e = {"value": ntiles * 1e3 / e_ms, "unit": UNIT, "h2d_bytes_per_step": int(a_in.nbytes) * ntiles,
+               "d2h_bytes_per_step": int(a_out.nbytes) * ntiles,
+               "what": "per rank: Model.set_state(host pinned [N_tile,V]) -> Model.cycle() -> get_state(host pinned [N_tile,V]); "
+                       "bytes summed over ranks"}
 
     per_rank = None
     if distributed:   # every rank's per-kernel time: the step is as slow as the slowest tile

@@ -191,6 +191,9 @@ int sb_model_tendency(sb_model_t m);
  * then :305-314 of the next iteration): var_np1 -> K1 -> shared sum -> K2 -> K3 -> equation set ->
  * var_np1.  Same work as sb_model_step; used for host-buffer (end-to-end) stepping. */
 int sb_model_cycle(sb_model_t m, int64_t t);
+/* the first half of advanceTimestep alone (src/semiimplicit.jl:305-314): tileTransform! + equation set + time step.
+ * sb_model_tendency + caller-driven exchange + sb_model_physics = sb_model_cycle when the exchange is the caller's. */
+int sb_model_physics(sb_model_t m, int64_t t);
 /* per-kernel CUDA-event timing on the model's stream: enable/disable, then read
  * "name launches total_ms\n" lines (clears the records). */
 int sb_model_profile(sb_model_t m, int32_t on);

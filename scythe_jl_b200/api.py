@@ -777,8 +777,9 @@ class Model:
             return
         self.lib.check(self.lib.sb_model_tendency(self.handle))
         self._exchange()
-        self.lib.check(self.lib.sb_model_spline_transform(self.handle))
-        raise NotImplementedError("physics half after a torch exchange: use step()")
+        if not self.columns:
+            self.lib.check(self.lib.sb_model_spline_transform(self.handle))
+        self.lib.check(self.lib.sb_model_physics(self.handle, self.t))
 
     def initialize_tiles(self, tile_ics):
         """Tile-parallel initialize_model: each local tile gets its own slice of the initial state

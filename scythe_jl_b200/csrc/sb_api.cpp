@@ -1504,6 +1504,9 @@ int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* 
 int sb_model_tendency(sb_model_t m) {
   return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); tiles_tendency(m); });
 }
+int sb_model_physics(sb_model_t m, int64_t t) {
+  return guarded([&] { if (!m || t < 1) throw std::invalid_argument("bad argument"); tiles_physics(m, t); });
+}
 int sb_model_cycle(sb_model_t m, int64_t t) {
   try {
     if (!m || t < 1) return fail(SB_EINVAL, "bad argument");

@@ -39,6 +39,17 @@ def main():
             outs[(name, ex)] = m.state(0, "var_np1")
             m.close()
             dist.barrier()
+            if ex in ("columns", "columns-p2p"):
+                # host-driven cycle (tendency -> exchange -> physics), the path bench.py's e2e times: same state as stepping
+                m = pkg_model(case, ntiles, lib, distributed=True, exchange=ex, device=local)
+                m.initialize_tiles(ics)
+                for _ in range(case["n"]):
+                    m.cycle()
+                same = np.array_equal(m.state(0, "var_np1"), outs[(name, ex)])
+                print(f"rank {rank} {name} {ex}: cycle() == step(): {same}", flush=True)
+                assert same
+                m.close()
+                dist.barrier()
         ref = outs[(name, "torch")]
         for ex in ("columns", "columns-native", "columns-p2p", "columns-p2p-native"):
             same = np.array_equal(outs[(name, ex)], ref)
