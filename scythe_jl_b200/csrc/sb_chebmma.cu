@@ -199,8 +199,11 @@ void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
   ProfScope prof_scope_(c, "inv_z");
   // 16-byte async copies need every [mode] row of every tile 16-byte aligned
   const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0 && in_vstride % 2 == 0 && (g.has_l || g.rDim % 2 == 0);
-  static const bool wide = std::getenv("SB_INVZ_COLS") && std::atoi(std::getenv("SB_INVZ_COLS")) == 32;   // A/B switch
-  if (wide) {
+  static const int cols = std::getenv("SB_INVZ_COLS") ? std::atoi(std::getenv("SB_INVZ_COLS")) : 16;   // A/B switch
+  if (cols == 8 && g.zDim == 64) {   // 4 level tiles x 1 column group = 4 warps, four CTAs per SM
+    if (al16) launch_inv_z_mma_t<16, 8>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
+    else launch_inv_z_mma_t<8, 8>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
+  } else if (cols == 32) {
     if (al16) launch_inv_z_mma_t<16, 32>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
     else launch_inv_z_mma_t<8, 32>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
   } else {
