@@ -439,7 +439,7 @@ struct R3Ctx {
 };
 
 // steps shared by forward and inverse: x thirds are in the group's buffers -> s_r -> convolution -> c_r' back in the buffers
-template <int LOG2L2>
+template <int LOG2L2, bool TW1C = false>
 __device__ __forceinline__ void conv3(const R3Ctx<LOG2L2>& cx, double2* const (&gb)[3], const double2* __restrict__ FHt,
                                       int r, int grp, int team, int tl, bool active) {
   typedef R3Cfg<LOG2L2> C;
@@ -460,7 +460,7 @@ __device__ __forceinline__ void conv3(const R3Ctx<LOG2L2>& cx, double2* const (&
     }
   }
   group_sync<T>(grp);              // every team has gathered its s_r: the buffers may be overwritten
-  conv2<LOG2L2, false>(v, gb[r], cx.s_tw0, cx.s_twr, FHt + (size_t)r * L2, tl, team, active);
+  conv2<LOG2L2, false, TW1C>(v, gb[r], cx.s_tw0, cx.s_twr, FHt + (size_t)r * L2, tl, team, active);
   team_sync<T>(team);              // the team's last-pass loads are done
   if (active) {
 #pragma unroll
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(R3Cfg<LOG2L2>::NT, 1) k_inv_l3(DevGrid g, cons
         }
       }
       group_sync<T>(grp);            // x is complete
-      conv3<LOG2L2>(cx, gb, FHt, r, grp, team, tl, active);
+      conv3<LOG2L2, true>(cx, gb, FHt, r, grp, team, tl, active);
       if (active) {
         double* orow;
         if (out_is_phys)
