@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 3) k_fwd_z_mma(DevGrid g, const ZT
                                                           double* __restrict__ mirror, long long mirror_vs,
                                                           double* __restrict__ out, long long out_vs,
                                                           const double* __restrict__ fwdB) {
-  SB_DYN_SMEM(double, u);       // [2 buffers][32 columns][FZ_US]
+  SB_DYN_SMEM(double, u);       // [3 stages][32 columns][FZ_US]
   const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nkt = zh >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = lane & 3, i = lane >> 2;
@@ -249,19 +249,22 @@ __global__ void __launch_bounds__(FZ_THREADS, 3) k_fwd_z_mma(DevGrid g, const ZT
     }
     sb_cp_commit();
   };
+  // three-stage ring of tiles: two tiles are always in flight behind the one being transformed
   const int G = gridDim.x;
   auto desc = [&](int w) { return w < nwork ? tiles[w % ntiles] : ZTile{}; };
+  auto issue_w = [&](int w, int stage) {          // always commits a group (possibly empty): uniform group counting
+    if (w < nwork) issue(w, desc(w), u + stage * 32 * FZ_US);
+    else sb_cp_commit();
+  };
   int w = blockIdx.x, cur = 0;
-  ZTile zt0 = desc(w), zt1 = desc(w + G), zt2;
-  if (w < nwork) issue(w, zt0, u);
+  issue_w(w, 0);
+  issue_w(w + G, 1);
   for (; w < nwork; w += G) {
-    zt2 = desc(w + 2 * G);       // descriptor prefetch: keeps the L2 round trip off the barrier -> copy path
-    sb_cp_wait<0>();
-    __syncthreads();
-    if (w + G < nwork) issue(w + G, zt1, u + (cur ^ 1) * 32 * FZ_US);
+    const ZTile zt = desc(w);     // (cached: it was fetched when the tile was issued) -- overlaps the wait below
+    sb_cp_wait<1>();              // everything but the newest group has landed: tile w is in stage `cur`
+    __syncthreads();              // ... for every thread, and everybody has left the stage tile w-G used
+    issue_w(w + 2 * G, cur == 0 ? 2 : cur - 1);
     const int v = w / ntiles;
-    const ZTile zt = zt0;
-    zt0 = zt1; zt1 = zt2;
     const double* ub = u + cur * 32 * FZ_US;
     if (mirror) {
       double* mv = mirror + (long long)v * mirror_vs + (long long)zt.hcol0 * zDim;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 3) k_fwd_z_mma(DevGrid g, const ZT
         if (zb1 < bz) o[(long long)zb1 * zt.out_stride] = D[nt][1];
       }
     }
-    cur ^= 1;
+    cur = (cur == 2) ? 0 : cur + 1;
   }
 }
 
@@ -315,9 +318,13 @@ void launch_fwd_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
                       long long in_vstride, double* mirror, long long mirror_vstride, double* out, long long out_vstride,
                       const double* fwdB) {
   ProfScope prof_scope_(c, "fwd_z");
-  const size_t smem = (size_t)2 * 32 * FZ_US * sizeof(double);
+  const size_t smem = (size_t)3 * 32 * FZ_US * sizeof(double);
   const int nwork = ntiles * nvars;
   const int gx = nwork < 148 * 4 ? nwork : 148 * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e0 = cudaFuncSetAttribute(k_fwd_z_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e0 != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e0));
+  }
   SB_LAUNCH(k_fwd_z_mma, dim3(gx), dim3(FZ_THREADS), smem, c.stream, g, tiles, ntiles, nvars, in, in_vstride, mirror,
             mirror_vstride, out, out_vstride, fwdB);
   cudaError_t e = cudaGetLastError();
