@@ -45,6 +45,10 @@ def parse():
                     choices=["LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL"],
                     help="C4 step to time: the transform-dominated linear set (headline) or the 6-variable TC boundary-layer set")
     ap.add_argument("--no-tcbl", action="store_true", help="skip the secondary C4 run of the TC boundary-layer equation set")
+    ap.add_argument("--k3-slots", default="needed", choices=["needed", "all"],
+                    help="slots the in-step tileTransform! produces: what the equation-set kernel reads (product default) or "
+                         "all D slots of every variable (the reference's materialised dataflow); the default run times both")
+    ap.add_argument("--no-materialised", action="store_true", help="skip the secondary all-slots timing (ncu captures)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -266,6 +270,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()              # nvidia-smi needs ~0.3 s to produce its first sample: start it before the warm-up
+    m.set_k3_slots(args.k3_slots)
     for _ in range(args.warmup):
         m.step()
     l0 = m.launch_count()
@@ -277,6 +282,18 @@ def run_ours(args):
     launches = m.launch_count() - l0
     ms_step = total_ms / args.steps
     value = ntiles * 1e3 / ms_step
+    # the same step with tileTransform! producing all D slots of every variable (the reference's dataflow)
+    mat = None
+    if args.k3_slots == "needed" and not args.no_materialised:
+        m.set_k3_slots("all")
+        nmat = max(3, min(args.steps, 10))
+        for _ in range(2):
+            m.step()
+        m.profile(True)
+        mat_ms = timed(m.step, nmat) / nmat
+        m.profile(False)
+        mat = {"ms_per_step": mat_ms, "value": ntiles * 1e3 / mat_ms, "steps": nmat, "prof": m.profile_report()}
+        m.set_k3_slots("needed")
 
     # transforms/sec (the second half of the BASELINE metric): K1 alone and K2+K3 alone on the tile
     def k1():
@@ -327,23 +344,36 @@ def run_ours(args):
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     N, Sg, D, V = d["N"], d["S"], d["D"], NVARS
     Sp = m.patch.S
-    groups = {
-        "K3 tileTransform! (inv_r+inv_l+inv_z)": (["inv_r", "inv_l", "inv_z"], 8.0 * V * (Sg + N * D)),
-        "K1 spectralTransform! (fwd_z+fwd_l+fwd_r)": (["fwd_z", "fwd_l", "fwd_r"], 8.0 * V * (N + Sg)),
-        "K2 splineTransform! (spline_solve)": (["spline_solve"], 8.0 * V * 2 * Sp),
-        f"K4 equation set + AB3 ({args.equation_set})": (["equation_set"], 8.0 * N * ((5 + 2 + 6 + 6) if not tcbl else (26 + 10 + 13))),
-    }
-    detail = {}
-    for name, (ks, nbytes) in groups.items():
-        ms = sum(prof.get(k, {"ms": 0.0})["ms"] for k in ks) / args.steps
-        detail[name] = {"ms_per_step": ms, "algorithmic_GB": nbytes / 1e9,
-                        "achieved_GBps": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else None,
-                        "frac": ((nbytes / 1e9) / (ms / 1e3) / peak) if ms > 0 else None}
-    kern_ms = {k: v["ms"] / args.steps for k, v in prof.items()}
+    # (variable, slot) pairs the equation-set kernel reads / variables it reads at all (sb_model.cu: equation_set_needs)
+    ns_needed, v_read = (21, 5) if tcbl else (7, 3)
+
+    def tables(prof_, steps_, ns, vr):
+        """per-K-group time and HBM-roofline fraction on ALGORITHMIC bytes; ns = slots K3 writes and K4
+        reads (all: V*D), vr = variables K3 transforms"""
+        k4_hist = 4 * V + (1 if tcbl else 0)              # K4 kernel: read 2 history arrays, write var_np1 + expdot_n (+ wb)
+        groups = {
+            "K3 tileTransform! (inv_r+inv_l+inv_z)": (["inv_r", "inv_l", "inv_z"], 8.0 * (vr * Sg + N * ns)),
+            "K1 spectralTransform! (fwd_z+fwd_l+fwd_r)": (["fwd_z", "fwd_l", "fwd_r"], 8.0 * V * (N + Sg)),
+            "K2 splineTransform! (spline_solve)": (["spline_solve"], 8.0 * V * 2 * Sp),
+            f"K4 equation set + AB3 ({args.equation_set})": (["equation_set"], 8.0 * N * (ns_needed + k4_hist)),
+        }
+        det = {}
+        for name, (ks, nbytes) in groups.items():
+            ms = sum(prof_.get(k, {"ms": 0.0})["ms"] for k in ks) / steps_
+            det[name] = {"ms_per_step": ms, "algorithmic_GB": nbytes / 1e9,
+                         "achieved_GBps": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else None,
+                         "frac": ((nbytes / 1e9) / (ms / 1e3) / peak) if ms > 0 else None}
+        # timestep, SURVEY 8(d): K3 (S + N slots) + K4 (N slots + 5N) + K1 (N + S) + K2 (2S); all slots: 8V(2ND + 6N + 4S)
+        step_b = 8.0 * ((vr * Sg + N * ns) + N * (ns + 5 * V) + V * (N + Sg) + 2 * V * Sg)
+        return det, {k: v["ms"] / steps_ for k, v in prof_.items()}, step_b
+
+    ns_run, vr_run = (ns_needed, v_read) if args.k3_slots == "needed" else (V * D, V)
+    detail, kern_ms, step_bytes = tables(prof, args.steps, ns_run, vr_run)
     top = max(detail, key=lambda k: detail[k]["ms_per_step"])
     # measured DRAM traffic / FP64-pipe activity of the same step from the committed ncu pass (profiles/), if present
     traffic, ncu_note = None, None
-    prof_file = ROOT / "profiles" / "r1j_step_kernels.json"
+    prof_name = "r1k_step_kernels_needed.json" if args.k3_slots == "needed" else "r1j_step_kernels.json"
+    prof_file = ROOT / "profiles" / prof_name
     if prof_file.exists() and world == 1 and cells_tile == C4_CELLS and not tcbl:
         pk = json.loads(prof_file.read_text())["one_step"]
         sel = {"K3": ("k_inv_r", "k_inv_l", "k_inv_z"), "K1": ("k_fwd_z", "k_fwd_l", "k_fwd_r"), "K2": ("k_spline",),
@@ -351,7 +381,7 @@ def run_ours(args):
         rows = [v for k, v in pk.items() if any(s_ in k for s_ in sel)]
         traffic = 1e9 * sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows)
         fft = [v for k, v in pk.items() if "k_inv_l2" in k]
-        ncu_note = {"file": "profiles/r1j_step_kernels.json",
+        ncu_note = {"file": "profiles/" + prof_name,
                     "k_inv_l2_fp64_pipe_pct": sum(r["fp64_pipe_pct"] * r["ms"] for r in fft) / max(sum(r["ms"] for r in fft), 1e-9),
                     "k_inv_l2_share_of_step_under_ncu": sum(r["share"] for r in fft),
                     "note": "the ring FFT inside K3 is FP64-pipe bound (Bluestein), not HBM bound; measured FP64 peak "
@@ -360,7 +390,6 @@ def run_ours(args):
             "frac": detail[top]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": detail[top]["algorithmic_GB"] * 1e9,
             "share_of_step": detail[top]["ms_per_step"] / ms_step, "ncu": ncu_note}
-    step_bytes = 8.0 * V * (2 * N * D + 6 * N + 4 * Sg)
     cfg_exchange = m.exchange
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -370,6 +399,20 @@ def run_ours(args):
             "timestep_frac_of_hbm_roofline": (step_bytes / 1e9) / (ms_step / 1e3) / peak,
             "transforms_per_s": {"spectralTransform_K1": 1e3 / k1_ms, "gridTransform_K2K3": 1e3 / k23_ms,
                                  "K1_ms": k1_ms, "K2K3_ms": k23_ms, "vars": V}}
+    line["config"]["k3_slots"] = (
+        f"needed: the in-step tileTransform! produces the {ns_needed} (variable, slot) pairs the {args.equation_set} kernel reads, "
+        f"not all {V * D} (state bit-identical, tests/test_gpu_parity.py::test_needed_slots_*); the all-slots step is timed in "
+        "'materialised'" if args.k3_slots == "needed" else f"all: every one of the {V * D} (variable, slot) pairs is produced")
+    if mat:
+        mdet, mkern, mbytes = tables(mat["prof"], mat["steps"], V * D, V)
+        mtop = max(mdet, key=lambda k: mdet[k]["ms_per_step"])
+        line["materialised"] = {
+            "what": "same step, tileTransform! producing all D slots of all variables (SURVEY 8(d) 'materialised dataflow')",
+            "value": mat["value"], "unit": UNIT, "ms_per_step": mat["ms_per_step"], "steps": mat["steps"],
+            "kernel_ms_per_step": mkern, "roofline_detail": mdet, "timestep_algorithmic_GB": mbytes / 1e9,
+            "timestep_frac_of_hbm_roofline": (mbytes / 1e9) / (mat["ms_per_step"] / 1e3) / peak,
+            "roofline": {"bound": "hbm", "kernel": mtop, "achieved": mdet[mtop]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": mdet[mtop]["frac"], "algorithmic_bytes_per_launch": mdet[mtop]["algorithmic_GB"] * 1e9}}
     if world == 1 and not tcbl and not args.no_tcbl and not args.cells:
         # secondary number (north_star item 4): the same C4 grid stepped with the 6-variable height-resolved TC
         # boundary-layer set, in a fresh process once this model's 60 GB are released
@@ -381,7 +424,11 @@ def run_ours(args):
             t2 = json.loads(r.stdout.strip().splitlines()[-1])
             line["tcbl"] = {"equation_set": "Oneway_ShallowWater_HeightResolvedBL", "vars": 6, "value": t2["value"], "unit": UNIT,
                             "ms_per_step": t2["ms_per_step"], "kernel_ms_per_step": t2["kernel_ms_per_step"],
-                            "timestep_frac_of_hbm_roofline": t2["timestep_frac_of_hbm_roofline"]}
+                            "timestep_frac_of_hbm_roofline": t2["timestep_frac_of_hbm_roofline"],
+                            "k3_slots": t2["config"].get("k3_slots"),
+                            "materialised": {k: t2["materialised"][k] for k in ("value", "ms_per_step", "kernel_ms_per_step",
+                                                                                "timestep_frac_of_hbm_roofline")}
+                            if "materialised" in t2 else None}
         except Exception as e:  # the headline line must still print
             line["tcbl"] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "sb_model_tendency": (C.c_int, [model_t]),
     "sb_model_cycle": (C.c_int, [model_t, C.c_int64]),
     "sb_model_physics": (C.c_int, [model_t, C.c_int64]),
+    "sb_model_set_k3_slots": (C.c_int, [model_t, C.c_int32]),
     "sb_model_profile": (C.c_int, [model_t, C.c_int32]),
     "sb_model_profile_report": (C.c_int, [model_t, C.c_char_p, C.c_int64]),
     "sb_model_sync": (C.c_int, [model_t]),

@@ -378,7 +378,7 @@ static void grid_forward(sb_grid* G, const double* in, double* mirror) {
   }
 }
 
-static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in, long long fs, long long vs);
+static void grid_inv_z(sb_grid* T, const LaunchCtx& c, int nv, int v0, int nfields, const double* in, long long fs, long long vs);
 
 // Chebyshev analysis of a variable chunk: tensor-core (DMMA) kernel when the level count allows it
 static void grid_fwd_z(sb_grid* G, int nv, const double* in, double* mir, double* out, long long out_vs) {
@@ -390,8 +390,39 @@ static void grid_fwd_z(sb_grid* G, int nv, const double* in, double* mir, double
     launch_fwd_z(G->ctx(), d, G->d_ztiles, G->nztiles, nv, in, d.N, mir, d.N, out, out_vs, G->d_fwdT);
 }
 
-// inverse transform: patch A -> tile physical (K3)
-static void grid_inverse(sb_grid* P, sb_grid* T) {
+// Physical slots (bit d of the mask) -> what each K3 stage has to produce.  Slot order: R {f, r, rr}; RL {f, r, rr, l, ll};
+// RZ {f, r, rr, z, zz}; RLZ {f, r, rr, l, ll, z, zz}.
+static K3Need k3_need_from_slots(const DevGrid& t, unsigned slots) {
+  K3Need n;
+  const unsigned all = (1u << t.D) - 1u;
+  slots &= all;
+  if (slots == all) return n;
+  if (t.has_l && t.has_z) {
+    const unsigned zz = (slots >> 5) & 3u;
+    n.lmask = (slots & 31u) | (zz ? 1u : 0u);
+    n.zmask = n.lmask;
+    n.zsel = (slots & 1u) | (zz << 1);
+    n.smask = ((n.lmask & 25u) ? 1u : 0u) | (n.lmask & 6u);
+  } else if (t.has_l) {
+    n.lmask = slots & 31u;
+    n.smask = ((n.lmask & 25u) ? 1u : 0u) | (n.lmask & 6u);
+  } else if (t.has_z) {
+    const unsigned zz = (slots >> 3) & 3u;
+    n.smask = (slots & 7u) | (zz ? 1u : 0u);
+    n.zmask = n.smask;
+    n.zsel = (slots & 1u) | (zz << 1);
+  } else {
+    n.smask = slots & 7u;
+  }
+  return n;
+}
+
+// inverse transform: patch A -> tile physical (K3).  `need` (optional): per variable, the physical slots that
+// will be read before the next K3 (tiles_physics passes what the equation-set kernel reads; the derivative slots
+// of a tile are intermediates between K3 and K4 and are visible to nothing else -- in the reference they are
+// overwritten by calcTendency's broadcast right after, src/semiimplicit.jl:731).  Slots outside the mask keep
+// stale values.
+static void grid_inverse(sb_grid* P, sb_grid* T, const unsigned* need = nullptr, bool poison = false) {
   DevGrid& t = T->dg;
   DevGrid& p = P->dg;
   if (t.has_l != p.has_l || t.has_z != p.has_z || t.V != p.V || t.bz != p.bz || t.zDim != p.zDim)
@@ -399,16 +430,30 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
   if (t.coefOffset < p.coefOffset || t.coefOffset + t.b_rDim > p.coefOffset + p.b_rDim)
     throw std::invalid_argument("tile is not inside the patch");
   T->ensure_physical();
-  T->slot0_src = nullptr;                 // every slot is rewritten below
+  const unsigned all = (1u << t.D) - 1u;
+  if (need && poison)   // test hook: slots outside the mask become NaN
+    CU(cudaMemsetAsync(T->physical, 0xFF, (size_t)t.N * t.V * t.D * sizeof(double), T->stream));
+  // a variable with an empty mask is never read (diagnostic output of the equation set); any other variable's
+  // slot 0 is always produced
+  auto chunk_slots = [&](int v0, int nv) {
+    unsigned m = need ? 0u : all;
+    for (int v = v0; need && v < v0 + nv; ++v) m |= (need[v] & all) ? ((need[v] & all) | 1u) : 0u;
+    return m;
+  };
+  T->slot0_src = nullptr;                 // slot 0 of every variable that is read is rewritten below
   LaunchCtx c = T->ctx();
   if (!t.has_l && !t.has_z) {
-    launch_inv_r(c, t, p, t.V, P->spectralA, p.S, T->physical, 0, 0, 1, 0);
+    c.need = k3_need_from_slots(t, chunk_slots(0, t.V));
+    if (c.need.smask) launch_inv_r(c, t, p, t.V, P->spectralA, p.S, T->physical, 0, 0, 1, 0);
     return;
   }
   T->ensure_scratch();
   const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
   for (int v0 = 0; v0 < t.V; v0 += T->vchunk) {
     const int nv = std::min(T->vchunk, t.V - v0);
+    const unsigned slots = chunk_slots(v0, nv);
+    if (!slots) continue;                             // nothing of these variables is read (diagnostic outputs)
+    c.need = k3_need_from_slots(t, slots);
     double* SL = T->scratch;                          // [3][vchunk][slN]
     double* SZ = T->scratch + ((3 * slN * T->vchunk + 15) & ~15LL);    // [5][vchunk][szN], 128-byte aligned
     const long long sl_fs = slN * T->vchunk, sz_fs = szN * T->vchunk;
@@ -416,28 +461,28 @@ static void grid_inverse(sb_grid* P, sb_grid* T) {
     if (t.has_l && t.has_z) {
       launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
                    slN, SZ, sz_fs, szN, 0, v0, &T->iwork2, T->d_iwork2.data());
-      grid_inv_z(T, nv, v0, 5, SZ, sz_fs, szN);
+      grid_inv_z(T, c, nv, v0, 5, SZ, sz_fs, szN);
     } else if (t.has_l) {
       launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, nv, SL, sl_fs,
                    slN, T->physical, 0, 0, 1, v0, &T->iwork2, T->d_iwork2.data());
     } else {
-      grid_inv_z(T, nv, v0, 3, SL, sl_fs, slN);
+      grid_inv_z(T, c, nv, v0, 3, SL, sl_fs, slN);
     }
   }
 }
 
 // Chebyshev inverse of a variable chunk: parity fast path when no variable of the chunk has vertical BCs
-static void grid_inv_z(sb_grid* T, int nv, int v0, int nfields, const double* in, long long fs, long long vs) {
+static void grid_inv_z(sb_grid* T, const LaunchCtx& c, int nv, int v0, int nfields, const double* in, long long fs, long long vs) {
   const char* mode = std::getenv("SB_INVZ");   // A/B switch: "generic" | "fma" | (default) "mma"
   const std::string md = mode ? mode : "mma";
   bool bcfree = md != "generic";
   for (int v = v0; v < v0 + nv && bcfree; ++v) bcfree = T->z_bcfree[v] != 0;
   if (bcfree && md == "mma" && inv_z_mma_ok(T->dg, nfields))
-    launch_inv_z_mma(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parB);
+    launch_inv_z_mma(c, T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parB);
   else if (bcfree && inv_z_par_ok(T->dg, nfields))
-    launch_inv_z_par(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parM);
+    launch_inv_z_par(c, T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_parM);
   else
-    launch_inv_z(T->ctx(), T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_invM);
+    launch_inv_z(c, T->dg, T->d_ztiles, T->nztiles, nv, v0, nfields, in, fs, vs, T->physical, T->d_invM);
 }
 
 static void grid_spline(sb_grid* P, const double* B) {
@@ -627,6 +672,7 @@ struct sb_model {
   double ts = 0, integration_time = 0, output_interval = 0;
   int eq = -1;
   int semiimplicit = 0;
+  int k3_slots = 0;   // sb_model_set_k3_slots: 0 = what the equation set reads, 1 = all D slots, 2 = 0 + unread slots poisoned
   EqParams ep{};
   int ntiles = 1, tile_first = 0, tile_count = 1;
   std::vector<double> tile_params;
@@ -807,6 +853,7 @@ static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first
   M->ts = mp->ts; M->integration_time = mp->integration_time; M->output_interval = mp->output_interval;
   M->semiimplicit = mp->semiimplicit;
   M->eq = equation_set_from_name(mp->equation_set);
+  if (const char* e = std::getenv("SB_K3_FULL")) M->k3_slots = std::atoi(e) != 0 ? 1 : 0;
   if (M->eq < 0) throw Unsupported(std::string("equation set \"") + mp->equation_set + "\" is not built as a CUDA kernel (no CPU fallback)");
   const bool has_z = (M->gp.geometry == SB_GEOM_RZ || M->gp.geometry == SB_GEOM_RLZ);
   if (mp->ref_sbar && mp->ref_xibar && mp->ref_mubar && has_z) {
@@ -884,9 +931,13 @@ static void model_initialize(sb_model* M, const double* ic_host) {
 // first half of advanceTimestep: tileTransform! + equation set + explicit/semi-implicit step
 static void tiles_physics(sb_model* M, int64_t t) {
   sb_grid* P = M->patch;
+  // K3 produces what the equation-set kernel reads, not every slot (sb_model_set_k3_slots(m, 1): all D slots of all
+  // variables, the reference's materialised dataflow -- bench.py times both)
+  std::vector<unsigned> need(P->dg.V);
+  equation_set_needs(M->eq, M->ep, P->dg, need.data());
   for (auto& T : M->tiles) {
     sb_grid* G = T.grid;
-    grid_inverse(M->cs.on ? G : P, G);                      // tileTransform!  :305 (plane-distributed solve: A arrives tile-local)
+    grid_inverse(M->cs.on ? G : P, G, M->k3_slots == 1 ? nullptr : need.data(), M->k3_slots == 2);   // tileTransform!  :305 (plane-distributed solve: A arrives tile-local)
     ModelArrays a{};
     a.phys = G->physical; a.var_np1 = T.var_np1;
     a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
@@ -1517,6 +1568,13 @@ int sb_model_cycle(sb_model_t m, int64_t t) {
     return SB_OK;
   } catch (const CommError& e) { return fail(SB_ECOMM, e.what());
   } catch (const std::exception& e) { return fail(SB_ECUDA, e.what()); }
+}
+int sb_model_set_k3_slots(sb_model_t m, int32_t mode) {
+  return guarded([&] {
+    if (!m) throw std::invalid_argument("NULL model");
+    if (mode < 0 || mode > 2) throw std::invalid_argument("k3 slot mode must be 0 (needed), 1 (all) or 2 (needed, rest poisoned)");
+    m->k3_slots = mode;
+  });
 }
 int sb_model_profile(sb_model_t m, int32_t on) {
   return guarded([&] {

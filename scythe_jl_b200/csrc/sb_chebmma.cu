@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(COLS * 16, 32 / COLS) k_inv_z_mma(DevGrid g, c
                                                              int nvars, int var0, int nfields,
                                                              const double* __restrict__ in, long long in_fs,
                                                              long long in_vs, double* __restrict__ phys,
-                                                             const double* __restrict__ parB) {
+                                                             const double* __restrict__ parB, unsigned zmask,
+                                                             unsigned zsel) {
   SB_DYN_SMEM(double, a);       // [2 buffers][nfields][2 parities][ZM_KK][ZM_CS]
   constexpr int ZM_CS = COLS + 4, ZM_THREADS = COLS * 16, SPLIT = 32 / COLS;
   const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = (ZM_THREADS / 32) / nzt;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(COLS * 16, 32 / COLS) k_inv_z_mma(DevGrid g, c
     for (int c = tid; c < total; c += ZM_THREADS) {
       const int row = c / CPR, col = (c - row * CPR) * CE;
       const int4 rt = rowtab[row];
-      if (col < ztile.ncols) {
+      if (col < ztile.ncols && ((zmask >> rt.x) & 1)) {   // fields nobody reads are not fetched
         const double* sp = src + (long long)rt.x * in_fs + (long long)rt.y * ztile.out_stride + col;
         double* dp = dst + rt.z + col;
         if (CB == 16) sb_cp_async16(dp, sp); else sb_cp_async8(dp, sp);
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(COLS * 16, 32 / COLS) k_inv_z_mma(DevGrid g, c
       const bool live = c < ztile.ncols;
       double* const o = pv + ((long long)ztile.hcol0 + c) * zDim;
       const double* ap = ab + q * ZM_CS + c;        // + (parity*ZM_KK + kt*4) * ZM_CS per fragment
-      // ---- field 0: value, d/dz, d2/dz2 share the A fragments
-      {
+      // ---- field 0: value, d/dz, d2/dz2 share the A fragments (zsel: which of the three anybody reads)
+      if (zsel == 7u) {
         double E0[2] = {0, 0}, O0[2] = {0, 0}, E1[2] = {0, 0}, O1[2] = {0, 0}, E2[2] = {0, 0}, O2[2] = {0, 0};
 #pragma unroll
         for (int kt = 0; kt < ZM_KT; ++kt) {
@@ -135,9 +136,28 @@ __global__ void __launch_bounds__(COLS * 16, 32 / COLS) k_inv_z_mma(DevGrid g, c
           *reinterpret_cast<double2*>(ozz + z0) = make_double2(E2[0] + O2[0], E2[1] + O2[1]);
           *reinterpret_cast<double2*>(ozz + zDim - 2 - z0) = make_double2(E2[1] - O2[1], E2[0] - O2[0]);
         }
+      } else {
+        // one matrix at a time (same DMMA order per output as above, so the values are bit-identical)
+#pragma unroll
+        for (int mtx = 0; mtx < 3; ++mtx) {
+          if (!((zsel >> mtx) & 1)) continue;
+          double E[2] = {0, 0}, O[2] = {0, 0};
+#pragma unroll
+          for (int kt = 0; kt < ZM_KT; ++kt) {
+            sb_dmma(E[0], E[1], ap[(kt * 4) * ZM_CS], B[mtx][0][kt]);
+            sb_dmma(O[0], O[1], ap[(ZM_KK + kt * 4) * ZM_CS], B[mtx][1][kt]);
+          }
+          if (live) {
+            const double sg = (mtx == 1) ? -1.0 : 1.0;   // d/dz is odd under z -> zDim-1-z
+            double* om = o + (mtx ? (long long)(nfields + mtx - 1) * slotN : 0);
+            *reinterpret_cast<double2*>(om + z0) = make_double2(E[0] + O[0], E[1] + O[1]);
+            *reinterpret_cast<double2*>(om + zDim - 2 - z0) = make_double2(sg * (E[1] - O[1]), sg * (E[0] - O[0]));
+          }
+        }
       }
       // ---- remaining fields: value matrix only
       for (int f = 1; f < nfields; ++f) {
+        if (!((zmask >> f) & 1)) continue;
         const double* af = ap + (size_t)f * 2 * ZM_KK * ZM_CS;
         double E[2] = {0, 0}, O[2] = {0, 0};
 #pragma unroll
@@ -187,7 +207,7 @@ static void launch_inv_z_mma_t(const LaunchCtx& c, const DevGrid& g, const ZTile
   const int cap = 148 * (32 / COLS);
   const int gx = nwork < cap ? nwork : cap;
   SB_LAUNCH((k_inv_z_mma<CB, COLS>), dim3(gx), dim3(COLS * 16), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
-            in_fstride, in_vstride, phys, parB);
+            in_fstride, in_vstride, phys, parB, c.need.zmask, c.need.zsel);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_z_mma launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;

@@ -96,7 +96,12 @@ struct Profiler {
   struct Rec { const char* name; cudaEvent_t a, b; };
   std::vector<Rec> recs;
 };
-struct LaunchCtx { cudaStream_t stream; long long* launches; Profiler* prof; };
+// What a K3 pass has to produce (tiles_physics: only what the equation-set kernel reads; everywhere else: all).
+//   smask: radial spectra  A | dA/dr | d2A/dr2                      (inv_r outputs, bit d)
+//   lmask: ring rows       value | r | rr | lambda | lambda-lambda  (inv_l outputs, bit f)
+//   zmask: fields the Chebyshev synthesis reads (bit f);  zsel: of field 0, bit 0 = value, 1 = d/dz, 2 = d2/dz2
+struct K3Need { unsigned smask = 7, lmask = 31, zmask = 31, zsel = 7; };
+struct LaunchCtx { cudaStream_t stream; long long* launches; Profiler* prof; K3Need need; };
 struct ProfScope {
   cudaStream_t s;
   cudaEvent_t b = nullptr;
@@ -231,6 +236,7 @@ struct ModelArrays {
   const double* helm;     // [2][zDim][zDim] inverse Helmholtz matrices (tau=0.5 ts, 1.25 ts)
   const double* sicols;   // [2 vars (xi,w)][3][zDim][zDim] composite column operators for semi-implicit
 };
+void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* need /*[V]: slots the kernel reads*/);
 void build_colop_fragments(int nz, const double* Mt /*[k][z]*/, std::vector<double>& out);
 void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p,
                          const ModelArrays& a, int tstep);

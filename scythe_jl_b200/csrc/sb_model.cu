@@ -25,6 +25,44 @@ int equation_set_from_name(const char* name) {
   return -1;
 }
 
+// Physical slots each equation-set kernel below READS, per variable (bit d = slot d; slot order R {f,r,rr},
+// RL {f,r,rr,l,ll}, RZ {f,r,rr,z,zz}, RLZ {f,r,rr,l,ll,z,zz}).  tiles_physics hands this to K3 so that rows nobody reads
+// are neither transformed nor written.  0 = the variable is a diagnostic the kernel itself writes (never read).
+// Keep in step with the P(v, d) reads of the kernels: tests/test_gpu_parity.py::test_needed_slots_* runs every
+// equation set with the unread slots poisoned (SB_K3_POISON) against the all-slots path.
+void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* need) {
+  const unsigned all = (1u << g.D) - 1u;
+  for (int v = 0; v < g.V; ++v) need[v] = all;
+  auto set = [&](int v, unsigned m) { if (v < g.V) need[v] = m & all; };
+  const unsigned F = 1u, R = 2u, RR = 4u, S3 = 8u, S4 = 16u, S5 = 32u;   // S3.. = slots 3, 4, 5 of the geometry
+  switch (eq) {
+    case EQ_LinearAdvection1D: set(0, F | R | RR); break;
+    case EQ_LinearShallowWater1D: set(0, F | R); set(1, F | R | RR); break;
+    case EQ_LinearAdvectionRZ:                         // h: r, rr, z, zz ; every other variable: value only
+      for (int v = 1; v < g.V; ++v) set(v, F);
+      break;
+    case EQ_LinearAdvectionRL:
+    case EQ_LinearAdvectionRLZ:                        // h: r, l (+ rr, ll for the diffusion term) ; others: value only
+      set(0, (eq == EQ_LinearAdvectionRL && !(p.K > 0.0)) ? (F | R | S3) : (F | R | RR | S3 | S4));
+      for (int v = 1; v < g.V; ++v) set(v, F);
+      break;
+    case EQ_LinearShallowWaterRL: set(0, F | R | S3); set(1, F | R | RR | S4); set(2, F | R | RR | S3 | S4); break;
+    case EQ_Oneway_ShallowWater_Slab:
+    case EQ_Twoway_ShallowWater_Slab:                  // h, ug, vg: r, l ; ub, vb: all five ; w: written, never read
+      set(0, F | R | S3); set(1, F | R | S3); set(2, F | R | S3);
+      set(3, F | R | RR | S3 | S4); set(4, F | R | RR | S3 | S4); set(5, 0u);
+      break;
+    case EQ_Oneway_ShallowWater_HeightResolvedBL:      // as the slab + d/dz of ub, vb ; wb: written, never read
+      set(0, F | R | S3); set(1, F | R | S3); set(2, F | R | S3);
+      set(3, F | R | RR | S3 | S4 | S5); set(4, F | R | RR | S3 | S4 | S5); set(5, 0u);
+      break;
+    case EQ_Euler_test:                                // RZ: s, mu, u, w all five ; xi: r, z
+      set(1, F | R | S3);
+      break;
+    default: break;
+  }
+}
+
 // explicit_timestep for one value (src/semiimplicit.jl:682-696)
 __device__ __forceinline__ double ab_step(int t, double ts, double u, double fn, double fnm1, double fnm2) {
   if (t == 1) return u + (ts * fn);

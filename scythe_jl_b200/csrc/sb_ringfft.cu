@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(512) k_inv_l_fast(DevGrid g, const LWork* __re
                                                     const RingPlan* __restrict__ plans, const double* __restrict__ blob,
                                                     const double* __restrict__ in, long long in_fs, long long in_vs,
                                                     double* __restrict__ out, long long out_fs, long long out_vs,
-                                                    int out_is_phys, int var0) {
+                                                    int out_is_phys, int var0, unsigned lmask) {
   SB_DYN_SMEM(double2, sm);
   const LWork wk = work[blockIdx.x];
   const int v_ = blockIdx.y;
@@ -199,10 +199,10 @@ __global__ void __launch_bounds__(512) k_inv_l_fast(DevGrid g, const LWork* __re
   const int nseq = 2 * wk.nrows;
   for (int it = 0; it < fc.iters; ++it) {
     const int s = it * fc.nteams + team;
-    const bool active = s < nseq;
     const int row = s >> 1, half = s & 1;
     const int rho = wk.row0 + row;
     const int zb = rho / 5, f = rho - zb * 5;
+    const bool active = s < nseq && ((lmask >> f) & 1);   // rows the equation set does not read are skipped
     double2 v[16];
     if (it > 0) __syncthreads();   // the previous sequence's last pass has finished reading buf
     if (active) {
@@ -405,7 +405,7 @@ void launch_inv_l_fast(const LaunchCtx& c, const DevGrid& g, const LWork* work, 
     if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
   }
   SB_LAUNCH(k_inv_l_fast, dim3(nwork, nvars), dim3(fc.nteams * fc.T), smem, c.stream, g, work, fc, plans, blob, in, in_fs,
-            in_vs, out, out_fs, out_vs, out_is_phys, var0);
+            in_vs, out, out_fs, out_vs, out_is_phys, var0, c.need.lmask);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l_fast launch: ") + cudaGetErrorString(e));
   fcount(c);

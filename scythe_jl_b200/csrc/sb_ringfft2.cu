@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
                                                    const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
                                                    const double* __restrict__ blob, const double* __restrict__ in,
                                                    long long in_fs, long long in_vs, double* __restrict__ out,
-                                                   long long out_fs, long long out_vs, int out_is_phys, int var0) {
+                                                   long long out_fs, long long out_vs, int out_is_phys, int var0,
+                                                   unsigned lmask) {
   typedef RCfg<LOG2L> C;
   constexpr int L = C::L, T = C::T;
   SB_DYN_SMEM(double2, sm);
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
       const int row = s >> 1, half = s & 1;
       const int rho = wk.row0 + row;
       const int zb = rho / 5, f = rho - zb * 5;
+      if (!((lmask >> f) & 1)) continue;   // row not read by the equation set (team-uniform: no barrier is skipped by part of a team)
       double2 v[16];
       team_sync<T>(team);            // the team's previous sequence has finished reading buf
       if (active) {
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(R3Cfg<LOG2L2>::NT, 1) k_inv_l3(DevGrid g, cons
                                                                 const double* __restrict__ blob,
                                                                 const double* __restrict__ in, long long in_fs,
                                                                 long long in_vs, double* __restrict__ out, long long out_fs,
-                                                                long long out_vs, int out_is_phys, int var0) {
+                                                                long long out_vs, int out_is_phys, int var0, unsigned lmask) {
   typedef R3Cfg<LOG2L2> C;
   constexpr int L2 = C::L2, T = C::T;
   SB_DYN_SMEM(double2, sm);
@@ -525,6 +527,7 @@ __global__ void __launch_bounds__(R3Cfg<LOG2L2>::NT, 1) k_inv_l3(DevGrid g, cons
       const int row = s >> 1, half = s & 1;
       const int rho = wk.row0 + row;
       const int zb = rho / 5, f = rho - zb * 5;
+      if (!((lmask >> f) & 1)) continue;   // group-uniform
       group_sync<T>(grp);            // the group's previous outputs have been read out of the buffers
       if (active) {                  // prologue: this team's third of x (see k_inv_l2 for the formula)
         const int fin = (f < 3) ? f : 0;
@@ -719,7 +722,8 @@ static void launch_inv2(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
   const int total = nwork * nvars, gx = total < 148 ? total : 148;
   SB_LAUNCH(k_inv_l2<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
-            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0);
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
+            c.need.lmask);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l2 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;
@@ -804,7 +808,8 @@ static void launch_inv3(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
   const int total = nwork * nvars, gx = total < 148 ? total : 148;
   SB_LAUNCH(k_inv_l3<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEM, c.stream, g, work, nwork, nvars,
-            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0);
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
+            c.need.lmask);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l3 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;

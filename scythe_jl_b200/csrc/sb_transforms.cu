@@ -792,7 +792,7 @@ void launch_fwd_r(const LaunchCtx& c, const DevGrid& g, int nvars, const double*
 // =====================================================================================
 __global__ void __launch_bounds__(RQ) k_inv_r(DevGrid t, DevGrid p, const double* __restrict__ A, long long A_vs,
                                               double* __restrict__ out, long long out_fs, long long out_vs,
-                                              int out_is_phys, int var0) {
+                                              int out_is_phys, int var0, unsigned smask) {
   __shared__ double tile[RQ][33];
   const int tid = threadIdx.x;
   const int q0 = blockIdx.x * RQ, q = q0 + tid;
@@ -825,6 +825,7 @@ __global__ void __launch_bounds__(RQ) k_inv_r(DevGrid t, DevGrid p, const double
         if (valid && q < ncol_r) {
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
+            if (!((smask >> d) & 1)) continue;
             double s = t.phi[d][mu][0] * a0;
             s = fma(t.phi[d][mu][1], a1, s);
             s = fma(t.phi[d][mu][2], a2, s);
@@ -844,7 +845,7 @@ __global__ void __launch_bounds__(RQ) k_inv_r(DevGrid t, DevGrid p, const double
 // through a transposed shared-memory tile, the 9 outputs per cell leave coalesced along the ring.
 __global__ void __launch_bounds__(RQ) k_inv_r2(DevGrid t, DevGrid p, int nvars, const double* __restrict__ A, long long A_vs,
                                                double* __restrict__ out, long long out_fs, long long out_vs,
-                                               int out_is_phys, int var0) {
+                                               int out_is_phys, int var0, unsigned smask) {
   __shared__ double tile[RQ][RM + 5];          // odd row stride: the per-thread column walk is conflict-free
   __shared__ long long s_wo[3 * RM + 1];
   const int tid = threadIdx.x;
@@ -878,6 +879,7 @@ __global__ void __launch_bounds__(RQ) k_inv_r2(DevGrid t, DevGrid p, int nvars, 
       if (q < ncol_r) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
+          if (!((smask >> d) & 1)) continue;
           double s = t.phi[d][mu][0] * a0;
           s = fma(t.phi[d][mu][1], a1, s);
           s = fma(t.phi[d][mu][2], a2, s);
@@ -901,11 +903,11 @@ void launch_inv_r(const LaunchCtx& c, const DevGrid& tile, const DevGrid& patch,
   if (v1) {
     dim3 grid((tile.ncolp + RQ - 1) / RQ, tile.bz, nvars);
     SB_LAUNCH(k_inv_r, grid, dim3(RQ), 0, c.stream, tile, patch, A, A_vstride, out, out_fstride, out_vstride,
-              out_is_phys, var0);
+              out_is_phys, var0, c.need.smask);
   } else {
     dim3 grid((tile.ncolp + RQ - 1) / RQ, (tile.num_cells + RM - 1) / RM, tile.bz * nvars);
     SB_LAUNCH(k_inv_r2, grid, dim3(RQ), 0, c.stream, tile, patch, nvars, A, A_vstride, out, out_fstride, out_vstride,
-              out_is_phys, var0);
+              out_is_phys, var0, c.need.smask);
   }
   SB_CHECK_LAUNCH();
   count(c);

@@ -249,3 +249,20 @@ def check_model(case, lib, **kw):
         errs.append(rel_err(out[:, :, 1], oout[:, :, 1]))   # radial derivative
         m.close()
     return max(errs)
+
+
+def check_needed_slots(case, lib, ntiles=None, **kw):
+    """In-step tileTransform! producing only the slots the equation-set kernel reads (every other slot NaN) must leave
+    exactly the state that producing all D slots leaves (src/semiimplicit.jl:305-314): bit-identical, no NaN."""
+    nt = ntiles or case["tiles"][-1]
+    states = {}
+    for mode in ("all", "needed-poisoned"):
+        m = pkg_model(case, nt, lib, **kw)
+        m.set_k3_slots(mode)
+        m.initialize(case["ic"])
+        m.run(case["n"])
+        states[mode] = [(m.state(i, "var_np1").copy(), m.state(i, "expdot_nm1").copy()) for i in range(nt)]
+        m.close()
+    for (a0, a1), (b0, b1) in zip(states["all"], states["needed-poisoned"]):
+        assert np.isfinite(b0).all() and np.isfinite(b1).all(), "a slot outside the declared mask was read"
+        assert np.array_equal(a0, b0) and np.array_equal(a1, b1), "needed-slots state differs from the all-slots state"

@@ -4,8 +4,8 @@ import numpy as np
 import pytest
 
 import scythe_jl_b200 as S
-from helpers import (STATE_TOL, TRANSFORM_TOL, check_model, check_transforms, model_cases, pkg_model, rel_err,
-                     slot_errs, to_pkg, transform_cases)
+from helpers import (STATE_TOL, TRANSFORM_TOL, check_model, check_needed_slots, check_transforms, model_cases, pkg_model,
+                     rel_err, slot_errs, to_pkg, transform_cases)
 from oracle import grids as G
 from oracle import splines as spl
 
@@ -29,6 +29,32 @@ def test_transforms_match_oracle(name, gpu_lib):
 @pytest.mark.parametrize("name", sorted(M_CASES))
 def test_timestep_matches_oracle(name, gpu_lib):
     assert check_model(M_CASES[name], gpu_lib) <= STATE_TOL
+
+
+@pytest.mark.parametrize("name", sorted(M_CASES))
+def test_needed_slots_state_is_bit_identical(name, gpu_lib):
+    """Every equation set: K3 restricted to the (variable, slot) pairs its kernel reads, all other slots NaN,
+    vs K3 producing all D slots (the reference's dataflow)."""
+    for nt in M_CASES[name]["tiles"]:
+        check_needed_slots(M_CASES[name], gpu_lib, ntiles=nt)
+
+
+@pytest.mark.parametrize("geometry,num_cells,zDim", [("RL", 180, 0), ("RLZ", 40, 16), ("RLZ", 24, 64)])
+def test_needed_slots_large_rings(geometry, num_cells, zDim, gpu_lib):
+    """The same identity on rings long enough for the persistent Bluestein kernels (power-of-two and 3 x 2^a
+    convolution lengths) and the DMMA Chebyshev synthesis, where the row / field masks are applied."""
+    kw = dict(zmin=0, zmax=1e3, zDim=zDim) if zDim else {}
+    gp = G.GridParameters(geometry=geometry, xmin=0, xmax=1e3 * num_cells, num_cells=num_cells, vars={"h": 1, "u": 2, "v": 3}, **kw)
+    pts = G.createGrid(gp).getGridpoints()
+    r, l = pts[:, 0], pts[:, 1]
+    zf = np.cos(pts[:, 2] / 400.0) if zDim else 1.0
+    ic = np.zeros((r.size, 3))
+    ic[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * zf
+    ic[:, 1] = 5 * np.cos(l)
+    ic[:, 2] = -5 * np.sin(l) * zf
+    case = dict(gp=gp, eq="LinearAdvection" + geometry, prm={"K": 100.0}, ts=20.0, n=2, ic=ic, tiles=(1,))
+    check_needed_slots(case, gpu_lib, ntiles=1)
+    check_needed_slots(case, gpu_lib, ntiles=2)
 
 
 def test_cha_bell_rl_config_transforms(gpu_lib):

@@ -4,7 +4,8 @@ This catches indexing / maths errors before GPU time is spent; the GPU parity te
 test_gpu_parity.py.  The emulated library is never reachable from the product package."""
 import pytest
 
-from helpers import STATE_TOL, TRANSFORM_TOL, check_model, check_transforms, model_cases, transform_cases
+from helpers import (STATE_TOL, TRANSFORM_TOL, check_model, check_needed_slots, check_transforms, model_cases,
+                     transform_cases)
 
 T_CASES = transform_cases()
 M_CASES = model_cases()
@@ -25,6 +26,13 @@ def test_timestep_matches_oracle(name, emu_lib):
     case["tiles"] = case["tiles"][-1:]   # the multi-tile variant only (CPU time)
     case["n"] = min(case["n"], 3)
     assert check_model(case, emu_lib) <= STATE_TOL
+
+
+@pytest.mark.parametrize("name", ["LinearShallowWater1D", "LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL_z16"])
+def test_needed_slots_state_is_bit_identical(name, emu_lib):
+    case = dict(M_CASES[name])
+    case["n"] = min(case["n"], 2)
+    check_needed_slots(case, emu_lib)
 
 
 @pytest.mark.parametrize("name,ntiles", [("LinearAdvection1D", 3), ("LinearAdvectionRLZ", 2), ("Euler_test_semiimplicit", 2)])
