@@ -45,9 +45,11 @@ def parse():
                     choices=["LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL"],
                     help="C4 step to time: the transform-dominated linear set (headline) or the 6-variable TC boundary-layer set")
     ap.add_argument("--no-tcbl", action="store_true", help="skip the secondary C4 run of the TC boundary-layer equation set")
-    ap.add_argument("--k3-slots", default="needed", choices=["needed", "all"],
-                    help="slots the in-step tileTransform! produces: what the equation-set kernel reads (product default) or "
-                         "all D slots of every variable (the reference's materialised dataflow); the default run times both")
+    ap.add_argument("--k3-slots", default="fused", choices=["fused", "needed", "all"],
+                    help="slots the in-step tileTransform! produces: what the equation-set kernel reads, with the equation set + "
+                         "AB3 fused into the last transform stage where such a kernel is built (product default); the same slots "
+                         "with separate kernels; or all D slots of every variable (the reference's materialised dataflow).  The "
+                         "default run times the first and the last")
     ap.add_argument("--no-materialised", action="store_true", help="skip the secondary all-slots timing (ncu captures)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -284,7 +286,7 @@ def run_ours(args):
     value = ntiles * 1e3 / ms_step
     # the same step with tileTransform! producing all D slots of every variable (the reference's dataflow)
     mat = None
-    if args.k3_slots == "needed" and not args.no_materialised:
+    if args.k3_slots != "all" and not args.no_materialised:
         m.set_k3_slots("all")
         nmat = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -293,7 +295,7 @@ def run_ours(args):
         mat_ms = timed(m.step, nmat) / nmat
         m.profile(False)
         mat = {"ms_per_step": mat_ms, "value": ntiles * 1e3 / mat_ms, "steps": nmat, "prof": m.profile_report()}
-        m.set_k3_slots("needed")
+        m.set_k3_slots(args.k3_slots)
 
     # transforms/sec (the second half of the BASELINE metric): K1 alone and K2+K3 alone on the tile
     def k1():
@@ -347,9 +349,9 @@ def run_ours(args):
     # (variable, slot) pairs the equation-set kernel reads / variables it reads at all (sb_model.cu: equation_set_needs)
     ns_needed, v_read = (21, 5) if tcbl else (7, 3)
 
-    def tables(prof_, steps_, ns, vr):
+    def tables(prof_, steps_, ns, vr, fused=False):
         """per-K-group time and HBM-roofline fraction on ALGORITHMIC bytes; ns = slots K3 writes and K4
-        reads (all: V*D), vr = variables K3 transforms"""
+        reads (all: V*D), vr = variables K3 transforms; fused: K3's last stage and K4 are one kernel (no slot traffic)"""
         k4_hist = 4 * V + (1 if tcbl else 0)              # K4 kernel: read 2 history arrays, write var_np1 + expdot_n (+ wb)
         groups = {
             "K3 tileTransform! (inv_r+inv_l+inv_z)": (["inv_r", "inv_l", "inv_z"], 8.0 * (vr * Sg + N * ns)),
@@ -357,27 +359,35 @@ def run_ours(args):
             "K2 splineTransform! (spline_solve)": (["spline_solve"], 8.0 * V * 2 * Sp),
             f"K4 equation set + AB3 ({args.equation_set})": (["equation_set"], 8.0 * N * (ns_needed + k4_hist)),
         }
+        if fused:     # read A and 2 history arrays, write var_np1 + expdot_n: nothing else is algorithmically required
+            del groups["K3 tileTransform! (inv_r+inv_l+inv_z)"], groups[f"K4 equation set + AB3 ({args.equation_set})"]
+            groups[f"K3+K4 tileTransform! + {args.equation_set} + AB3 (inv_r+inv_l+inv_z_k4, fused)"] = (
+                ["inv_r", "inv_l", "inv_z_k4"], 8.0 * (vr * Sg + N * k4_hist))
         det = {}
         for name, (ks, nbytes) in groups.items():
             ms = sum(prof_.get(k, {"ms": 0.0})["ms"] for k in ks) / steps_
             det[name] = {"ms_per_step": ms, "algorithmic_GB": nbytes / 1e9,
                          "achieved_GBps": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else None,
                          "frac": ((nbytes / 1e9) / (ms / 1e3) / peak) if ms > 0 else None}
-        # timestep, SURVEY 8(d): K3 (S + N slots) + K4 (N slots + 5N) + K1 (N + S) + K2 (2S); all slots: 8V(2ND + 6N + 4S)
+        # timestep, SURVEY 8(d): K3 (S + N slots) + K4 (N slots + 5N) + K1 (N + S) + K2 (2S); all slots: 8V(2ND + 6N + 4S);
+        # fused minimum: 8V(6N + 4S)
         step_b = 8.0 * ((vr * Sg + N * ns) + N * (ns + 5 * V) + V * (N + Sg) + 2 * V * Sg)
+        if fused:
+            step_b = 8.0 * V * (6 * N + 4 * Sg)
         return det, {k: v["ms"] / steps_ for k, v in prof_.items()}, step_b
 
-    ns_run, vr_run = (ns_needed, v_read) if args.k3_slots == "needed" else (V * D, V)
-    detail, kern_ms, step_bytes = tables(prof, args.steps, ns_run, vr_run)
+    is_fused = args.k3_slots == "fused" and "inv_z_k4" in prof
+    ns_run, vr_run = (V * D, V) if args.k3_slots == "all" else (ns_needed, v_read)
+    detail, kern_ms, step_bytes = tables(prof, args.steps, ns_run, vr_run, is_fused)
     top = max(detail, key=lambda k: detail[k]["ms_per_step"])
     # measured DRAM traffic / FP64-pipe activity of the same step from the committed ncu pass (profiles/), if present
     traffic, ncu_note = None, None
-    prof_name = "r1k_step_kernels_needed.json" if args.k3_slots == "needed" else "r1j_step_kernels.json"
+    prof_name = {"fused": "r1l_step_kernels_fused.json", "needed": "r1k_step_kernels_needed.json"}.get(args.k3_slots, "r1j_step_kernels.json")
     prof_file = ROOT / "profiles" / prof_name
     if prof_file.exists() and world == 1 and cells_tile == C4_CELLS and not tcbl:
         pk = json.loads(prof_file.read_text())["one_step"]
         sel = {"K3": ("k_inv_r", "k_inv_l", "k_inv_z"), "K1": ("k_fwd_z", "k_fwd_l", "k_fwd_r"), "K2": ("k_spline",),
-               "K4": ("k_pointwise",)}[top[:2]]
+               "K4": ("k_pointwise",)}[top[:2]]      # ("K3+K4 ..." starts with K3: k_inv_z matches k_inv_z_advection too)
         rows = [v for k, v in pk.items() if any(s_ in k for s_ in sel)]
         traffic = 1e9 * sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows)
         fft = [v for k, v in pk.items() if "k_inv_l2" in k]
@@ -399,10 +409,15 @@ def run_ours(args):
             "timestep_frac_of_hbm_roofline": (step_bytes / 1e9) / (ms_step / 1e3) / peak,
             "transforms_per_s": {"spectralTransform_K1": 1e3 / k1_ms, "gridTransform_K2K3": 1e3 / k23_ms,
                                  "K1_ms": k1_ms, "K2K3_ms": k23_ms, "vars": V}}
-    line["config"]["k3_slots"] = (
-        f"needed: the in-step tileTransform! produces the {ns_needed} (variable, slot) pairs the {args.equation_set} kernel reads, "
-        f"not all {V * D} (state bit-identical, tests/test_gpu_parity.py::test_needed_slots_*); the all-slots step is timed in "
-        "'materialised'" if args.k3_slots == "needed" else f"all: every one of the {V * D} (variable, slot) pairs is produced")
+    what = {"fused": f"fused: the in-step tileTransform! produces the {ns_needed} (variable, slot) pairs the {args.equation_set} kernel "
+                     f"reads, not all {V * D}" + (", and the equation set + AB3 run in the epilogue of its last stage (no slot is "
+                     "written to HBM)" if is_fused else " (no fused kernel for this equation set: separate K4 kernel)"),
+            "needed": f"needed: the in-step tileTransform! produces the {ns_needed} (variable, slot) pairs the {args.equation_set} "
+                      f"kernel reads, not all {V * D}; separate K4 kernel",
+            "all": f"all: every one of the {V * D} (variable, slot) pairs is produced"}[args.k3_slots]
+    if args.k3_slots != "all":
+        what += "; state bit-identical to the all-slots step (tests/test_gpu_parity.py::test_needed_slots_*), which is timed in 'materialised'"
+    line["config"]["k3_slots"] = what
     if mat:
         mdet, mkern, mbytes = tables(mat["prof"], mat["steps"], V * D, V)
         mtop = max(mdet, key=lambda k: mdet[k]["ms_per_step"])

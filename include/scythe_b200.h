@@ -197,9 +197,11 @@ int sb_model_physics(sb_model_t m, int64_t t);
 /* Which physical slots the tileTransform! inside a step (src/semiimplicit.jl:305) produces.  The derivative slots of a
  * tile are intermediates between tileTransform! and the equation set: nothing else reads them (calcTendency
  * overwrites them right after, src/semiimplicit.jl:731).  mode 0 (default): the (variable, slot) pairs the built-in
- * equation-set kernel reads; 1: all D slots of every variable, the reference's dataflow (env SB_K3_FULL=1 makes it
- * the default); 2: as 0 with every other slot set to NaN first (test hook).  var_np1 is bit-identical in all modes;
- * sb_tile_transform / sb_grid_transform / sb_model_output always produce every slot. */
+ * equation-set kernel reads, and where a fused kernel exists (LinearAdvectionRLZ) the equation set + time step run in
+ * the epilogue of the last transform stage, so no slot is written at all; 1: all D slots of every variable, the
+ * reference's dataflow (env SB_K3_FULL=1 makes it the default); 2: the needed slots with every other slot set to NaN
+ * first (test hook); 3: the needed slots, no fusion.  var_np1 is bit-identical in all modes; sb_tile_transform /
+ * sb_grid_transform / sb_model_output always produce every slot. */
 int sb_model_set_k3_slots(sb_model_t m, int32_t mode);
 /* per-kernel CUDA-event timing on the model's stream: enable/disable, then read
  * "name launches total_ms\n" lines (clears the records). */

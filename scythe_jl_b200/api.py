@@ -797,11 +797,13 @@ class Model:
             self.lib.check(self.lib.sb_model_spline_transform(self.handle))
         self.t = 0
 
-    def set_k3_slots(self, mode: str | int = "needed"):
-        """Slots the in-step tileTransform! produces: "needed" (what the equation-set kernel reads, default),
-        "all" (every slot of every variable, the reference's dataflow, src/semiimplicit.jl:305) or
-        "needed-poisoned" (test hook: every other slot is NaN).  The state is bit-identical in all modes."""
-        modes = {"needed": 0, "all": 1, "needed-poisoned": 2}
+    def set_k3_slots(self, mode: str | int = "fused"):
+        """Slots the in-step tileTransform! produces: "fused" (default: what the equation-set kernel reads, with the
+        equation set + time step fused into the last transform stage where such a kernel is built), "needed" (the
+        same slots, separate kernels), "all" (every slot of every variable, the reference's dataflow,
+        src/semiimplicit.jl:305) or "needed-poisoned" (test hook: every other slot is NaN).  The state is
+        bit-identical in all modes."""
+        modes = {"fused": 0, "all": 1, "needed-poisoned": 2, "needed": 3}
         self.lib.check(self.lib.sb_model_set_k3_slots(self.handle, modes.get(mode, mode)))
 
     def profile(self, on: bool):

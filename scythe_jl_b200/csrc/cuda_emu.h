@@ -149,6 +149,7 @@ static inline void sb_dmma(double& d0, double& d1, double a, double b) {
 // asynchronous global->shared copies (LDGSTS): the emulation copies at once
 static inline void sb_cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
 static inline void sb_cp_async8(void* dst, const void* src) { std::memcpy(dst, src, 8); }
+static inline void sb_prefetch_l2(const void*) {}
 static inline void sb_cp_commit() {}
 template <int N> static inline void sb_cp_wait() {}
 // named barrier for a subset of the block (bar.sync id, nthreads)
@@ -173,6 +174,7 @@ __device__ __forceinline__ void sb_cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void sb_cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void sb_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sb_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void sb_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void sb_bar_sync(int id, int nthreads) {

@@ -135,6 +135,15 @@ struct sb_grid {
     long long sz = (dg.has_l && dg.has_z) ? 5LL * dg.bz * dg.hpoints : 0;
     return (dg.has_l || dg.has_z) ? sl + sz : 0;
   }
+  void ensure_scratch_doubles(long long n) {   // fused K3+K4 keeps the rows of all variables at once
+    ensure_scratch();
+    if (scratch_doubles >= n) return;
+    CU(cudaStreamSynchronize(stream));
+    cudaFree(scratch);
+    scratch = nullptr;
+    scratch_doubles = n;
+    CU(cudaMalloc((void**)&scratch, (size_t)scratch_doubles * sizeof(double)));
+  }
   void ensure_scratch() {
     if (scratch) return;
     long long per_v = std::max(fwd_need(), inv_need());
@@ -672,7 +681,8 @@ struct sb_model {
   double ts = 0, integration_time = 0, output_interval = 0;
   int eq = -1;
   int semiimplicit = 0;
-  int k3_slots = 0;   // sb_model_set_k3_slots: 0 = what the equation set reads, 1 = all D slots, 2 = 0 + unread slots poisoned
+  int k3_slots = 0;   // sb_model_set_k3_slots: 0 = what the equation set reads (+ K4 fused where built), 1 = all D slots,
+                      // 2 = needed slots, the others poisoned, 3 = needed slots (no fusion)
   EqParams ep{};
   int ntiles = 1, tile_first = 0, tile_count = 1;
   std::vector<double> tile_params;
@@ -928,6 +938,35 @@ static void model_initialize(sb_model* M, const double* ic_host) {
   if ((size_t)P->dg.N * P->dg.V * P->dg.D * sizeof(double) > ((size_t)4 << 30)) P->release_physical();
 }
 
+// LinearAdvectionRLZ: inv_r + inv_l of the seven rows the equation reads (h: value, r, rr, l, ll; u, v: value), then the
+// Chebyshev synthesis with the tendency and the AB3 step in its epilogue (k_inv_z_advection).  `physical` is not touched.
+static bool fused_advection_ok(const sb_model* M, const sb_grid* G) {
+  static const bool off = std::getenv("SB_FUSE_K4") != nullptr && std::atoi(std::getenv("SB_FUSE_K4")) == 0;   // A/B switch
+  if (off || M->eq != EQ_LinearAdvectionRLZ || !inv_z_advection_ok(G->dg)) return false;
+  for (int v = 0; v < G->dg.V; ++v)
+    if (!G->z_bcfree[v]) return false;        // vertical BCs: the parity split does not hold
+  return true;
+}
+static void grid_inverse_advection_fused(sb_grid* P, sb_grid* T, const EqParams& ep, const ModelArrays& a, int tq) {
+  DevGrid& t = T->dg;
+  DevGrid& p = P->dg;
+  const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
+  const long long sz_off = (3 * slN + 15) & ~15LL;
+  T->ensure_scratch_doubles(sz_off + 7 * szN + 16);
+  double* SL = T->scratch;                  // [3][slN]   one variable at a time
+  double* SZ = T->scratch + sz_off;         // [7][szN]   h: 5 rows | u | v
+  T->slot0_src = nullptr;                   // the state the step starts from is synthesised in registers
+  LaunchCtx c = T->ctx();
+  const unsigned slots[3] = {31u, 1u, 1u};
+  for (int v = 0; v < 3; ++v) {
+    c.need = k3_need_from_slots(t, slots[v]);
+    launch_inv_r(c, t, p, 1, P->spectralA + (long long)v * p.S, p.S, SL, slN, slN, 0, v);
+    launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, 1, SL, slN,
+                 slN, SZ + (v ? (4 + v) * szN : 0), szN, szN, 0, v, &T->iwork2, T->d_iwork2.data());
+  }
+  launch_inv_z_advection(c, t, T->d_ztiles, T->nztiles, SZ, szN, T->d_parB, ep, a, tq);
+}
+
 // first half of advanceTimestep: tileTransform! + equation set + explicit/semi-implicit step
 static void tiles_physics(sb_model* M, int64_t t) {
   sb_grid* P = M->patch;
@@ -937,13 +976,19 @@ static void tiles_physics(sb_model* M, int64_t t) {
   equation_set_needs(M->eq, M->ep, P->dg, need.data());
   for (auto& T : M->tiles) {
     sb_grid* G = T.grid;
-    grid_inverse(M->cs.on ? G : P, G, M->k3_slots == 1 ? nullptr : need.data(), M->k3_slots == 2);   // tileTransform!  :305 (plane-distributed solve: A arrives tile-local)
     ModelArrays a{};
-    a.phys = G->physical; a.var_np1 = T.var_np1;
+    a.var_np1 = T.var_np1;
     a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
     a.imp_n = T.impd[0]; a.imp_nm1 = T.impd[1]; a.imp_nm2 = T.impd[2];
     a.colops = M->d_colops; a.colfrag = M->d_colfrag; a.refstate = M->d_refstate; a.sicols = M->d_sicols;
-    launch_equation_set(G->ctx(), M->eq, G->dg, M->ep, a, (int)std::min<int64_t>(t, 3));  // :308-314
+    const int tq = (int)std::min<int64_t>(t, 3);
+    if (M->k3_slots == 0 && fused_advection_ok(M, G)) {   // K3's last stage and K4 in one kernel: no slot reaches HBM
+      grid_inverse_advection_fused(M->cs.on ? G : P, G, M->ep, a, tq);
+    } else {
+      grid_inverse(M->cs.on ? G : P, G, M->k3_slots == 1 ? nullptr : need.data(), M->k3_slots == 2);   // tileTransform!  :305 (plane-distributed solve: A arrives tile-local)
+      a.phys = G->physical;
+      launch_equation_set(G->ctx(), M->eq, G->dg, M->ep, a, tq);  // :308-314
+    }
     // history rotation (:685-695): nm2 <- nm1 <- n ; the old nm2 buffer becomes next step's n
     std::rotate(T.expd, T.expd + 2, T.expd + 3);
     if (M->semiimplicit) std::rotate(T.impd, T.impd + 2, T.impd + 3);
@@ -1572,7 +1617,7 @@ int sb_model_cycle(sb_model_t m, int64_t t) {
 int sb_model_set_k3_slots(sb_model_t m, int32_t mode) {
   return guarded([&] {
     if (!m) throw std::invalid_argument("NULL model");
-    if (mode < 0 || mode > 2) throw std::invalid_argument("k3 slot mode must be 0 (needed), 1 (all) or 2 (needed, rest poisoned)");
+    if (mode < 0 || mode > 3) throw std::invalid_argument("k3 slot mode must be 0 (fused/needed), 1 (all), 2 (needed, rest poisoned) or 3 (needed)");
     m->k3_slots = mode;
   });
 }

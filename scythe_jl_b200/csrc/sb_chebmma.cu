@@ -15,6 +15,7 @@
 // whole kernel; A fragments come from a [mode][column] smem tile whose stride (40) makes both the
 // transposing stores and the fragment loads bank-conflict-free.
 #include "sb_internal.hpp"
+#include "sb_eqcore.hpp"
 
 #include <cstdint>
 #include <cstdlib>
@@ -230,6 +231,159 @@ void launch_inv_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
     if (al16) launch_inv_z_mma_t<16, 16>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
     else launch_inv_z_mma_t<8, 16>(c, g, tiles, ntiles, nvars, var0, nfields, in, in_fstride, in_vstride, phys, parB);
   }
+}
+
+// =====================================================================================
+// K3's last stage + K4 in one kernel for LinearAdvectionRLZ (src/testModels.jl:75-98): the Chebyshev
+// synthesis of the seven rows the equation reads -- h: value, r, rr, lambda, lambda-lambda; u, v: value -- stays in
+// registers, the tendency and the Euler/AB2/AB3 step (src/semiimplicit.jl:672-698) run on it, and only var_np1 and
+// expdot_n are written: the derivative slots never exist in HBM.  Same DMMA order and the same tendency / AB3
+// expressions (sb_eqcore.hpp) as k_inv_z_mma + k_pointwise, so the state is bit-identical to the two-kernel path.
+// in: [ZF_NF field rows][bz][ring rows] (SZ layout), field row s = 0..4: h fields, 5: u, 6: v.
+// 16-column tiles, 256 threads (4 level tiles x 2 column groups at 64 levels), two CTAs per SM, cp.async double buffer.
+// =====================================================================================
+#define ZF_NF 7
+template <int CB>
+__global__ void __launch_bounds__(256, 2) k_inv_z_advection(DevGrid g, const ZTile* __restrict__ tiles, int ntiles,
+                                                            const double* __restrict__ in, long long in_fs,
+                                                            const double* __restrict__ parB, EqParams p, ModelArrays arr, int t) {
+  SB_DYN_SMEM(double, a);       // [2 buffers][ZF_NF][2 parities][ZM_KK][ZM_CS]
+  constexpr int COLS = 16, ZM_CS = COLS + 4, ZM_THREADS = COLS * 16, SPLIT = 32 / COLS;
+  const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = (ZM_THREADS / 32) / nzt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane & 3, i = lane >> 2;
+  const int zt = warp % nzt, cg = warp / nzt;
+  constexpr int bufsz = ZF_NF * 2 * ZM_KK * ZM_CS;
+  double B[2][ZM_KT];           // value matrix only
+#pragma unroll
+  for (int par = 0; par < 2; ++par)
+#pragma unroll
+    for (int kt = 0; kt < ZM_KT; ++kt) B[par][kt] = parB[(((par * ZM_KT + kt) * 4) + zt) * 32 + lane];
+  for (int j = tid; j < 2 * bufsz; j += ZM_THREADS) a[j] = 0.0;   // zero padding (modes >= bz) stays zero
+  __syncthreads();
+  const int z0 = zt * 8 + 2 * q;                 // this lane's pair of levels (z0, z0+1) and mirror (zDim-2-z0, +1)
+  const int nwork = ntiles * SPLIT;
+  constexpr int CPR = COLS * 8 / CB, CE = CB / 8;
+  int4* rowtab = reinterpret_cast<int4*>(a + 2 * bufsz);
+  const int nrow = ZF_NF * bz;
+  for (int r = tid; r < nrow; r += ZM_THREADS) {
+    const int f = r / bz, zb = r - f * bz;
+    rowtab[r] = make_int4(f, zb, ((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS, 0);
+  }
+  __syncthreads();
+  auto desc = [&](int w) {       // COLS-column sub-tile of a 32-column ZTile
+    ZTile tl = tiles[w / SPLIT];
+    const int off = (w % SPLIT) * COLS;
+    tl.hcol0 += off; tl.out_base += off;
+    tl.ncols = tl.ncols - off < COLS ? tl.ncols - off : COLS;   // may be <= 0: empty sub-tile
+    return tl;
+  };
+  auto issue = [&](const ZTile& ztile, double* dst) {
+    const double* src = in + ztile.out_base;
+    const int total = nrow * CPR;
+    for (int c = tid; c < total; c += ZM_THREADS) {
+      const int row = c / CPR, col = (c - row * CPR) * CE;
+      const int4 rt = rowtab[row];
+      if (col < ztile.ncols) {
+        const double* sp = src + (long long)rt.x * in_fs + (long long)rt.y * ztile.out_stride + col;
+        double* dp = dst + rt.z + col;
+        if (CB == 16) sb_cp_async16(dp, sp); else sb_cp_async8(dp, sp);
+      }
+    }
+    sb_cp_commit();
+  };
+  const long long N = g.N;
+  const double ts = p.ts, K = p.K;
+  const int G = gridDim.x;
+  int w = blockIdx.x, cur = 0;
+  ZTile zt0 = desc(w < nwork ? w : 0), zt1;
+  if (w < nwork) issue(zt0, a);
+  for (; w < nwork; w += G) {
+    zt1 = desc(w + G < nwork ? w + G : w);
+    sb_cp_wait<0>();
+    __syncthreads();            // tile w has landed; everybody is done with the other buffer
+    if (w + G < nwork) issue(zt1, a + (cur ^ 1) * bufsz);
+    const ZTile ztile = zt0;
+    zt0 = zt1;
+    const double* ab = a + cur * bufsz;
+    const double r = ztile.ncols > 0 ? g.rad[g.h2r[ztile.hcol0]] : 1.0;   // a ZTile lies inside one ring
+    for (int ct = cg; ct < COLS / 8; ct += ncg) {
+      const int c = ct * 8 + i;
+      const bool live = c < ztile.ncols;
+      const double* ap = ab + q * ZM_CS + c;
+      // f[s][0..3]: field row s at levels z0, z0+1, zDim-2-z0, zDim-1-z0
+      double f[ZF_NF][4];
+#pragma unroll
+      for (int s = 0; s < ZF_NF; ++s) {
+        const double* af = ap + (size_t)s * 2 * ZM_KK * ZM_CS;
+        double E[2] = {0, 0}, O[2] = {0, 0};
+#pragma unroll
+        for (int kt = 0; kt < ZM_KT; ++kt) {
+          sb_dmma(E[0], E[1], af[(kt * 4) * ZM_CS], B[0][kt]);
+          sb_dmma(O[0], O[1], af[(ZM_KK + kt * 4) * ZM_CS], B[1][kt]);
+        }
+        f[s][0] = E[0] + O[0]; f[s][1] = E[1] + O[1]; f[s][2] = E[1] - O[1]; f[s][3] = E[0] - O[0];
+      }
+      if (live) {
+        const long long col0 = ((long long)ztile.hcol0 + c) * zDim;
+#pragma unroll
+        for (int hm = 0; hm < 2; ++hm) {          // the level pair and its mirror pair
+          const long long o0 = col0 + (hm ? zDim - 2 - z0 : z0);
+          // the six history loads of this pair first (the stores below may alias them as far as the compiler knows, so
+          // it would otherwise serialise load -> use -> store per variable and pay the memory latency each time)
+          double2 h1[3], h2[3];
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            h1[v] = t >= 2 ? *reinterpret_cast<const double2*>(arr.exp_nm1 + (long long)v * N + o0) : make_double2(0.0, 0.0);
+            h2[v] = t >= 3 ? *reinterpret_cast<const double2*>(arr.exp_nm2 + (long long)v * N + o0) : make_double2(0.0, 0.0);
+          }
+          double e[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int x = 2 * hm + k;
+            e[k] = advection_rl_tendency(f[5][x], f[6][x], f[1][x], f[3][x], f[2][x], f[4][x], r, K);
+          }
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            const long long o = (long long)v * N + o0;
+            const int s = v == 0 ? 0 : 4 + v;
+            const double2 f1 = h1[v], f2 = h2[v];
+            const double fn0 = v == 0 ? e[0] : 0.0, fn1 = v == 0 ? e[1] : 0.0;
+            *reinterpret_cast<double2*>(arr.exp_n + o) = make_double2(fn0, fn1);
+            *reinterpret_cast<double2*>(arr.var_np1 + o) =
+                make_double2(ab_step(t, ts, f[s][2 * hm], fn0, f1.x, f2.x), ab_step(t, ts, f[s][2 * hm + 1], fn1, f1.y, f2.y));
+          }
+        }
+      }
+    }
+    cur ^= 1;
+  }
+}
+
+bool inv_z_advection_ok(const DevGrid& g) {
+  return g.has_l && g.has_z && g.V == 3 && (g.zDim == 16 || g.zDim == 32 || g.zDim == 64) && g.bz <= 2 * ZM_KK && g.N % 2 == 0;
+}
+
+void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, const double* in,
+                            long long in_fstride, const double* parB, const EqParams& p, const ModelArrays& arr, int t) {
+  ProfScope prof_scope_(c, "inv_z_k4");
+  const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0;
+  const size_t smem = (size_t)2 * ZF_NF * 2 * ZM_KK * (16 + 4) * sizeof(double) + (size_t)ZF_NF * g.bz * 16;
+  const int nwork = ntiles * 2;
+  const int gx = nwork < 148 * 2 ? nwork : 148 * 2;
+  cudaError_t e;
+  if (al16) {
+    e = cudaFuncSetAttribute(k_inv_z_advection<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+    SB_LAUNCH((k_inv_z_advection<16>), dim3(gx), dim3(256), smem, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
+  } else {
+    e = cudaFuncSetAttribute(k_inv_z_advection<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+    SB_LAUNCH((k_inv_z_advection<8>), dim3(gx), dim3(256), smem, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_z_advection launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
 }
 
 // =====================================================================================

@@ -238,6 +238,10 @@ struct ModelArrays {
 };
 void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* need /*[V]: slots the kernel reads*/);
 void build_colop_fragments(int nz, const double* Mt /*[k][z]*/, std::vector<double>& out);
+// K3 last stage + K4 fused for LinearAdvectionRLZ (sb_chebmma.cu): in = [7 field rows: h value,r,rr,l,ll | u | v][bz][ring rows]
+bool inv_z_advection_ok(const DevGrid& g);
+void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, const double* in,
+                            long long in_fstride, const double* parB, const EqParams& p, const ModelArrays& arr, int t);
 void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p,
                          const ModelArrays& a, int tstep);
 

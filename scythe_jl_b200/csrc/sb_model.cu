@@ -6,6 +6,7 @@
 // One pass over the point reads the derivative slots it needs and the two history arrays and
 // writes var_np1 and expdot_n; the history rotation (:689-695) is a pointer rotation on the host.
 #include "sb_internal.hpp"
+#include "sb_eqcore.hpp"
 
 #include <cmath>
 #include <cstdlib>
@@ -63,12 +64,6 @@ void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* n
   }
 }
 
-// explicit_timestep for one value (src/semiimplicit.jl:682-696)
-__device__ __forceinline__ double ab_step(int t, double ts, double u, double fn, double fnm1, double fnm2) {
-  if (t == 1) return u + (ts * fn);
-  if (t == 2) return u + (0.5 * ts) * ((3.0 * fn) - fnm1);
-  return u + ((ts / 12.0) * ((23.0 * fn) - (16.0 * fnm1) + (5.0 * fnm2)));
-}
 
 struct PointCtx {
   const DevGrid& g;
@@ -150,7 +145,7 @@ __global__ void __launch_bounds__(256) k_pointwise(DevGrid g, EqParams p, ModelA
       e = (-u * hr) - (v * (hl / r));
     } else {
       double hrr = c.P(0, 2), hll = c.P(0, 4);
-      e = (-u * hr) - (v * (hl / r)) + (p.K * ((hr / r) + hrr + (hll / (r * r))));
+      e = advection_rl_tendency(u, v, hr, hl, hrr, hll, r, p.K);
     }
     c.advance(0, t, ts, c.P(0, 0), e);
     c.advance(1, t, ts, u, 0.0);

@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restric
                                                const double2* __restrict__ tw, const RingPlan* __restrict__ plans,
                                                const double* __restrict__ blob, const double* __restrict__ in,
                                                long long in_fs, long long in_vs, double* __restrict__ out,
-                                               long long out_fs, long long out_vs, int out_is_phys, int var0) {
+                                               long long out_fs, long long out_vs, int out_is_phys, int var0,
+                                               unsigned lmask) {
   SB_DYN_SMEM(double2, buf);
   const LWork wk = work[blockIdx.x];
   const int v = blockIdx.y;
@@ -604,6 +605,7 @@ __global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restric
     int row = i / m, a = i - row * m;
     const int rho = wk.row0 + row;
     const int zb = rho / 5, f = rho - zb * 5;
+    if (!((lmask >> f) & 1)) continue;     // row nobody reads: not stored (its destination may not exist)
     const double2* b0 = buf + ((size_t)(2 * row) << log2L);
     const double2* b1 = b0 + L;
     const double2 c = chirp[a];
@@ -650,7 +652,7 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
     SB_LAUNCH(k_inv_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci], classes[ci].log2L,
               reinterpret_cast<const double2*>(tw[ci]), plans, blob, in, in_fstride, in_vstride, out, out_fstride,
-              out_vstride, out_is_phys, var0);
+              out_vstride, out_is_phys, var0, c.need.lmask);
     SB_CHECK_LAUNCH();
     count(c);
   }

@@ -154,6 +154,16 @@ def model_cases(small=True):
     ic[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
     ic[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
     cases["LinearAdvectionRLZ"] = dict(gp=gp, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=3, ic=ic, tiles=(1, 2))
+    # 16 levels, no vertical BCs: the fused synthesis + tendency + AB3 kernel (k_inv_z_advection)
+    gpf = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=6, zmin=0, zmax=1e3, zDim=16,
+                           vars={"h": 1, "u": 2, "v": 3})
+    r, l, z = G.createGrid(gpf).getGridpoints().T
+    icf = np.zeros((r.size, 3))
+    icf[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * np.cos(z / 400.0)
+    icf[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
+    icf[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
+    cases["LinearAdvectionRLZ_z16_fused"] = dict(gp=gpf, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=4, ic=icf,
+                                                 tiles=(1, 2))
     gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e5, num_cells=12, zmin=0, zmax=1e4, zDim=12,
                           vars={"h": 1, "u": 2, "x": 3, "w": 4})
     r, z = G.createGrid(gp).getGridpoints().T
@@ -256,13 +266,16 @@ def check_needed_slots(case, lib, ntiles=None, **kw):
     exactly the state that producing all D slots leaves (src/semiimplicit.jl:305-314): bit-identical, no NaN."""
     nt = ntiles or case["tiles"][-1]
     states = {}
-    for mode in ("all", "needed-poisoned"):
+    for mode in ("all", "needed-poisoned", "fused"):
         m = pkg_model(case, nt, lib, **kw)
         m.set_k3_slots(mode)
         m.initialize(case["ic"])
         m.run(case["n"])
         states[mode] = [(m.state(i, "var_np1").copy(), m.state(i, "expdot_nm1").copy()) for i in range(nt)]
         m.close()
-    for (a0, a1), (b0, b1) in zip(states["all"], states["needed-poisoned"]):
+    for (a0, a1), (b0, b1), (c0, c1) in zip(states["all"], states["needed-poisoned"], states["fused"]):
         assert np.isfinite(b0).all() and np.isfinite(b1).all(), "a slot outside the declared mask was read"
         assert np.array_equal(a0, b0) and np.array_equal(a1, b1), "needed-slots state differs from the all-slots state"
+        assert np.array_equal(a0, c0) and np.array_equal(a1, c1), (
+            f"fused K3+K4 state differs from the all-slots state: max |d var_np1| {np.abs(a0 - c0).max():.3e} of "
+            f"{np.abs(a0).max():.3e}, max |d expdot| {np.abs(a1 - c1).max():.3e} of {np.abs(a1).max():.3e}")
