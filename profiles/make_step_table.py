@@ -18,7 +18,7 @@ import re
 import sys
 from collections import OrderedDict
 
-EQ_KERNELS = ("k_pointwise", "k_heightresolved_bl", "k_euler_test")
+EQ_KERNELS = ("k_pointwise", "k_heightresolved_bl", "k_euler_test", "k_inv_z_advection")
 
 
 def short(name: str) -> str:

@@ -24,7 +24,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = _lib.load()
     outs = {}
-    for name in ("LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL"):
+    for name in ("LinearAdvectionRLZ", "LinearAdvectionRLZ_z16_fused", "Oneway_ShallowWater_HeightResolvedBL"):
         case = dict(model_cases()[name])
         case["n"] = 3
         ntiles = world
@@ -50,6 +50,16 @@ def main():
                 assert same
                 m.close()
                 dist.barrier()
+        # the default in-step tileTransform! (needed slots / fused K4) against the all-slots dataflow, tile by tile
+        m = pkg_model(case, ntiles, lib, distributed=True, exchange="columns-p2p", device=local)
+        m.set_k3_slots("all")
+        m.initialize_tiles(ics)
+        m.run(case["n"])
+        same = np.array_equal(m.state(0, "var_np1"), outs[(name, "columns-p2p")])
+        print(f"rank {rank} {name}: needed/fused slots == all slots: {same}", flush=True)
+        assert same
+        m.close()
+        dist.barrier()
         ref = outs[(name, "torch")]
         for ex in ("columns", "columns-native", "columns-p2p", "columns-p2p-native"):
             same = np.array_equal(outs[(name, ex)], ref)

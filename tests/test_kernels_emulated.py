@@ -31,7 +31,7 @@ def test_timestep_matches_oracle(name, emu_lib):
 @pytest.mark.parametrize("name", ["LinearShallowWater1D", "LinearAdvectionRLZ_z16_fused", "Oneway_ShallowWater_HeightResolvedBL_z16"])
 def test_needed_slots_state_is_bit_identical(name, emu_lib):
     case = dict(M_CASES[name])
-    case["n"] = min(case["n"], 3)
+    case["n"] = 2
     check_needed_slots(case, emu_lib)
 
 
