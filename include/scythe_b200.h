@@ -191,6 +191,19 @@ int sb_model_tendency(sb_model_t m);
  * then :305-314 of the next iteration): var_np1 -> K1 -> shared sum -> K2 -> K3 -> equation set ->
  * var_np1.  Same work as sb_model_step; used for host-buffer (end-to-end) stepping. */
 int sb_model_cycle(sb_model_t m, int64_t t);
+/* Host-driven stepping without stalls: asynchronous, pipelined forms of sb_model_set_state(which = 0) and
+ * sb_model_get_state(which = 0) for a caller whose state lives in HOST memory between steps (the reference's workers
+ * own `var_np1` as Julia host arrays, src/semiimplicit.jl:18-42).  stage_in: host [N_tile,V] -> a device staging buffer
+ * on a copy stream, then into var_np1 on the compute stream; stage_out: var_np1 -> a staging buffer on the compute
+ * stream, then to host [N_tile,V] on a second copy stream.  Two staging buffers each way, ordered by events only, so the
+ * H2D copy of step i+1, the kernels of step i and the D2H copy of step i-1 overlap (PCIe is full duplex).  The calls
+ * return at once: `host` must be page-locked for the copies to be asynchronous and must stay valid (stage_in:
+ * unmodified; stage_out: unread) until sb_model_stage_drain(m, 1) or sb_model_sync(m) returns.
+ * sb_model_stage_drain makes the compute stream wait for every staged copy issued so far (block = 0: stream-ordered
+ * only, so that a following sb_timer_stop covers them; block = 1: also waits on the host). */
+int sb_model_stage_in(sb_model_t m, int32_t tile, const double* host);
+int sb_model_stage_out(sb_model_t m, int32_t tile, double* host);
+int sb_model_stage_drain(sb_model_t m, int32_t block);
 /* the first half of advanceTimestep alone (src/semiimplicit.jl:305-314): tileTransform! + equation set + time step.
  * sb_model_tendency + caller-driven exchange + sb_model_physics = sb_model_cycle when the exchange is the caller's. */
 int sb_model_physics(sb_model_t m, int64_t t);

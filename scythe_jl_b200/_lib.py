@@ -86,6 +86,9 @@ PROTOTYPES = {
     "sb_model_output": (C.c_int, [model_t, c_f64p]),
     "sb_model_get_state": (C.c_int, [model_t, C.c_int32, C.c_int32, c_f64p]),
     "sb_model_set_state": (C.c_int, [model_t, C.c_int32, C.c_int32, c_f64p]),
+    "sb_model_stage_in": (C.c_int, [model_t, C.c_int32, c_f64p]),
+    "sb_model_stage_out": (C.c_int, [model_t, C.c_int32, c_f64p]),
+    "sb_model_stage_drain": (C.c_int, [model_t, C.c_int32]),
     "sb_model_tendency": (C.c_int, [model_t]),
     "sb_model_cycle": (C.c_int, [model_t, C.c_int64]),
     "sb_model_physics": (C.c_int, [model_t, C.c_int64]),

@@ -753,6 +753,36 @@ class Model:
     def get_state_into(self, tile: int, out: np.ndarray):
         self.lib.check(self.lib.sb_model_get_state(self.handle, tile, 0, _ptr(out)))
 
+    # -- host-driven stepping, pipelined (sb_model_stage_*) ---------------------------------
+    def stage_in(self, tile: int, var_np1: np.ndarray):
+        """Asynchronous set_state: host [N_tile, V] (Fortran order, float64, ideally page-locked) -> var_np1 through a
+        copy stream.  The array must stay alive and unmodified until :meth:`drain`."""
+        g = self.tiles[tile]
+        if not (var_np1.flags.f_contiguous and var_np1.dtype == np.float64 and var_np1.size == g.N * g.V):
+            raise ValueError("stage_in needs a Fortran-contiguous float64 [N_tile, V] array (no hidden copy: the transfer is asynchronous)")
+        self.lib.check(self.lib.sb_model_stage_in(self.handle, tile, _ptr(var_np1)))
+
+    def stage_out(self, tile: int, out: np.ndarray):
+        """Asynchronous get_state: var_np1 -> host ``out`` [N_tile, V]; valid after :meth:`drain`."""
+        g = self.tiles[tile]
+        if not (out.flags.f_contiguous and out.flags.writeable and out.dtype == np.float64 and out.size == g.N * g.V):
+            raise ValueError("stage_out needs a writable Fortran-contiguous float64 [N_tile, V] array")
+        self.lib.check(self.lib.sb_model_stage_out(self.handle, tile, _ptr(out)))
+
+    def drain(self, block: bool = True):
+        """Compute stream waits for every staged copy; with ``block`` the host waits too."""
+        self.lib.check(self.lib.sb_model_stage_drain(self.handle, int(block)))
+
+    def cycle_host(self, tile_in, tile_out):
+        """One model_loop iteration with the state in HOST memory on both sides: every local tile's var_np1 comes from
+        ``tile_in[i]`` and the stepped state goes to ``tile_out[i]``.  Returns at once; successive calls overlap their
+        copies with each other's kernels.  Results are valid after :meth:`drain`."""
+        for i, a in enumerate(tile_in):
+            self.stage_in(i, a)
+        self.cycle()
+        for i, a in enumerate(tile_out):
+            self.stage_out(i, a)
+
     def _exchange(self):
         if self.dist is None or self.world == 1:
             return

@@ -123,6 +123,10 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+enum { cudaStreamNonBlocking = 1 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }   // everything runs at once
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)1 << 40; return 0; }

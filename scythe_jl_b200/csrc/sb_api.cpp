@@ -666,11 +666,26 @@ struct CommError : std::runtime_error { using std::runtime_error::runtime_error;
   } while (0)
 
 // ====================================================================================== model
+// Host-driven stepping without stalls (sb_model_stage_in / sb_model_stage_out): two device staging buffers each way and
+// two copy streams, so that the H2D copy of step i+1's state, the kernels of step i and the D2H copy of step i-1's
+// result overlap (PCIe is full duplex).  All ordering is by events; the host never blocks.
+struct HostPipe {
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  double* in[2] = {nullptr, nullptr};
+  double* out[2] = {nullptr, nullptr};
+  cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
+  cudaEvent_t out_ready[2] = {nullptr, nullptr}, out_free[2] = {nullptr, nullptr};
+  bool in_used[2] = {false, false}, out_used[2] = {false, false};
+  int ki = 0, ko = 0;
+  bool on = false;
+};
+
 struct TileState {
   sb_grid* grid = nullptr;
   double* var_np1 = nullptr;
   double* expd[3] = {nullptr, nullptr, nullptr};  // n, nm1, nm2 (rotating)
   double* impd[3] = {nullptr, nullptr, nullptr};
+  HostPipe pipe;
 };
 
 struct sb_model {
@@ -916,6 +931,15 @@ static void model_free(sb_model* M) {
   for (void* p : M->cs.ipc_opened) cudaIpcCloseMemHandle(p);
 #endif
   for (auto& t : M->tiles) {
+    if (t.pipe.on) {
+      cudaStreamSynchronize(t.pipe.s_in); cudaStreamSynchronize(t.pipe.s_out);
+      for (int k = 0; k < 2; ++k) {
+        cudaFree(t.pipe.in[k]); cudaFree(t.pipe.out[k]);
+        cudaEventDestroy(t.pipe.in_ready[k]); cudaEventDestroy(t.pipe.in_free[k]);
+        cudaEventDestroy(t.pipe.out_ready[k]); cudaEventDestroy(t.pipe.out_free[k]);
+      }
+      cudaStreamDestroy(t.pipe.s_in); cudaStreamDestroy(t.pipe.s_out);
+    }
     grid_free(t.grid);
     cudaFree(t.var_np1);
     for (int k = 0; k < 3; ++k) { cudaFree(t.expd[k]); cudaFree(t.impd[k]); }
@@ -1597,6 +1621,71 @@ int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* 
     CU(cudaStreamSynchronize(m->stream));
   });
 }
+static void pipe_open(sb_model* m, TileState& T) {
+  HostPipe& p = T.pipe;
+  if (p.on) return;
+  const size_t bytes = (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double);
+  CU(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));    // non-blocking: the compute stream may be the legacy
+  CU(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));   // default stream, which would serialise blocking streams
+  for (int k = 0; k < 2; ++k) {
+    CU(cudaMalloc((void**)&p.in[k], bytes));
+    CU(cudaMalloc((void**)&p.out[k], bytes));
+    CU(cudaEventCreate(&p.in_ready[k])); CU(cudaEventCreate(&p.in_free[k]));
+    CU(cudaEventCreate(&p.out_ready[k])); CU(cudaEventCreate(&p.out_free[k]));
+  }
+  (void)m;
+  p.on = true;
+}
+int sb_model_stage_in(sb_model_t m, int32_t tile, const double* host) {
+  return guarded([&] {
+    if (!m || !host || tile < 0 || tile >= (int)m->tiles.size()) throw std::invalid_argument("bad argument");
+    TileState& T = m->tiles[tile];
+    pipe_open(m, T);
+    HostPipe& p = T.pipe;
+    const int k = p.ki;
+    const size_t bytes = (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double);
+    if (p.in_used[k]) CU(cudaStreamWaitEvent(p.s_in, p.in_free[k], 0));    // the step two back has consumed this buffer
+    CU(cudaMemcpyAsync(p.in[k], host, bytes, cudaMemcpyHostToDevice, p.s_in));
+    CU(cudaEventRecord(p.in_ready[k], p.s_in));
+    CU(cudaStreamWaitEvent(m->stream, p.in_ready[k], 0));
+    CU(cudaMemcpyAsync(T.var_np1, p.in[k], bytes, cudaMemcpyDeviceToDevice, m->stream));
+    CU(cudaEventRecord(p.in_free[k], m->stream));
+    p.in_used[k] = true;
+    p.ki ^= 1;
+  });
+}
+int sb_model_stage_out(sb_model_t m, int32_t tile, double* host) {
+  return guarded([&] {
+    if (!m || !host || tile < 0 || tile >= (int)m->tiles.size()) throw std::invalid_argument("bad argument");
+    TileState& T = m->tiles[tile];
+    pipe_open(m, T);
+    HostPipe& p = T.pipe;
+    const int k = p.ko;
+    const size_t bytes = (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double);
+    if (p.out_used[k]) CU(cudaStreamWaitEvent(m->stream, p.out_free[k], 0));   // its previous D2H copy has left the buffer
+    CU(cudaMemcpyAsync(p.out[k], T.var_np1, bytes, cudaMemcpyDeviceToDevice, m->stream));
+    CU(cudaEventRecord(p.out_ready[k], m->stream));
+    CU(cudaStreamWaitEvent(p.s_out, p.out_ready[k], 0));
+    CU(cudaMemcpyAsync(host, p.out[k], bytes, cudaMemcpyDeviceToHost, p.s_out));
+    CU(cudaEventRecord(p.out_free[k], p.s_out));
+    p.out_used[k] = true;
+    p.ko ^= 1;
+  });
+}
+int sb_model_stage_drain(sb_model_t m, int32_t block) {
+  return guarded([&] {
+    if (!m) throw std::invalid_argument("NULL model");
+    for (auto& T : m->tiles) {
+      HostPipe& p = T.pipe;
+      if (!p.on) continue;
+      for (int k = 0; k < 2; ++k) {
+        if (p.out_used[k]) CU(cudaStreamWaitEvent(m->stream, p.out_free[k], 0));
+        if (p.in_used[k]) CU(cudaStreamWaitEvent(m->stream, p.in_free[k], 0));
+      }
+    }
+    if (block) CU(cudaStreamSynchronize(m->stream));
+  });
+}
 int sb_model_tendency(sb_model_t m) {
   return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); tiles_tendency(m); });
 }
@@ -1655,7 +1744,12 @@ int sb_model_profile_report(sb_model_t m, char* buf, int64_t buflen) {
   });
 }
 int sb_model_sync(sb_model_t m) {
-  return guarded([&] { if (!m) throw std::invalid_argument("NULL model"); CU(cudaStreamSynchronize(m->stream)); });
+  return guarded([&] {
+    if (!m) throw std::invalid_argument("NULL model");
+    CU(cudaStreamSynchronize(m->stream));
+    for (auto& T : m->tiles)
+      if (T.pipe.on) { CU(cudaStreamSynchronize(T.pipe.s_in)); CU(cudaStreamSynchronize(T.pipe.s_out)); }
+  });
 }
 int64_t sb_model_launch_count(sb_model_t m) {
   if (!m) return 0;

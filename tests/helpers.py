@@ -261,6 +261,51 @@ def check_model(case, lib, **kw):
     return max(errs)
 
 
+def check_host_pipeline(case, lib, ntiles=1, nsteps=5, pinned=False, **kw):
+    """Host-driven stepping: the pipelined cycle_host (sb_model_stage_in/out: copy streams, double staging buffers)
+    must leave, for every step, exactly the bytes that set_state -> cycle -> get_state leaves.  Every step gets a
+    different input and its own output buffer, so a staging buffer reused too early or a copy ordered wrongly shows."""
+    def alloc(shape):
+        if not pinned:
+            return np.zeros(shape, order="F")
+        import torch
+        t = torch.zeros((shape[1], shape[0]), dtype=torch.float64, pin_memory=True)
+        keep.append(t)
+        return t.numpy().T
+    keep = []
+    a = pkg_model(case, ntiles, lib, **kw)
+    a.initialize(case["ic"])
+    a.run(1)
+    base = [a.state(i, "var_np1") for i in range(ntiles)]
+    ins = [[alloc(b.shape) for b in base] for _ in range(nsteps)]
+    for s_, row in enumerate(ins):
+        for x, b in zip(row, base):
+            x[...] = b * (1.0 + 0.05 * s_)
+    ref = []
+    for s_ in range(nsteps):
+        for i in range(ntiles):
+            a.set_state(i, ins[s_][i])
+        a.cycle()
+        ref.append([a.state(i, "var_np1") for i in range(ntiles)])
+    hist_a = [a.state(i, "expdot_nm1") for i in range(ntiles)]
+    a.close()
+    b = pkg_model(case, ntiles, lib, **kw)
+    b.initialize(case["ic"])
+    b.run(1)
+    outs = [[alloc(x.shape) for x in base] for _ in range(nsteps)]
+    for s_ in range(nsteps):
+        b.cycle_host(ins[s_], outs[s_])
+    b.drain()
+    for s_ in range(nsteps):
+        for i in range(ntiles):
+            assert np.array_equal(outs[s_][i], ref[s_][i]), f"step {s_} tile {i}: pipelined host cycle differs"
+    for i in range(ntiles):
+        assert np.array_equal(b.state(i, "expdot_nm1"), hist_a[i])
+        assert np.array_equal(b.state(i, "var_np1"), ref[-1][i])
+    b.sync()
+    b.close()
+
+
 def check_needed_slots(case, lib, ntiles=None, **kw):
     """In-step tileTransform! producing only the slots the equation-set kernel reads (every other slot NaN) must leave
     exactly the state that producing all D slots leaves (src/semiimplicit.jl:305-314): bit-identical, no NaN."""

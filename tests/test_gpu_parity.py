@@ -286,6 +286,24 @@ def test_chebyshev_column_api(bcb, bct, gpu_lib):
     check_chebyshev_column_api(S, och, gpu_lib, bcb, bct, nz=64, ncol=1000)
 
 
+@pytest.mark.parametrize("ntiles", [1, 2])
+def test_pipelined_host_cycle_is_bit_identical(ntiles, gpu_lib):
+    """Host-driven stepping through the copy streams (sb_model_stage_in/out, page-locked host buffers, 4.2 M points x 3
+    variables = 101 MB each way per step so that copies and kernels really overlap): every step's result is
+    bit-identical to set_state -> cycle -> get_state."""
+    from helpers import check_host_pipeline
+    from oracle import grids as G
+    gp = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=60, zmin=0, zmax=1e3, zDim=64, vars={"h": 1, "u": 2, "v": 3})
+    r, l, z = G.createGrid(gp).getGridpoints().T
+    ic = np.zeros((r.size, 3))
+    ic[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * np.cos(z / 400.0)
+    ic[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
+    ic[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
+    case = dict(gp=gp, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=8, ic=ic, tiles=(1,))
+    check_host_pipeline(case, gpu_lib, ntiles=ntiles, nsteps=6, pinned=True)
+    check_host_pipeline(M_CASES["LinearAdvectionRLZ"], gpu_lib, ntiles=ntiles, nsteps=5, pinned=False)   # pageable buffers: still correct
+
+
 def test_linearity_rlz(gpu_lib):
     gp = S.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=30, zmin=0, zmax=1e4, zDim=64, vars={"a": 1, "b": 2, "c": 3})
     g = S.createGrid(gp, lib=gpu_lib)

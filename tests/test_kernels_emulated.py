@@ -49,6 +49,13 @@ def test_plane_distributed_solve_single_process(name, ntiles, emu_lib):
         assert check_model(case, emu_lib, exchange="columns-p2p") <= STATE_TOL
 
 
+@pytest.mark.parametrize("name,ntiles", [("LinearAdvectionRLZ", 2), ("LinearAdvection1D", 1)])
+def test_pipelined_host_cycle_is_bit_identical(name, ntiles, emu_lib):
+    """sb_model_stage_in / cycle / sb_model_stage_out (asynchronous, double-buffered) == set_state / cycle / get_state."""
+    from helpers import check_host_pipeline
+    check_host_pipeline(M_CASES[name], emu_lib, ntiles=ntiles, nsteps=4)
+
+
 @pytest.mark.parametrize("name,ntiles,exchange", [("LinearAdvectionRLZ", 2, "torch"), ("Euler_test_semiimplicit", 2, "columns")])
 def test_checkpoint_restart_is_exact(name, ntiles, exchange, emu_lib, tmp_path):
     """4 steps straight == 2 steps, checkpoint, restore into a fresh model, 2 more steps (bit for bit): the AB3 /
