@@ -35,6 +35,10 @@ def main(case_name, out_path, lib_path, ntiles, exchange="columns"):
     np.save(f"{out_path}.rank{rank}.npy", out)
     dist.barrier()
     m.close()
+    if os.environ.get("SB_TEST_HOST_PIPELINE"):   # pipelined host-driven stepping with the exchange between ranks inside the cycle
+        from helpers import check_host_pipeline
+        check_host_pipeline(case, lib, ntiles=int(ntiles), nsteps=3, distributed=True, exchange=exchange)
+        dist.barrier()
     dist.destroy_process_group()
 
 

@@ -276,6 +276,7 @@ def check_host_pipeline(case, lib, ntiles=1, nsteps=5, pinned=False, **kw):
     a = pkg_model(case, ntiles, lib, **kw)
     a.initialize(case["ic"])
     a.run(1)
+    nmodel, ntiles = ntiles, len(a.tiles)   # tiles of the patch / tiles this process owns (distributed: its share)
     base = [a.state(i, "var_np1") for i in range(ntiles)]
     ins = [[alloc(b.shape) for b in base] for _ in range(nsteps)]
     for s_, row in enumerate(ins):
@@ -289,7 +290,7 @@ def check_host_pipeline(case, lib, ntiles=1, nsteps=5, pinned=False, **kw):
         ref.append([a.state(i, "var_np1") for i in range(ntiles)])
     hist_a = [a.state(i, "expdot_nm1") for i in range(ntiles)]
     a.close()
-    b = pkg_model(case, ntiles, lib, **kw)
+    b = pkg_model(case, nmodel, lib, **kw)
     b.initialize(case["ic"])
     b.run(1)
     outs = [[alloc(x.shape) for x in base] for _ in range(nsteps)]

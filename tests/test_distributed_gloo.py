@@ -20,6 +20,8 @@ ROOT = Path(__file__).resolve().parent.parent
 def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, emu_lib, tmp_path):
     out = tmp_path / "out"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 2000), OMP_NUM_THREADS="1")
+    if case_name == "LinearAdvection1D":     # also: Model.cycle_host == set_state/cycle/get_state across two ranks
+        env["SB_TEST_HOST_PIPELINE"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", env["MASTER_PORT"], str(ROOT / "tests" / "dist_worker.py"), case_name, str(out),
            str(emu_lib.path), str(ntiles), exchange]

@@ -32,7 +32,9 @@ def test_timestep_matches_oracle(name, emu_lib):
 def test_needed_slots_state_is_bit_identical(name, emu_lib):
     case = dict(M_CASES[name])
     case["n"] = 2
-    check_needed_slots(case, emu_lib)
+    # one tile for the RLZ cases: a thread-per-CUDA-thread emulation of the DMMA kernels is slow, and the GPU suite runs the
+    # same check on two tiles (tests/test_gpu_parity.py::test_needed_slots_state_is_bit_identical)
+    check_needed_slots(case, emu_lib, ntiles=1 if case["gp"].geometry == "RLZ" else None)
 
 
 @pytest.mark.parametrize("name,ntiles", [("LinearAdvection1D", 3), ("LinearAdvectionRLZ", 2), ("Euler_test_semiimplicit", 2)])
