@@ -60,8 +60,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(4) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs),
+    tmp = LIB.with_name(LIB.name + ".tmp")      # link beside the target, then rename: a reader never sees a partial library
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *map(str, objs),
           "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-ldl", "-lcudart"])
+    os.replace(tmp, LIB)
     return LIB
 
 
@@ -85,7 +87,9 @@ def build_emu(force: bool = False) -> Path:
 
     with ThreadPoolExecutor(5) as ex:
         objs = list(ex.map(compile_one, srcs))
-    _run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(EMU_LIB), *map(str, objs), "-ldl"])
+    tmp = EMU_LIB.with_name(EMU_LIB.name + ".tmp")
+    _run(["g++", "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", str(tmp), *map(str, objs), "-ldl"])
+    os.replace(tmp, EMU_LIB)
     return EMU_LIB
 
 

@@ -1625,15 +1625,31 @@ static void pipe_open(sb_model* m, TileState& T) {
   HostPipe& p = T.pipe;
   if (p.on) return;
   const size_t bytes = (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double);
-  CU(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));    // non-blocking: the compute stream may be the legacy
-  CU(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));   // default stream, which would serialise blocking streams
-  for (int k = 0; k < 2; ++k) {
-    CU(cudaMalloc((void**)&p.in[k], bytes));
-    CU(cudaMalloc((void**)&p.out[k], bytes));
-    CU(cudaEventCreate(&p.in_ready[k])); CU(cudaEventCreate(&p.in_free[k]));
-    CU(cudaEventCreate(&p.out_ready[k])); CU(cudaEventCreate(&p.out_free[k]));
-  }
   (void)m;
+  try {
+    CU(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));    // non-blocking: the compute stream may be the legacy
+    CU(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));   // default stream, which would serialise blocking streams
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaMalloc((void**)&p.in[k], bytes));
+      CU(cudaMalloc((void**)&p.out[k], bytes));
+      CU(cudaEventCreate(&p.in_ready[k])); CU(cudaEventCreate(&p.in_free[k]));
+      CU(cudaEventCreate(&p.out_ready[k])); CU(cudaEventCreate(&p.out_free[k]));
+    }
+  } catch (...) {   // e.g. no room for the four staging buffers: leave nothing behind, the blocking calls still work
+    cudaGetLastError();
+    for (int k = 0; k < 2; ++k) {
+      if (p.in[k]) cudaFree(p.in[k]);
+      if (p.out[k]) cudaFree(p.out[k]);
+      if (p.in_ready[k]) cudaEventDestroy(p.in_ready[k]);
+      if (p.in_free[k]) cudaEventDestroy(p.in_free[k]);
+      if (p.out_ready[k]) cudaEventDestroy(p.out_ready[k]);
+      if (p.out_free[k]) cudaEventDestroy(p.out_free[k]);
+    }
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    p = HostPipe{};
+    throw;
+  }
   p.on = true;
 }
 int sb_model_stage_in(sb_model_t m, int32_t tile, const double* host) {
