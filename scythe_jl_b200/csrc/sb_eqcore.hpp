@@ -18,10 +18,13 @@ __device__ __forceinline__ double ab_step(int t, double ts, double u, double fn,
 
 // LinearAdvectionRL (K > 0) / LinearAdvectionRLZ: dh/dt = -u h_r - v h_l / r + K (h_r / r + h_rr + h_ll / r^2)
 // (src/testModels.jl:62-68, :93)
+// The three divisions by r and r^2 are multiplications by ri = 1/r and ri2 = ri*ri, which the caller computes ONCE per
+// radius (a ring shares r; the fused kernel has one r per tile): 12 FP64 divisions per thread of k_inv_z_advection were
+// 9.5 % of its stall samples (profiles/r1m_ncu_full_k_inv_z_advection_t1.txt).  Differs from `/ r` by <= 1 ulp per term.
 __device__ __forceinline__ double advection_rl_tendency(double u, double v, double hr, double hl, double hrr, double hll,
-                                                        double r, double K) {
-  const double q = hl / r;
-  const double lap = ((hr / r) + hrr) + (hll / (r * r));
+                                                        double ri, double ri2, double K) {
+  const double q = hl * ri;
+  const double lap = ((hr * ri) + hrr) + (hll * ri2);
   return fma(K, lap, fma(-v, q, -(u * hr)));
 }
 

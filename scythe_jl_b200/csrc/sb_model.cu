@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) k_pointwise(DevGrid g, EqParams p, ModelA
       e = (-u * hr) - (v * (hl / r));
     } else {
       double hrr = c.P(0, 2), hll = c.P(0, 4);
-      e = advection_rl_tendency(u, v, hr, hl, hrr, hll, r, p.K);
+      const double ri = 1.0 / r;
+      e = advection_rl_tendency(u, v, hr, hl, hrr, hll, ri, ri * ri, p.K);
     }
     c.advance(0, t, ts, c.P(0, 0), e);
     c.advance(1, t, ts, u, 0.0);
