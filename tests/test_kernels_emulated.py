@@ -56,6 +56,24 @@ def test_pipelined_host_cycle_is_bit_identical(name, ntiles, emu_lib):
     """sb_model_stage_in / cycle / sb_model_stage_out (asynchronous, double-buffered) == set_state / cycle / get_state."""
     from helpers import check_host_pipeline
     check_host_pipeline(M_CASES[name], emu_lib, ntiles=ntiles, nsteps=4)
+    if name == "LinearAdvection1D":      # argument checking of the asynchronous calls (no hidden copies, no bad tiles)
+        import ctypes as C
+        import numpy as np
+        from helpers import pkg_model
+        m = pkg_model(M_CASES[name], 1, emu_lib)
+        m.initialize(M_CASES[name]["ic"])
+        g = m.tiles[0]
+        good = np.zeros((g.N, g.V), order="F")
+        with pytest.raises(ValueError):
+            m.stage_in(0, np.zeros((g.N, g.V + 1), order="F")[:, 1:][::1].astype(np.float32))
+        with pytest.raises(ValueError):
+            m.stage_out(0, np.zeros((g.V, 2 * g.N)).T[::2])          # strided view
+        buf = good.ctypes.data_as(C.POINTER(C.c_double))
+        assert emu_lib.sb_model_stage_in(m.handle, 7, buf) != 0 and b"bad argument" in emu_lib.sb_last_error()
+        assert emu_lib.sb_model_stage_out(m.handle, -1, buf) != 0
+        assert emu_lib.sb_model_stage_drain(None, 1) != 0
+        m.stage_in(0, good); m.drain()
+        m.close()
 
 
 @pytest.mark.parametrize("name,ntiles,exchange", [("LinearAdvectionRLZ", 2, "torch"), ("Euler_test_semiimplicit", 2, "columns")])
