@@ -45,6 +45,14 @@ struct RCfg {
                                                    (CH_SMEM ? L / 2 : 0));
 };
 
+// One prefetch.global.L2 per thread for the NEXT sequence's input while the current convolution runs: the input rows
+// come from DRAM (the SZ / SL scratch does not fit L2) and nothing else requests them early -- every register is taken
+// (128 x 512) and so is the shared memory, so the row cannot be staged; 25 % of k_fwd_l2's stall samples were
+// long-scoreboard waits on these loads (profiles/r1m_ncu_full_k_fwd_l2.txt).  A hint only: results cannot change.
+#ifndef SB_FFT_L2PF
+#define SB_FFT_L2PF 1
+#endif
+
 #ifndef SB_PRO_BATCH
 #define SB_PRO_BATCH 2
 #endif
@@ -223,6 +231,11 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
       if (!((lmask >> f) & 1)) continue;   // row not read by the equation set (team-uniform: no barrier is skipped by part of a team)
       double2 v[16];
       team_sync<T>(team);            // the team's previous sequence has finished reading buf
+      if (SB_FFT_L2PF && s + C::NTEAMS < nseq) {   // the team's next spectrum row: (2m-1) doubles <= T lines of 128 B
+        const int rho2 = wk.row0 + ((s + C::NTEAMS) >> 1), zb2 = rho2 / 5, f2 = rho2 - zb2 * 5;
+        const double* sp2 = in + (long long)(f2 < 3 ? f2 : 0) * in_fs + (long long)v_ * in_vs + (long long)zb2 * g.W + woff;
+        if (tl * 16 < 2 * m) sb_prefetch_l2(sp2 + tl * 16);
+      }
       if (active) {
         const int fin = (f < 3) ? f : 0;
         const double* sp = in + (long long)fin * in_fs + (long long)v_ * in_vs + (long long)zb * g.W + woff;
@@ -340,6 +353,10 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l2(DevGrid g, const LWork* __res
       const bool active = row < wk.nrows;
       double2 v[16];
       pair_sync<T>(pair);            // the pair has finished combining the previous row out of buf0 / buf1
+      if (SB_FFT_L2PF && row + NPAIRS < wk.nrows) {   // the pair's next row: n doubles <= 2T lines of 128 B
+        const int ln = half * T + tl;
+        if (ln * 16 < n) sb_prefetch_l2(src + (long long)(wk.row0 + row + NPAIRS) * n + ln * 16);
+      }
       if (active) {
         const double* rp = src + (long long)(wk.row0 + row) * n + 2 * half;
         double* mp = mir ? mir + (long long)(wk.row0 + row) * n + 2 * half : nullptr;
