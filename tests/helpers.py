@@ -121,6 +121,18 @@ def _slab_case(nc=6):
     return gp, ic, prm
 
 
+def fused_advection_case(num_cells, tiles=(1, 2)):
+    """16 levels, no vertical BCs: the fused synthesis + tendency + AB3 kernel (k_inv_z_advection)"""
+    gpf = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=num_cells, zmin=0, zmax=1e3, zDim=16,
+                           vars={"h": 1, "u": 2, "v": 3})
+    r, l, z = G.createGrid(gpf).getGridpoints().T
+    icf = np.zeros((r.size, 3))
+    icf[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * np.cos(z / 400.0)
+    icf[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
+    icf[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
+    return dict(gp=gpf, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=4, ic=icf, tiles=tiles)
+
+
 def model_cases(small=True):
     cases = {}
     gp = G.GridParameters(geometry="R", xmin=-50, xmax=50, num_cells=30, BCL={"u": spl.PERIODIC},
@@ -154,16 +166,7 @@ def model_cases(small=True):
     ic[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
     ic[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
     cases["LinearAdvectionRLZ"] = dict(gp=gp, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=3, ic=ic, tiles=(1, 2))
-    # 16 levels, no vertical BCs: the fused synthesis + tendency + AB3 kernel (k_inv_z_advection)
-    gpf = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=6, zmin=0, zmax=1e3, zDim=16,
-                           vars={"h": 1, "u": 2, "v": 3})
-    r, l, z = G.createGrid(gpf).getGridpoints().T
-    icf = np.zeros((r.size, 3))
-    icf[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * np.cos(z / 400.0)
-    icf[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
-    icf[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
-    cases["LinearAdvectionRLZ_z16_fused"] = dict(gp=gpf, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=4, ic=icf,
-                                                 tiles=(1, 2))
+    cases["LinearAdvectionRLZ_z16_fused"] = fused_advection_case(6)
     gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e5, num_cells=12, zmin=0, zmax=1e4, zDim=12,
                           vars={"h": 1, "u": 2, "x": 3, "w": 4})
     r, z = G.createGrid(gp).getGridpoints().T
