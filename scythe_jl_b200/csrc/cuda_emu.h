@@ -129,6 +129,7 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }   // everything runs at once
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return 0; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)1 << 40; return 0; }
 cudaError_t cudaEventCreate(cudaEvent_t* e);
 cudaError_t cudaEventDestroy(cudaEvent_t e);

@@ -500,11 +500,17 @@ void launch_fwd_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
   ProfScope prof_scope_(c, "fwd_z");
   const size_t smem = (size_t)3 * 32 * FZ_US * sizeof(double);
   const int nwork = ntiles * nvars;
-  const int gx = nwork < 148 * 4 ? nwork : 148 * 4;
   if (smem > 48 * 1024) {
     cudaError_t e0 = cudaFuncSetAttribute(k_fwd_z_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e0 != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e0));
   }
+  // persistent grid = exactly the CTAs that are resident at once (80 registers x 256 threads -> 3 per SM, although four
+  // would fit in shared memory): with 148 x 4 CTAs the last 148 only started when the first wave had finished its share
+  // and ran one per SM (ncu: 1.33 waves)
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd_z_mma, FZ_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 3;
+  const int cap = 148 * per_sm;
+  const int gx = nwork < cap ? nwork : cap;
   SB_LAUNCH(k_fwd_z_mma, dim3(gx), dim3(FZ_THREADS), smem, c.stream, g, tiles, ntiles, nvars, in, in_vstride, mirror,
             mirror_vstride, out, out_vstride, fwdB);
   cudaError_t e = cudaGetLastError();
