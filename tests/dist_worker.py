@@ -21,7 +21,8 @@ def main(case_name, out_path, lib_path, ntiles, exchange="columns"):
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = _lib.load(lib_path)
-    case = model_cases()[case_name]
+    case = dict(model_cases()[case_name])
+    case["n"] = int(os.environ.get("SB_TEST_STEPS", case["n"]))
     m = pkg_model(case, int(ntiles), lib, distributed=True, exchange=exchange)
     assert m.tile_count == int(ntiles) // world and m.tile_first == rank * m.tile_count
     # each rank only ever sees its own slice of the initial state

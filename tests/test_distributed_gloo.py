@@ -22,6 +22,8 @@ def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, 
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 2000), OMP_NUM_THREADS="1")
     if case_name == "LinearAdvection1D":     # also: Model.cycle_host == set_state/cycle/get_state across two ranks
         env["SB_TEST_HOST_PIPELINE"] = "1"
+    nsteps = model_cases()[case_name]["n"] if case_name == "LinearAdvection1D" else 2    # (emulation time; Euler + AB2 with the exchange)
+    env["SB_TEST_STEPS"] = str(nsteps)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", env["MASTER_PORT"], str(ROOT / "tests" / "dist_worker.py"), case_name, str(out),
            str(emu_lib.path), str(ntiles), exchange]
@@ -29,7 +31,7 @@ def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, 
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     o0, o1 = np.load(f"{out}.rank0.npy"), np.load(f"{out}.rank1.npy")
     assert np.array_equal(o0, o1)                      # every rank holds the same patch coefficients
-    case = model_cases()[case_name]
+    case = dict(model_cases()[case_name], n=nsteps)
     m = pkg_model(case, ntiles, emu_lib)               # same tiles, one process
     m.initialize(case["ic"])
     m.run(case["n"])

@@ -25,6 +25,8 @@ def test_timestep_matches_oracle(name, emu_lib):
     case = dict(M_CASES[name])
     case["tiles"] = case["tiles"][-1:]   # the multi-tile variant only (CPU time)
     case["n"] = min(case["n"], 3)
+    if name == "Oneway_ShallowWater_HeightResolvedBL_z16":
+        case["n"] = 1    # (the emulated DMMA kernels are slow; two steps of this set run in the needed-slots test below)
     assert check_model(case, emu_lib) <= STATE_TOL
 
 
@@ -58,7 +60,7 @@ def test_plane_distributed_solve_single_process(name, ntiles, emu_lib):
 def test_pipelined_host_cycle_is_bit_identical(name, ntiles, emu_lib):
     """sb_model_stage_in / cycle / sb_model_stage_out (asynchronous, double-buffered) == set_state / cycle / get_state."""
     from helpers import check_host_pipeline
-    check_host_pipeline(M_CASES[name], emu_lib, ntiles=ntiles, nsteps=4)
+    check_host_pipeline(M_CASES[name], emu_lib, ntiles=ntiles, nsteps=3)
     if name == "LinearAdvection1D":      # argument checking of the asynchronous calls (no hidden copies, no bad tiles)
         import ctypes as C
         import numpy as np
