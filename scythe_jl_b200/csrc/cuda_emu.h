@@ -6,20 +6,21 @@
 // tests/_emu/libscythe_b200_emu.so and is loaded ONLY by tests; the product loader
 // (scythe_jl_b200/_lib.py) never looks for it and fails loudly without the sm_100a build.
 //
-// Model: one OS thread per CUDA thread of a block, blocks executed one after another,
-// __syncthreads() = std::barrier, __shared__ = function-level static (safe because only
-// one block is live at a time), warp shuffles through a per-warp exchange buffer.
+// Model: the CUDA threads of a block are cooperative fibers (ucontext) on the calling OS thread, blocks executed
+// one after another; a fiber runs until it reaches a barrier (__syncthreads, warp exchange, named bar.sync) and
+// then hands over to the next one, so a barrier costs user-level context switches instead of futex sleeps of
+// hundreds of oversubscribed OS threads.  __shared__ = function-level static (safe because only one block is live
+// at a time), warp shuffles through a per-warp exchange buffer.  Kernels must not spin on another thread's flag
+// without a barrier (none does: there is no inter-thread communication outside barriers in this code base).
 #pragma once
 #ifdef SB_EMU
 #include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
 
 #define __global__
@@ -45,11 +46,22 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 
 namespace sbemu {
-extern thread_local uint3 t_threadIdx, t_blockIdx;
-extern thread_local dim3 t_blockDim, t_gridDim;
-extern thread_local int t_lin;            // linear thread id in block
-extern std::barrier<>* g_block_barrier;
-extern std::vector<std::unique_ptr<std::barrier<>>> g_warp_barriers;
+extern uint3 t_threadIdx, t_blockIdx;   // of the fiber that is running (set at every switch)
+extern dim3 t_blockDim, t_gridDim;
+extern int t_lin;                       // linear thread id in block
+void fiber_yield();                     // run the other fibers of the block once, then come back
+struct FiberBarrier {                   // all `n` fibers arrive before any leaves; reusable
+  int n, count = 0;
+  unsigned gen = 0;
+  explicit FiberBarrier(int n_) : n(n_) {}
+  void arrive_and_wait() {
+    const unsigned g = gen;
+    if (++count == n) { count = 0; ++gen; return; }
+    while (gen == g) fiber_yield();
+  }
+};
+extern FiberBarrier* g_block_barrier;
+extern std::vector<std::unique_ptr<FiberBarrier>> g_warp_barriers;
 extern double g_warp_buf[64][32];
 extern double g_warp_buf2[64][32];
 extern unsigned char* g_dyn_smem;
