@@ -22,7 +22,7 @@ def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, 
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 2000), OMP_NUM_THREADS="1")
     if case_name == "LinearAdvection1D":     # also: Model.cycle_host == set_state/cycle/get_state across two ranks
         env["SB_TEST_HOST_PIPELINE"] = "1"
-    nsteps = model_cases()[case_name]["n"] if case_name == "LinearAdvection1D" else 2    # (emulation time; Euler + AB2 with the exchange)
+    nsteps = min(model_cases()[case_name]["n"], 4)
     env["SB_TEST_STEPS"] = str(nsteps)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", env["MASTER_PORT"], str(ROOT / "tests" / "dist_worker.py"), case_name, str(out),

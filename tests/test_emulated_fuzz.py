@@ -1,17 +1,17 @@
 """The seeded random grid configurations of tests/test_gpu_fuzz.py (geometry, cells, levels, boundary conditions, tile
 offset, variables) through the TEST-ONLY CPU emulation of the kernel sources vs the oracle, for the configurations small
-enough for a thread-per-CUDA-thread emulation: kernel indexing at the boundaries between kernel variants is checked
-before any GPU time is spent.  The GPU suite runs 60 seeds on the product library."""
+enough for the emulation: kernel indexing at the boundaries between kernel variants is checked
+before any GPU time is spent.  The GPU suite runs the same 60 seeds on the product library."""
 import pytest
 
 from helpers import TRANSFORM_TOL, check_transforms
 from oracle import grids as G
 from test_gpu_fuzz import random_case
 
-MAX_POINTS = 60000
+MAX_POINTS = 400000
 
 
-@pytest.mark.parametrize("seed", range(32))
+@pytest.mark.parametrize("seed", range(60))
 def test_random_grid_transforms_match_oracle_emulated(seed, emu_lib):
     gp = random_case(seed)
     og = G.createGrid(gp)

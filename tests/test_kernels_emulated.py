@@ -25,21 +25,14 @@ def test_timestep_matches_oracle(name, emu_lib):
     case = dict(M_CASES[name])
     case["tiles"] = case["tiles"][-1:]   # the multi-tile variant only (CPU time)
     case["n"] = min(case["n"], 3)
-    if name == "Oneway_ShallowWater_HeightResolvedBL_z16":
-        case["n"] = 1    # (the emulated DMMA kernels are slow; two steps of this set run in the needed-slots test below)
     assert check_model(case, emu_lib) <= STATE_TOL
 
 
 @pytest.mark.parametrize("name", ["LinearShallowWater1D", "LinearAdvectionRLZ_z16_fused", "Oneway_ShallowWater_HeightResolvedBL_z16"])
 def test_needed_slots_state_is_bit_identical(name, emu_lib):
     case = dict(M_CASES[name])
-    if name == "LinearAdvectionRLZ_z16_fused":   # a 4-cell grid here (12 rings); the GPU suite and smoke() run the 6-cell one
-        from helpers import fused_advection_case
-        case = fused_advection_case(4)
-    case["n"] = 1 if name == "Oneway_ShallowWater_HeightResolvedBL_z16" else 2    # which slots a kernel reads does not depend on t
-    # one tile for the RLZ cases: a thread-per-CUDA-thread emulation of the DMMA kernels is slow, and the GPU suite runs the
-    # same check on two tiles (tests/test_gpu_parity.py::test_needed_slots_state_is_bit_identical)
-    check_needed_slots(case, emu_lib, ntiles=1 if case["gp"].geometry == "RLZ" else None)
+    case["n"] = min(case["n"], 3)     # Euler, AB2, AB3
+    check_needed_slots(case, emu_lib)
 
 
 @pytest.mark.parametrize("name,ntiles", [("LinearAdvection1D", 3), ("LinearAdvectionRLZ", 2), ("Euler_test_semiimplicit", 2)])
@@ -48,7 +41,7 @@ def test_plane_distributed_solve_single_process(name, ntiles, emu_lib):
     its own slice of A (here one process owns every plane) -- same answer as the shared-array scheme."""
     case = dict(M_CASES[name])
     case["tiles"] = (ntiles,)
-    case["n"] = min(case["n"], 2 if case["gp"].geometry == "RLZ" else 3)
+    case["n"] = min(case["n"], 3)
     assert check_model(case, emu_lib, exchange="columns") <= STATE_TOL
     if name == "LinearAdvectionRLZ":
         # peer-memory form (here every "peer" buffer is this process's own): fwd_r scatters into the owner's slots,
@@ -60,7 +53,7 @@ def test_plane_distributed_solve_single_process(name, ntiles, emu_lib):
 def test_pipelined_host_cycle_is_bit_identical(name, ntiles, emu_lib):
     """sb_model_stage_in / cycle / sb_model_stage_out (asynchronous, double-buffered) == set_state / cycle / get_state."""
     from helpers import check_host_pipeline
-    check_host_pipeline(M_CASES[name], emu_lib, ntiles=ntiles, nsteps=3 if ntiles == 1 else 2)
+    check_host_pipeline(M_CASES[name], emu_lib, ntiles=ntiles, nsteps=5)
     if name == "LinearAdvection1D":      # argument checking of the asynchronous calls (no hidden copies, no bad tiles)
         import ctypes as C
         import numpy as np
