@@ -9,8 +9,6 @@ from helpers import (STATE_TOL, TRANSFORM_TOL, check_model, check_needed_slots, 
 
 T_CASES = transform_cases()
 M_CASES = model_cases()
-FAST_MODELS = ["LinearAdvection1D", "LinearShallowWater1D", "LinearAdvectionRL_K0", "LinearAdvectionRZ",
-               "Euler_test_semiimplicit", "LinearAdvectionRLZ", "Oneway_ShallowWater_HeightResolvedBL_z16"]
 
 
 @pytest.mark.parametrize("name", sorted(T_CASES))
@@ -20,15 +18,14 @@ def test_transforms_match_oracle(name, emu_lib):
     assert max(eP) <= TRANSFORM_TOL, f"gridTransform rel err per slot {eP}"
 
 
-@pytest.mark.parametrize("name", FAST_MODELS)
+@pytest.mark.parametrize("name", sorted(M_CASES))
 def test_timestep_matches_oracle(name, emu_lib):
     case = dict(M_CASES[name])
-    case["tiles"] = case["tiles"][-1:]   # the multi-tile variant only (CPU time)
-    case["n"] = min(case["n"], 3)
+    case["n"] = min(case["n"], 4)
     assert check_model(case, emu_lib) <= STATE_TOL
 
 
-@pytest.mark.parametrize("name", ["LinearShallowWater1D", "LinearAdvectionRLZ_z16_fused", "Oneway_ShallowWater_HeightResolvedBL_z16"])
+@pytest.mark.parametrize("name", sorted(M_CASES))
 def test_needed_slots_state_is_bit_identical(name, emu_lib):
     case = dict(M_CASES[name])
     case["n"] = min(case["n"], 3)     # Euler, AB2, AB3
