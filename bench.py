@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-materialised", action="store_true", help="skip the secondary all-slots timing (ncu captures)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-preflight", action="store_true", help="N > 1: skip the multi-rank parity preflight against the oracle")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling run (C4 itself cut into N tiles)")
     return ap.parse_args()
 
 
@@ -154,13 +156,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm (oracle = the reference restated)
-def cpu_baseline(steps=2, warmup=1, cells=64, workers=None):
-    """Oracle ModelRun on a bounded sample of the same workload, all host threads, scaled by points."""
+def sample_case(cells):
+    """The bounded sample of the C4 workload the CPU arm runs: the inner `cells` radial cells of the same grid."""
     from oracle import grids as G
     from oracle import model as M
-    workers = workers or os.cpu_count() or 1
     gp = G.GridParameters(geometry="RLZ", xmin=0.0, xmax=XMAX * cells / C4_CELLS, num_cells=cells, zmin=0.0, zmax=ZMAX,
                           zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
+    return gp, M
+
+
+def cpu_baseline(steps=2, warmup=1, cells=64, workers=None):
+    """Oracle ModelRun on a bounded sample of the same workload, all host threads, scaled by points.
+    Returns (record, seconds per step, final var_np1 of the sample [N, V], steps taken)."""
+    workers = workers or os.cpu_count() or 1
+    gp, M = sample_case(cells)
     mp = M.ModelParameters(ts=TS, integration_time=TS * (steps + warmup), equation_set="LinearAdvectionRLZ",
                            grid_params=gp, physical_params={"K": KDIFF})
     ic = synthetic_state(0.0, XMAX / C4_CELLS, cells, 0, ZDIM, ZMAX)
@@ -171,24 +180,59 @@ def cpu_baseline(steps=2, warmup=1, cells=64, workers=None):
     dt = (time.perf_counter() - t0) / steps
     n_s, n_full = dims(cells)["N"], dims(C4_CELLS)["N"]
     value = (1.0 / dt) * n_s / n_full
-    sample = (f"oracle (NumPy/SciPy pocketfft restatement) ModelRun, RLZ {cells} cells x {ZDIM} levels x {NVARS} vars = "
-              f"{n_s} points, {steps} timed steps ({dt * 1e3:.0f} ms/step), scaled by points to the "
-              f"{n_full}-point C4 grid")
-    return {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample}, dt
+    sample = (f"oracle (NumPy/SciPy pocketfft restatement of the reference's algorithm, NOT Scythe.jl itself: Julia is not in "
+              f"the image) ModelRun, RLZ {cells} cells x {ZDIM} levels x {NVARS} vars = {n_s} points, {steps} timed steps "
+              f"({dt * 1e3:.0f} ms/step), EXTRAPOLATED by points to the {n_full}-point C4 grid")
+    rec = {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "extrapolated": True,
+           "label": "NumPy restatement, extrapolated from a 1/27 sample by points", "sample": sample,
+           "sample_points": n_s, "sample_ms_per_step": dt * 1e3}
+    return rec, dt, np.array(run.mtiles[0].var_np1), steps + warmup
+
+
+def gpu_sample_parity(ostate, nsteps, cells=64, device=0):
+    """The GPU path on the CPU arm's sample (same grid, same synthetic state, same number of steps, default fused
+    dataflow) against the oracle's final state: the parity check on the benchmarked level count and kernels."""
+    import scythe_jl_b200 as S
+    DX = XMAX / C4_CELLS
+    gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * cells, num_cells=cells, zmin=0.0, zmax=ZMAX, zDim=ZDIM,
+                          vars={"h": 1, "u": 2, "v": 3})
+    mp = S.ModelParameters(ts=TS, integration_time=TS * nsteps, equation_set="LinearAdvectionRLZ", grid_params=gp,
+                           physical_params={"K": KDIFF})
+    m = S.Model(mp, num_tiles=1, device=device)
+    m.initialize_tiles([synthetic_state(0.0, DX, cells, 0, ZDIM, ZMAX)])
+    m.run(nsteps)
+    got = m.state(0, "var_np1")
+    m.close()
+    scale = np.abs(ostate).max(axis=0)
+    err = float((np.abs(got - ostate).max(axis=0) / np.where(scale > 0, scale, 1.0)).max())
+    return {"rel_err": err, "tol": 1e-9, "ok": bool(err <= 1e-9), "steps": int(nsteps), "points": int(ostate.shape[0]),
+            "what": f"GPU (default fused K3+K4 step) vs oracle on the cpu_baseline sample: RLZ {cells} cells x {ZDIM} levels, "
+                    "max over variables of max|d var_np1| / max|var_np1|"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, dt = cpu_baseline(steps=max(min(args.steps, 3), 1), warmup=1)
+    cb, dt, _, _ = cpu_baseline(steps=max(min(args.steps, 3), 1), warmup=1)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"] * 1.0, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"] if cb["value"] else None,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, C4_CELLS), "cpu_baseline": cb,
+            "config": workload_config(args.gpus, C4_CELLS), "cpu_baseline": cb, "extrapolated": True,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def kernel_source_hash():
+    """sha256 over the kernel sources: profiles/step_kernels_*.json carry the hash they were captured at
+    (profiles/make_step_table.py), and `roofline.traffic` is only printed when it matches."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "scythe_jl_b200" / "csrc").glob("sb_*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
 
 
 def workload_config(ngpus, cells_per_tile, eq="LinearAdvectionRLZ", nvars=3):
@@ -201,6 +245,74 @@ def workload_config(ngpus, cells_per_tile, eq="LinearAdvectionRLZ", nvars=3):
                          "CUDA-IPC peer mappings (NVLink), two one-element rendezvous per step, no data collective"),
             "l2": "working set >> 126 MB L2 (physical 21.7 GB/GPU); no flush needed",
             "units": "C4-equivalent (128.9 M-point) tile-timesteps, summed over ranks"}
+
+
+# ------------------------------------------------------------------ multi-rank parity preflight (N > 1)
+def multi_rank_preflight(S, dist, rank, world, local_rank, cells=36, nsteps=3):
+    """N ranks, one radial tile each, the DEFAULT exchange (CUDA-IPC peer stores, `columns-p2p`), default fused step,
+    64 levels: every rank's tile state after `nsteps` against the oracle integrated with the same N tiles
+    (reference: /root/reference/src/semiimplicit.jl:320-329, 279-285).  Returns the record rank 0 prints."""
+    import torch
+    from oracle import grids as G
+    from oracle import model as M
+    cells = max(cells, 4 * world)
+    DX = XMAX / C4_CELLS
+    ogp = G.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * cells, num_cells=cells, zmin=0.0, zmax=ZMAX, zDim=ZDIM,
+                           vars={"h": 1, "u": 2, "v": 3})
+    ic = synthetic_state(0.0, DX, cells, 0, ZDIM, ZMAX)
+    gp = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=DX * cells, num_cells=cells, zmin=0.0, zmax=ZMAX, zDim=ZDIM,
+                          vars={"h": 1, "u": 2, "v": 3})
+    mp = S.ModelParameters(ts=TS, integration_time=TS * nsteps, equation_set="LinearAdvectionRLZ", grid_params=gp,
+                           physical_params={"K": KDIFF})
+    m = S.Model(mp, num_tiles=world, device=local_rank, distributed=True)
+    exchange = m.exchange
+    tp = m.tile_params
+    pts = np.concatenate([[0], np.cumsum(tp[4]).astype(np.int64)])
+    m.initialize_tiles([ic[pts[rank]:pts[rank + 1]]])
+    m.run(nsteps)
+    got = m.state(0, "var_np1")
+    m.close()
+    omp = M.ModelParameters(ts=TS, integration_time=TS * nsteps, equation_set="LinearAdvectionRLZ", grid_params=ogp,
+                            physical_params={"K": KDIFF})
+    orun = M.ModelRun(omp, world, ic, workers=max(1, (os.cpu_count() or 8) // world))
+    orun.run(nsteps)
+    want = np.array(orun.mtiles[rank].var_np1)
+    scale = np.abs(want).max(axis=0)
+    err = float((np.abs(got - want).max(axis=0) / np.where(scale > 0, scale, 1.0)).max())
+    t = torch.tensor([err], device="cuda", dtype=torch.float64)
+    allerr = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allerr, t)
+    errs = [float(x.item()) for x in allerr]
+    return {"ranks": world, "rel_err_max": max(errs), "rel_err_per_rank": errs, "tol": 1e-9, "ok": bool(max(errs) <= 1e-9),
+            "exchange": exchange, "steps": nsteps, "tile_cells": [int(c) for c in tp[2]],
+            "what": f"RLZ {cells} cells x {ZDIM} levels cut into {world} tiles, one per rank, default exchange and fused "
+                    "step: each rank's var_np1 vs the oracle's tile of the same N-tile integration"}
+
+
+def pcie_ceiling(torch, nbytes=1 << 30):
+    """This rank's concurrent H2D + D2H rate with plain pinned copies on two streams (the denominator of e2e)."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    res = {}
+    for name, both in (("h2d_alone", False), ("both", True)):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(2):          # second repetition is the measurement
+            with torch.cuda.stream(s1):
+                e0.record(); d_in.copy_(h_in, non_blocking=True); e1.record()
+            if both:
+                with torch.cuda.stream(s2):
+                    f0.record(); h_out.copy_(d_out, non_blocking=True); f1.record()
+            torch.cuda.synchronize()
+        res[name] = {"h2d_GBps": nbytes / 1e6 / e0.elapsed_time(e1)}
+        if both:
+            res[name]["d2h_GBps"] = nbytes / 1e6 / f0.elapsed_time(f1)
+    del h_in, h_out, d_in, d_out
+    return res
 
 
 # ------------------------------------------------------------------ our arm
@@ -218,6 +330,9 @@ def run_ours(args):
     if distributed:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    preflight = None
+    if distributed and not args.no_preflight:
+        preflight = multi_rank_preflight(S, dist, rank, world, local_rank)
     ntiles = world
     cells_tile = args.cells or C4_CELLS
     total_cells = int(round(cells_tile * math.sqrt(ntiles)))
@@ -239,6 +354,8 @@ def run_ours(args):
         mp = S.ModelParameters(ts=TS, integration_time=TS * 1000, equation_set="LinearAdvectionRLZ", grid_params=gp,
                                physical_params={"K": KDIFF})
     m = S.Model(mp, num_tiles=ntiles, device=local_rank, distributed=distributed)
+    cfg_exchange = m.exchange
+    Sp = m.patch.S
     tp = m.tile_params
     tcells, tsil = int(tp[2, m.tile_first]), int(tp[3, m.tile_first])
     ic = (synthetic_state_tcbl if tcbl else synthetic_state)(tp[0, m.tile_first], DX, tcells, (tsil - 1) * 3, ZDIM, ZMAX)
@@ -255,15 +372,16 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, n, tail=None):
+    def timed(fn, n, tail=None, model=None):
+        model = model or m
         barrier()
-        lib.check(lib.sb_timer_start(m.patch.handle))
+        lib.check(lib.sb_timer_start(model.patch.handle))
         for _ in range(n):
             fn()
         if tail:
             tail()           # stream-ordered only: makes the timed stream wait for work issued on the copy streams
         ms = C.c_float()
-        lib.check(lib.sb_timer_stop(m.patch.handle, C.byref(ms)))
+        lib.check(lib.sb_timer_stop(model.patch.handle, C.byref(ms)))
         barrier()
         t = torch.tensor([ms.value], device="cuda")
         if distributed:
@@ -350,12 +468,56 @@ def run_ours(args):
                           "what": "the same step with blocking copies: set_state -> cycle -> get_state, nothing overlapped"}}
         if pipe_note:
             e2e["note"] = pipe_note
+        del hin, hout, a_in, a_out
+        barrier()
+        ceil = pcie_ceiling(torch)      # every rank at the same time: what the box gives this rank while all ranks copy
+        ct = torch.tensor([ceil["h2d_alone"]["h2d_GBps"], ceil["both"]["h2d_GBps"], ceil["both"]["d2h_GBps"]], device="cuda")
+        if distributed:
+            dist.all_reduce(ct, op=dist.ReduceOp.SUM)
+        agg = [float(x) for x in ct.tolist()]
+        floor_ms = max(e2e["h2d_bytes_per_step"] / (agg[1] * 1e6), e2e["d2h_bytes_per_step"] / (agg[2] * 1e6))
+        e2e["host_link_ceiling"] = {
+            "h2d_alone_GBps_sum_over_ranks": agg[0], "h2d_concurrent_GBps_sum_over_ranks": agg[1],
+            "d2h_concurrent_GBps_sum_over_ranks": agg[2], "copy_floor_ms_per_step": floor_ms,
+            "frac_of_copy_floor": floor_ms / p_ms,
+            "what": "1 GiB pinned cudaMemcpyAsync H2D alone, then H2D and D2H concurrently on two streams, all ranks at once; "
+                    "copy_floor = this step's bytes at the concurrent rates (full duplex): e2e cannot beat it on this box"}
 
     per_rank = None
+    strong = None
     if distributed:   # every rank's per-kernel time: the step is as slow as the slowest tile
         mine = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items()}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
+        if not args.no_strong and not tcbl and not args.cells:
+            # strong scaling: C4 ITSELF cut into N equal-gridpoint tiles, one per rank
+            # (/root/reference/src/semiimplicit.jl:141-169): true timesteps/s of the 128.9 M-point problem
+            exch = m.exchange
+            m.close()
+            gps = S.GridParameters(geometry="RLZ", xmin=0.0, xmax=XMAX, num_cells=C4_CELLS, zmin=0.0, zmax=ZMAX,
+                                   zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
+            mps = S.ModelParameters(ts=TS, integration_time=TS * 1000, equation_set="LinearAdvectionRLZ", grid_params=gps,
+                                    physical_params={"K": KDIFF})
+            ms_ = S.Model(mps, num_tiles=world, device=local_rank, distributed=True)
+            tps = ms_.tile_params
+            sc, ssil = int(tps[2, ms_.tile_first]), int(tps[3, ms_.tile_first])
+            ms_.initialize_tiles([synthetic_state(tps[0, ms_.tile_first], XMAX / C4_CELLS, sc, (ssil - 1) * 3, ZDIM, ZMAX)])
+            ms_.set_k3_slots(args.k3_slots)
+            for _ in range(max(args.warmup, 3)):
+                ms_.step()
+            nst = max(3, min(args.steps, 10))
+            ms_.profile(True)
+            st_ms = timed(ms_.step, nst, model=ms_) / nst
+            ms_.profile(False)
+            sp = {k: round(v["ms"] / nst, 3) for k, v in ms_.profile_report().items()}
+            sp_all = [None] * world
+            dist.all_gather_object(sp_all, sp)
+            strong = {"what": "strong scaling: the C4 problem itself (334 cells, 128,897,280 points) cut into N equal-gridpoint "
+                              "radial tiles, one per rank; value = true timesteps/s of that problem (compare with the N=1 line)",
+                      "value": 1e3 / st_ms, "unit": UNIT, "ms_per_step": st_ms, "steps": nst, "tile_cells": [int(c) for c in tps[2]],
+                      "tile_points": [int(c) * ZDIM for c in tps[4]], "per_rank_kernel_ms": sp_all, "exchange": ms_.exchange}
+            ms_.close()
+            m = None
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -368,7 +530,6 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     N, Sg, D, V = d["N"], d["S"], d["D"], NVARS
-    Sp = m.patch.S
     # (variable, slot) pairs the equation-set kernel reads / variables it reads at all (sb_model.cu: equation_set_needs)
     ns_needed, v_read = (21, 5) if tcbl else (7, 3)
 
@@ -405,16 +566,20 @@ def run_ours(args):
     top = max(detail, key=lambda k: detail[k]["ms_per_step"])
     # measured DRAM traffic / FP64-pipe activity of the same step from the committed ncu pass (profiles/), if present
     traffic, ncu_note = None, None
-    prof_name = {"fused": "r1l_step_kernels_fused.json", "needed": "r1k_step_kernels_needed.json"}.get(args.k3_slots, "r1j_step_kernels.json")
+    prof_name = {"fused": "step_kernels_fused.json", "needed": "step_kernels_needed.json"}.get(args.k3_slots, "step_kernels_all.json")
     prof_file = ROOT / "profiles" / prof_name
-    if prof_file.exists() and world == 1 and cells_tile == C4_CELLS and not tcbl:
+    src_hash = kernel_source_hash()
+    if prof_file.exists() and json.loads(prof_file.read_text()).get("kernel_src_sha16") != src_hash:
+        ncu_note = {"file": "profiles/" + prof_name, "stale": True, "kernel_src_sha16_now": src_hash,
+                    "note": "the committed ncu per-step table was taken at a different state of csrc/: traffic not reported"}
+    elif prof_file.exists() and world == 1 and cells_tile == C4_CELLS and not tcbl:
         pk = json.loads(prof_file.read_text())["one_step"]
         sel = {"K3": ("k_inv_r", "k_inv_l", "k_inv_z"), "K1": ("k_fwd_z", "k_fwd_l", "k_fwd_r"), "K2": ("k_spline",),
                "K4": ("k_pointwise",)}[top[:2]]      # ("K3+K4 ..." starts with K3: k_inv_z matches k_inv_z_advection too)
         rows = [v for k, v in pk.items() if any(s_ in k for s_ in sel)]
         traffic = 1e9 * sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows)
         fft = [v for k, v in pk.items() if "k_inv_l2" in k]
-        ncu_note = {"file": "profiles/" + prof_name,
+        ncu_note = {"file": "profiles/" + prof_name, "kernel_src_sha16": src_hash,
                     "k_inv_l2_fp64_pipe_pct": sum(r["fp64_pipe_pct"] * r["ms"] for r in fft) / max(sum(r["ms"] for r in fft), 1e-9),
                     "k_inv_l2_share_of_step_under_ncu": sum(r["share"] for r in fft),
                     "note": "the ring FFT inside K3 is FP64-pipe bound (Bluestein), not HBM bound; measured FP64 peak "
@@ -423,11 +588,11 @@ def run_ours(args):
             "frac": detail[top]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": detail[top]["algorithmic_GB"] * 1e9,
             "share_of_step": detail[top]["ms_per_step"] / ms_step, "ncu": ncu_note}
-    cfg_exchange = m.exchange
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world, cells_tile, args.equation_set, NVARS), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "per_rank_kernel_ms": per_rank, "roofline": roof, "roofline_detail": detail, "kernel_ms_per_step": kern_ms,
+            "gpu_launches": int(launches), "per_rank_kernel_ms": per_rank, "parity_nranks": preflight, "strong": strong,
+            "roofline": roof, "roofline_detail": detail, "kernel_ms_per_step": kern_ms,
             "timestep_algorithmic_GB": step_bytes / 1e9,
             "timestep_frac_of_hbm_roofline": (step_bytes / 1e9) / (ms_step / 1e3) / peak,
             "transforms_per_s": {"spectralTransform_K1": 1e3 / k1_ms, "gridTransform_K2K3": 1e3 / k23_ms,
@@ -451,10 +616,11 @@ def run_ours(args):
             "timestep_frac_of_hbm_roofline": (mbytes / 1e9) / (mat["ms_per_step"] / 1e3) / peak,
             "roofline": {"bound": "hbm", "kernel": mtop, "achieved": mdet[mtop]["achieved_GBps"], "peak": peak, "unit": "GB/s",
                          "frac": mdet[mtop]["frac"], "algorithmic_bytes_per_launch": mdet[mtop]["algorithmic_GB"] * 1e9}}
+    if m is not None:
+        m.close()               # release this model's ~60 GB before the secondary runs
     if world == 1 and not tcbl and not args.no_tcbl and not args.cells:
         # secondary number (north_star item 4): the same C4 grid stepped with the 6-variable height-resolved TC
-        # boundary-layer set, in a fresh process once this model's 60 GB are released
-        m.close()
+        # boundary-layer set, in a fresh process
         try:
             r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--equation-set", "Oneway_ShallowWater_HeightResolvedBL",
                                 "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"], capture_output=True,
@@ -470,7 +636,14 @@ def run_ours(args):
         except Exception as e:  # the headline line must still print
             line["tcbl"] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"], _ = cpu_baseline()
+        # the CPU arm on its bounded sample; its final state then checks the GPU path on the same sample (64 levels, the
+        # benchmarked kernels): `parity`
+        line["cpu_baseline"], _, ostate, onsteps = cpu_baseline()
+        if not tcbl:
+            try:
+                line["parity"] = gpu_sample_parity(ostate, onsteps, device=local_rank)
+            except Exception as e:
+                line["parity"] = {"error": repr(e)[:300], "ok": False}
     else:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N=1 only"}
     line["config"]["exchange_mode"] = cfg_exchange

@@ -72,7 +72,10 @@ def main(src: str, dst: str, source_note: str = ""):
         t["ms"] = round(t["ms"], 4)
         t["dram_read_GB"] = round(t["dram_read_GB"], 4)
         t["dram_write_GB"] = round(t["dram_write_GB"], 4)
-    out = {"source": source_note or f"profiles/make_step_table.py {src}", "one_step": table, "step_ms_under_ncu": round(total, 4),
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    from bench import kernel_source_hash
+    out = {"source": source_note or f"profiles/make_step_table.py {src}", "kernel_src_sha16": kernel_source_hash(),
+           "one_step": table, "step_ms_under_ncu": round(total, 4),
            "launches_per_step": len(step),
            "dram_GB_per_step": round(sum(t["dram_read_GB"] + t["dram_write_GB"] for t in table.values()), 3)}
     with open(dst, "w") as f:

@@ -529,21 +529,25 @@ class Model:
         if self.dist is not None and self.world > 1 and self.exchange in ("native", "columns-native", "columns-p2p-native"):
             self._init_native_comm()
         if self.p2p:
-            ok = True
+            # Two phases: every rank first maps its peers' buffers, then ALL ranks agree on the outcome, and only
+            # then is the peer-store path switched on in the library (sb_model_p2p_enable cannot be undone).  A rank whose
+            # cudaIpcOpenMemHandle failed while the others enabled would be written to by kernels it knows nothing about.
+            ok, err = True, None
             try:
-                self._init_p2p()
-            except ScytheError:
-                if not self._p2p_is_default:
-                    raise
-                ok = False
-            if self.dist is not None and self.world > 1 and self._p2p_is_default:
+                self._open_p2p()
+            except ScytheError as e:
+                ok, err = False, e
+            if self.dist is not None and self.world > 1:
+                ok = self._all_agree(ok)
+            fallback_ok = self._p2p_is_default or os.environ.get("SB_P2P_FALLBACK") == "1"
+            if ok:
+                self.lib.check(self.lib.sb_model_p2p_enable(self.handle))
+            elif fallback_ok:
                 # the peer mappings are an optimisation of the default: if CUDA IPC is unavailable on ANY rank, every
                 # rank drops to the message form of the same exchange (still NCCL over NVLink, same results)
-                import torch
-                flag = torch.tensor([1.0 if ok else 0.0], device=f"cuda:{torch.cuda.current_device()}")
-                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
-                if flag.item() < 1.0:
-                    self.exchange, self.p2p = "columns", False
+                self.exchange, self.p2p = "columns", False
+            else:
+                raise err or ScytheError(_lib.SB_ECUDA, "CUDA IPC peer mapping failed on another rank")
 
     # -- multi-process plumbing -------------------------------------------------------
     def _init_native_comm(self):
@@ -559,8 +563,17 @@ class Model:
         uid = (C.c_ubyte * 128)(*t.cpu().tolist())
         self.lib.check(self.lib.sb_model_comm_init(self.handle, uid, self.rank, self.world))
 
-    def _init_p2p(self):
-        """exchange CUDA IPC handles of the receive buffers / tile A arrays and map the peers' memory"""
+    def _all_agree(self, ok: bool) -> bool:
+        """True only if `ok` on every rank (MIN all-reduce on the backend's device)."""
+        import torch
+        dev = f"cuda:{torch.cuda.current_device()}" if self.dist.get_backend() == "nccl" else "cpu"
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        return bool(flag.item() >= 1.0)
+
+    def _open_p2p(self):
+        """exchange CUDA IPC handles of the receive buffers / tile A arrays and map the peers' memory (nothing is switched
+        on yet: see the two-phase comment in __init__)"""
         lib = self.lib
         self._bar = None
         if self.dist is not None and self.world > 1:
@@ -576,20 +589,25 @@ class Model:
             self.dist.all_gather_object(everyone, mine)
             if any(h is None for _, h, _ in everyone):
                 raise ScytheError(_lib.SB_ECUDA, "CUDA IPC handles are not available on every rank")
+            if os.environ.get("SB_TEST_P2P_FAIL_RANK") == str(self.rank):     # test hook: an asymmetric mapping failure
+                raise ScytheError(_lib.SB_ECUDA, "cudaIpcOpenMemHandle failure injected on this rank (SB_TEST_P2P_FAIL_RANK)")
             for r, hrecv, tiles in everyone:
                 if r == self.rank:
                     continue
                 lib.check(lib.sb_model_ipc_open(self.handle, 0, r, (C.c_ubyte * 64).from_buffer_copy(hrecv)))
                 for t, h in tiles.items():
                     lib.check(lib.sb_model_ipc_open(self.handle, 1, t, (C.c_ubyte * 64).from_buffer_copy(h)))
-        lib.check(lib.sb_model_p2p_enable(self.handle))
 
     def _barrier(self):
         """stream-ordered rendezvous (a one-element all-reduce on the compute stream)"""
         if self.dist is None or self.world == 1:
             return
+        import torch
+        if self.dist.get_backend() == "nccl" and torch.cuda.current_stream().cuda_stream != 0:
+            # the library works on the legacy default stream (sb_model_create(stream = NULL)); the rendezvous only orders the
+            # peer stores before the owner's solve if torch enqueues it on that same stream
+            raise ScytheError(_lib.SB_EINVAL, "Model exchange must be called with torch's default CUDA stream current")
         if self._bar is None:
-            import torch
             dev = f"cuda:{torch.cuda.current_device()}" if self.dist.get_backend() == "nccl" else "cpu"
             self._bar = torch.zeros(1, dtype=torch.float64, device=dev)
         self.dist.all_reduce(self._bar)
@@ -720,26 +738,52 @@ class Model:
     # -- checkpoint / restart (the reference's restart drops the AB3 history) -----------------
     _HIST = {"var_np1": 0, "expdot_nm1": 2, "expdot_nm2": 3, "impdot_nm1": 5, "impdot_nm2": 6}
 
+    def checkpoint_path(self, path) -> str:
+        """File this rank writes / reads: ``path`` itself for a single process, ``<stem>.tiles<first>-<last>.npz`` per
+        rank in a distributed run (every rank calls checkpoint() with the same path)."""
+        path = str(path)
+        stem = path[:-4] if path.endswith(".npz") else path
+        if self.world > 1:
+            stem += f".tiles{self.tile_first}-{self.tile_first + self.tile_count - 1}"
+        return stem + ".npz"
+
     def checkpoint(self, path):
-        """Write step counter + var_np1 + AB3 (and semi-implicit) history of the local tiles to ``path`` (.npz)."""
+        """Write step counter + var_np1 + AB3 (and semi-implicit) history of the local tiles to ``path`` (.npz), with the
+        grid / equation-set identity that restore() checks."""
         semi = bool(self.model.options.get("semiimplicit", self.model.options.get(":semiimplicit", False)))
         keys = [k for k in self._HIST if semi or not k.startswith("impdot")]
-        data = {"t": np.int64(self.t), "tile_first": np.int64(self.tile_first)}
+        data = {"t": np.int64(self.t), "tile_first": np.int64(self.tile_first), "tile_count": np.int64(self.tile_count),
+                "num_tiles": np.int64(self.num_tiles), "equation_set": np.array(self.model.equation_set),
+                "V": np.int64(self.patch.V), "N_patch": np.int64(self.patch.N),
+                "tile_N": np.array([g.N for g in self.tiles], dtype=np.int64)}
         for i in range(len(self.tiles)):
             for k in keys:
                 data[f"{k}_{i}"] = self.state(i, k)
-        np.savez(path, **data)
+        out = self.checkpoint_path(path)
+        np.savez(out, **data)
+        return out
 
     def restore(self, path):
         """Exact restart from :meth:`checkpoint`: the history goes back in, the spectral state (B -> A) is
         rebuilt from var_np1 exactly as the step that produced it did, and stepping continues at t+1."""
-        data = np.load(path)
+        data = np.load(self.checkpoint_path(path))
         if int(data["tile_first"]) != self.tile_first:
             raise ValueError("checkpoint belongs to a different rank / tile range")
+        if "num_tiles" in data:     # identity written since round 2
+            want = dict(num_tiles=self.num_tiles, tile_count=self.tile_count, V=self.patch.V, N_patch=self.patch.N)
+            for k, v in want.items():
+                if int(data[k]) != int(v):
+                    raise ValueError(f"checkpoint does not match this model: {k} = {int(data[k])}, expected {int(v)}")
+            if str(data["equation_set"]) != self.model.equation_set:
+                raise ValueError(f"checkpoint is of equation set {data['equation_set']}, this model runs {self.model.equation_set}")
+            if [int(n) for n in data["tile_N"]] != [g.N for g in self.tiles]:
+                raise ValueError("checkpoint tiles have different sizes from this model's tiles")
         for i in range(len(self.tiles)):
             for k, which in self._HIST.items():
                 if f"{k}_{i}" in data:
                     a = np.asfortranarray(data[f"{k}_{i}"], dtype=np.float64)
+                    if a.shape != (self.tiles[i].N, self.tiles[i].V):
+                        raise ValueError(f"checkpoint array {k}_{i} has shape {a.shape}")
                     self.lib.check(self.lib.sb_model_set_state(self.handle, i, which, _ptr(a)))
         self.lib.check(self.lib.sb_model_tendency(self.handle))
         if self.world == 1 and self.columns:

@@ -537,16 +537,22 @@ static void require_device() {
 #endif
 }
 
+static void grid_free(sb_grid* G);
 static sb_grid* grid_new(const sb_grid_params* gp, int device, void* stream) {
   if (!gp) throw std::invalid_argument("grid params is NULL");
   if (gp->nvars < 1) throw std::invalid_argument("nvars >= 1 required");
   require_device();
-  std::unique_ptr<sb_grid> G(new sb_grid());
-  copy_params(G.get(), gp);
-  G->device = device;
-  G->stream = (cudaStream_t)stream;
-  build_grid(G.get());
-  return G.release();
+  sb_grid* G = new sb_grid();
+  try {
+    copy_params(G, gp);
+    G->device = device;
+    G->stream = (cudaStream_t)stream;
+    build_grid(G);
+  } catch (...) {          // e.g. out of memory half-way: release every device allocation made so far
+    grid_free(G);
+    throw;
+  }
+  return G;
 }
 
 static void grid_free(sb_grid* G) {
@@ -604,7 +610,7 @@ static void calc_tile_sizes(const sb_grid_params* gp, int ntiles, double* out) {
 }
 
 static void check_cfl(sb_grid* G, int32_t* var, int64_t* index) {
-  if (!G->physical) throw std::invalid_argument("grid has no physical array");
+  G->ensure_physical();
   G->materialize_slot0();
   long long init = 0x7fffffffffffffffLL;
   CU(cudaMemcpyAsync(G->d_nan, &init, sizeof(init), cudaMemcpyHostToDevice, G->stream));
@@ -861,13 +867,20 @@ static void build_column_ops(sb_model* M) {
   }
 }
 
+static void model_free(sb_model* M);
 static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first, int tile_count, int device, void* stream) {
   if (!mp || !mp->grid || !mp->equation_set) throw std::invalid_argument("NULL model parameter");
   if (!(mp->ts > 0)) throw std::invalid_argument("ts must be positive");
   if (ntiles < 1 || tile_first < 0 || tile_count < 1 || tile_first + tile_count > ntiles)
     throw std::invalid_argument("bad tile range");
   require_device();
-  std::unique_ptr<sb_model> M(new sb_model());
+  struct Guard {          // a throw below (bad parameter, out of memory) frees every device allocation made so far
+    sb_model* m;
+    ~Guard() { if (m) model_free(m); }
+    sb_model* get() const { return m; }
+    sb_model* operator->() const { return m; }
+    sb_model* release() { sb_model* r = m; m = nullptr; return r; }
+  } M{new sb_model()};
   M->gp = *mp->grid;
   const int V = mp->grid->nvars;
   auto cp = [&](const int32_t* src, std::vector<int32_t>& dst) { dst.assign(V, 0); if (src) std::copy(src, src + V, dst.begin()); };
@@ -905,20 +918,21 @@ static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first
     tp.tile_num = t + 2;
     tp.BCL = r0.data();  // tiles carry no radial BCs (src/semiimplicit.jl:163-164)
     tp.BCR = r0.data();
-    TileState ts;
+    M->tiles.emplace_back();
+    TileState& ts = M->tiles.back();     // registered before anything is allocated: model_free sees partial tiles
     ts.grid = grid_new(&tp, device, stream);
     if (ntiles == 1) {   // one tile == the patch: its B *is* the shared B (no clear / assemble pass per step)
       CU(cudaFree(ts.grid->spectralB));
       ts.grid->spectralB = M->patch->spectralB;
       ts.grid->owns_B = false;
     }
-    ts.grid->ensure_physical();
+    // the tile's physical [N,V,D] array is allocated on first use (a non-fused K3, an API read): the default fused
+    // step never touches it (7.2 GB at C4)
     const long long n = ts.grid->dg.N * V;
     ts.var_np1 = dev_zeros(n, M->stream);
     for (int k = 0; k < 3; ++k) ts.expd[k] = dev_zeros(n, M->stream);
     if (M->semiimplicit)
       for (int k = 0; k < 3; ++k) ts.impd[k] = dev_zeros(n, M->stream);
-    M->tiles.push_back(ts);
   }
   build_column_ops(M.get());
   return M.release();

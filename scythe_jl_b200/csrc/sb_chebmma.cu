@@ -205,7 +205,7 @@ static void launch_inv_z_mma_t(const LaunchCtx& c, const DevGrid& g, const ZTile
   cudaError_t e = cudaFuncSetAttribute(k_inv_z_mma<CB, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
   const int nwork = ntiles * (32 / COLS) * nvars;
-  const int cap = 148 * (32 / COLS);
+  const int cap = sb_sm_count() * (32 / COLS);
   const int gx = nwork < cap ? nwork : cap;
   SB_LAUNCH((k_inv_z_mma<CB, COLS>), dim3(gx), dim3(COLS * 16), smem, c.stream, g, tiles, ntiles, nvars, var0, nfields, in,
             in_fstride, in_vstride, phys, parB, c.need.zmask, c.need.zsel);
@@ -376,7 +376,7 @@ void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* t
   const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0;
   const size_t smem = (size_t)2 * ZF_NF * 2 * ZM_KK * (16 + 4) * sizeof(double) + (size_t)ZF_NF * g.bz * 16;
   const int nwork = ntiles * 2;
-  const int gx = nwork < 148 * 2 ? nwork : 148 * 2;
+  const int gx = nwork < sb_sm_count() * 2 ? nwork : sb_sm_count() * 2;
   cudaError_t e;
   if (al16) {
     e = cudaFuncSetAttribute(k_inv_z_advection<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -509,7 +509,7 @@ void launch_fwd_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
   // and ran one per SM (ncu: 1.33 waves)
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd_z_mma, FZ_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 3;
-  const int cap = 148 * per_sm;
+  const int cap = sb_sm_count() * per_sm;
   const int gx = nwork < cap ? nwork : cap;
   SB_LAUNCH(k_fwd_z_mma, dim3(gx), dim3(FZ_THREADS), smem, c.stream, g, tiles, ntiles, nvars, in, in_vstride, mirror,
             mirror_vstride, out, out_vstride, fwdB);

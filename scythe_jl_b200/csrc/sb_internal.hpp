@@ -86,6 +86,9 @@ struct DevGrid {
   double wq[3];
 };
 
+// number of SMs of the current device (148 on B200), queried once per device; grids of the persistent kernels are sized from it
+int sb_sm_count();
+
 struct ZTile { int hcol0; int ncols; long long out_base; int out_stride; int pad; };
 struct LWork { int r; int row0; int nrows; int pad; };
 

@@ -512,7 +512,7 @@ void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqP
       static const bool v1 = std::getenv("SB_TCBL_V1") != nullptr;   // A/B switch
       if (a.colfrag && !v1 && g.zDim % 8 == 0 && g.zDim <= 64) {
         long long ngroups = (g.hpoints + HB_COLS - 1) / HB_COLS;
-        long long blocks = ngroups < 148 * 8 ? ngroups : 148 * 8;
+        long long blocks = ngroups < sb_sm_count() * 8 ? ngroups : sb_sm_count() * 8;
         size_t smem = ((size_t)6 * HB_COLS * (g.zDim + 4) + 2 * HB_COLS) * sizeof(double);
         SB_LAUNCH(k_heightresolved_bl2, dim3((unsigned)blocks), dim3(g.zDim, HB_COLS), smem, c.stream, g, p, a, tstep, ngroups);
         break;

@@ -737,7 +737,7 @@ static void launch_inv2(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   const size_t smem = RCfg<LOG2L>::SMEM;
   cudaError_t e = cudaFuncSetAttribute(k_inv_l2<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int total = nwork * nvars, gx = total < 148 ? total : 148;
+  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
   SB_LAUNCH(k_inv_l2<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
             c.need.lmask);
@@ -767,7 +767,7 @@ static void launch_fwd2(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   const size_t smem = RCfg<LOG2L>::SMEM;
   cudaError_t e = cudaFuncSetAttribute(k_fwd_l2<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int total = nwork * nvars, gx = total < 148 ? total : 148;
+  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
   SB_LAUNCH(k_fwd_l2<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs);
   e = cudaGetLastError();
@@ -813,7 +813,7 @@ void fft3_class_tables(int L2, std::vector<double>& tab) {
 
 size_t fft3_scratch_doubles(int L) {
   const int L2 = L / 3, T = L2 / 16, ngroups = (512 / T) / 3;
-  return (size_t)2 * 148 * ngroups * 2 * (3 * L2 / 2);
+  return (size_t)2 * sb_sm_count() * ngroups * 2 * (3 * L2 / 2);
 }
 
 template <int LOG2L2>
@@ -823,7 +823,7 @@ static void launch_inv3(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   typedef R3Cfg<LOG2L2> C;
   cudaError_t e = cudaFuncSetAttribute(k_inv_l3<LOG2L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int total = nwork * nvars, gx = total < 148 ? total : 148;
+  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
   SB_LAUNCH(k_inv_l3<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEM, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
             c.need.lmask);
@@ -850,7 +850,7 @@ static void launch_fwd3(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   typedef R3Cfg<LOG2L2> C;
   cudaError_t e = cudaFuncSetAttribute(k_fwd_l3<LOG2L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int total = nwork * nvars, gx = total < 148 ? total : 148;
+  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
   SB_LAUNCH(k_fwd_l3<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEM, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs,
             reinterpret_cast<double2*>(scratch));

@@ -19,6 +19,23 @@
 
 namespace sb {
 
+int sb_sm_count() {
+#ifdef SB_EMU
+  return 4;                    // the emulation runs blocks one after another: a small persistent grid keeps the tests fast
+#else
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+#endif
+}
+
 #define SB_CHECK_LAUNCH()                                                             \
   do {                                                                                \
     cudaError_t e_ = cudaGetLastError();                                              \
@@ -98,7 +115,8 @@ void launch_fwd_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int 
   if (nwarps < 1) nwarps = 1;
   size_t smem = ((size_t)g.zDim * g.bzp + (size_t)ZT_COLS * (g.zDim | 1)) * sizeof(double);
   opt_in_smem(k_fwd_z, smem);
-  int gx = ntiles < 148 * 4 ? ntiles : 148 * 4;
+  const int nsm = sb_sm_count();
+  int gx = ntiles < nsm * 4 ? ntiles : nsm * 4;
   SB_LAUNCH(k_fwd_z, dim3(gx, nvars), dim3(32 * nwarps), smem, c.stream, g, tiles, ntiles, in, in_vstride,
             mirror, mirror_vstride, out, out_vstride, fwdT);
   SB_CHECK_LAUNCH();
@@ -294,7 +312,8 @@ void launch_inv_z_par(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
   ProfScope prof_scope_(c, "inv_z");
   size_t smem = (size_t)nfields * 32 * ZPAR_ZS * sizeof(double);
   opt_in_smem(k_inv_z_par, smem);
-  int gx = ntiles < 148 * 2 * 4 ? ntiles : 148 * 2 * 4;
+  const int nsm = sb_sm_count();
+  int gx = ntiles < nsm * 2 * 4 ? ntiles : nsm * 2 * 4;
   SB_LAUNCH(k_inv_z_par, dim3(gx, nvars), dim3(256), smem, c.stream, g, tiles, ntiles, var0, nfields, in, in_fstride,
             in_vstride, phys, parM);
   SB_CHECK_LAUNCH();
@@ -310,7 +329,8 @@ void launch_inv_z(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int 
   int nwarps = ngroups < 16 ? ngroups : 16;
   size_t smem = ((size_t)3 * g.bz * zp + (size_t)nfields * g.bz * 32) * sizeof(double);
   opt_in_smem(k_inv_z, smem);
-  int gx = ntiles < 148 * 2 ? ntiles : 148 * 2;
+  const int nsm = sb_sm_count();
+  int gx = ntiles < nsm * 2 ? ntiles : nsm * 2;
   SB_LAUNCH(k_inv_z, dim3(gx, nvars), dim3(32 * nwarps), smem, c.stream, g, tiles, ntiles, var0, nfields, in,
             in_fstride, in_vstride, phys, invM);
   SB_CHECK_LAUNCH();
@@ -1229,7 +1249,7 @@ __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src,
 void launch_copy(const LaunchCtx& c, double* dst, const double* src, long long n) {
   ProfScope prof_scope_(c, "copy");
   long long blocks = (n + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sb_sm_count() * 16) blocks = sb_sm_count() * 16;
   if (blocks < 1) blocks = 1;
   SB_LAUNCH(k_copy, dim3((unsigned)blocks), dim3(256), 0, c.stream, dst, src, n);
   SB_CHECK_LAUNCH();
@@ -1259,7 +1279,7 @@ void launch_nan_scan(const LaunchCtx& c, const double* phys, long long N, int V,
   ProfScope prof_scope_(c, "nan_scan");
   long long total = N * V;
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > sb_sm_count() * 8) blocks = sb_sm_count() * 8;
   if (blocks < 1) blocks = 1;
   SB_LAUNCH(k_nan_scan, dim3((unsigned)blocks), dim3(256), 0, c.stream, phys, total, result);
   SB_CHECK_LAUNCH();

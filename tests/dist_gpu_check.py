@@ -1,6 +1,9 @@
-"""Manual multi-GPU check (torchrun, NCCL): every exchange mode must give bit-identical patch coefficients.
+"""Multi-GPU check (torchrun, NCCL): every exchange mode must give bit-identical tile states, and those states must
+match the oracle run with the same number of tiles.
     torchrun --nproc-per-node 2 tests/dist_gpu_check.py
-Not collected by pytest (needs >= 2 GPUs); the same host logic is covered on CPU by test_distributed_gloo.py."""
+Run by tests/test_gpu_parity.py::test_multi_gpu_exchange_modes (skipped below 2 GPUs) and, in reduced form, by
+bench.py's multi-rank preflight (`parity_nranks` in the bench line).  The same host logic is covered on CPU by
+test_distributed_gloo.py."""
 import os
 import sys
 from pathlib import Path
@@ -15,7 +18,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 
 def main():
-    from helpers import model_cases, pkg_model
+    from helpers import STATE_TOL, model_cases, pkg_model, rel_err, run_oracle
     from oracle import grids as G
     from scythe_jl_b200 import _lib
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -57,6 +60,24 @@ def main():
         m.run(case["n"])
         same = np.array_equal(m.state(0, "var_np1"), outs[(name, "columns-p2p")])
         print(f"rank {rank} {name}: needed/fused slots == all slots: {same}", flush=True)
+        assert same
+        m.close()
+        dist.barrier()
+        # parity proper: this rank's tile against the oracle integrated with the same tiles
+        omt = run_oracle(case, ntiles).mtiles[rank]
+        for ex in ("torch", "columns-p2p"):
+            err = rel_err(outs[(name, ex)], omt.var_np1)
+            print(f"rank {rank} {name} {ex}: vs oracle rel_err={err:.2e} (tol {STATE_TOL:g})", flush=True)
+            assert err <= STATE_TOL
+        # asymmetric peer-mapping failure: rank 1 cannot map its peers -> every rank agrees to use messages, nobody enables p2p
+        os.environ["SB_TEST_P2P_FAIL_RANK"] = "1"
+        m = pkg_model(case, ntiles, lib, distributed=True, device=local)      # default exchange (columns-p2p under NCCL)
+        del os.environ["SB_TEST_P2P_FAIL_RANK"]
+        assert (m.exchange, m.p2p) == ("columns", False), (m.exchange, m.p2p)
+        m.initialize_tiles(ics)
+        m.run(case["n"])
+        same = np.array_equal(m.state(0, "var_np1"), outs[(name, "columns")])
+        print(f"rank {rank} {name}: injected IPC failure on rank 1 -> all ranks fell back to messages, state identical: {same}", flush=True)
         assert same
         m.close()
         dist.barrier()

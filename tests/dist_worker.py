@@ -30,12 +30,32 @@ def main(case_name, out_path, lib_path, ntiles, exchange="columns"):
     tp = G.calcTileSizes(patch, int(ntiles))
     pts = np.concatenate([[0], np.cumsum(tp[4]).astype(np.int64)])
     ics = [case["ic"][pts[t]:pts[t + 1]] for t in range(m.tile_first, m.tile_first + m.tile_count)]
+    m_exchange = (m.exchange, m.p2p)
     m.initialize_tiles(ics)
     m.run(case["n"])
     out = m.output()
     np.save(f"{out_path}.rank{rank}.npy", out)
     dist.barrier()
     m.close()
+    if os.environ.get("SB_TEST_P2P_FAIL_RANK") is not None:
+        # asymmetric peer-mapping failure: every rank must have dropped to the message form, none enabled p2p
+        assert m_exchange == ("columns", False), m_exchange
+    if os.environ.get("SB_TEST_CHECKPOINT"):      # every rank checkpoints to the SAME path: per-rank files, exact restart
+        a = pkg_model(case, int(ntiles), lib, distributed=True, exchange=exchange)
+        a.initialize_tiles(ics)
+        a.run(2)
+        written = a.checkpoint(f"{out_path}.ck.npz")
+        assert f".tiles{a.tile_first}-" in written
+        a.run(2)
+        b = pkg_model(case, int(ntiles), lib, distributed=True, exchange=exchange)
+        b.restore(f"{out_path}.ck.npz")
+        assert b.t == 2
+        b.run(2)
+        for i in range(len(a.tiles)):
+            for k in ("var_np1", "expdot_nm1", "expdot_nm2"):
+                assert np.array_equal(a.state(i, k), b.state(i, k)), (rank, i, k)
+        dist.barrier()
+        a.close(); b.close()
     if os.environ.get("SB_TEST_HOST_PIPELINE"):   # pipelined host-driven stepping with the exchange between ranks inside the cycle
         from helpers import check_host_pipeline
         check_host_pipeline(case, lib, ntiles=int(ntiles), nsteps=3, distributed=True, exchange=exchange)

@@ -227,6 +227,66 @@ def model_cases(small=True):
     return cases
 
 
+def benchmarked_shape_cases():
+    """N-step cases at the shapes bench.py and profiles/microbench time: 64 levels select other
+    kernel instantiations than the 10/16-level cases above (k_heightresolved_bl2 runs (64, 8)-thread blocks with
+    [zDim/8][zDim/4][32] fragments, k_inv_z_advection<16> its 64-level parity split, k_euler_test its 64 x 64 composite
+    column operators), and 100 radial cells is the reference's own production grid (C2).  GPU tests only: the oracle
+    needs 2-8 s for each."""
+    cases = {}
+    # C2, /root/reference/models/cha_bell2024/Oneway_ShallowWater_Slab.jl:1-40 (100 cells, 181,800 points, 6 variables)
+    gp, ic, prm = _slab_case(100)
+    cases["Oneway_ShallowWater_Slab_C2_100cells"] = dict(gp=gp, eq="Oneway_ShallowWater_Slab", prm=prm, ts=3.0, n=4, ic=ic,
+                                                         tiles=(1, 2))
+    # LinearAdvectionRLZ through the fused Chebyshev synthesis + tendency + AB3 kernel at the C4 level count
+    gpf = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=24, zmin=0, zmax=1e3, zDim=64,
+                           vars={"h": 1, "u": 2, "v": 3})
+    r, l, z = G.createGrid(gpf).getGridpoints().T
+    icf = np.zeros((r.size, 3))
+    icf[:, 0] = np.exp(-((r * np.cos(l) - 3e4) ** 2 + (r * np.sin(l)) ** 2) / 4e8) * np.cos(z / 400.0)
+    icf[:, 1] = 5 * np.cos(l) * (1 + 0.2 * np.sin(z / 300.0))
+    icf[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
+    cases["LinearAdvectionRLZ_z64_24cells_fused"] = dict(gp=gpf, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=4,
+                                                         ic=icf, tiles=(1, 2))
+    # the TC boundary-layer set (bench.py `tcbl`) at 64 levels
+    names = ["h", "u", "v", "ub", "vb", "wb"]
+    gp = G.GridParameters(geometry="RLZ", xmin=0, xmax=2e5, num_cells=8, zmin=0, zmax=2e3, zDim=64,
+                          vars={n: i + 1 for i, n in enumerate(names)},
+                          BCL={"h": spl.R1T1, "u": spl.R1T0, "v": spl.R1T0, "ub": spl.R1T0, "vb": spl.R1T0, "wb": spl.R1T1})
+    r, l, z = G.createGrid(gp).getGridpoints().T
+    Rmax, V0 = 5e4, 30.0 / 5e4
+    vbar = np.where(r < Rmax, V0 * r, Rmax * Rmax * V0 / r)
+    ic = np.zeros((r.size, 6))
+    ic[:, 0] = 50 * np.exp(-(r / 1e5) ** 2) * (1 + 0.1 * np.cos(l))
+    ic[:, 1] = 0.05 * vbar * np.sin(l)
+    ic[:, 2] = vbar
+    ic[:, 3] = -0.2 * vbar * np.exp(-z / 500)
+    ic[:, 4] = vbar * (1 - np.exp(-(z + 50) / 300))
+    cases["Oneway_ShallowWater_HeightResolvedBL_z64"] = dict(
+        gp=gp, eq="Oneway_ShallowWater_HeightResolvedBL",
+        prm=dict(g=9.81, Kh=1500.0, Cd=2.4e-3, Hfree=2000.0, f=5e-5, Um=3.0, Vm=-2.0), ts=2.0, n=3, ic=ic, tiles=(1, 2))
+    # C3: RZ 334 cells x 64 levels, Euler_test with the semi-implicit adjustment (/root/reference/src/testModels.jl:100-215,
+    # src/semiimplicit.jl:521-597)
+    gp = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=334, zmin=0, zmax=1e4, zDim=64,
+                          vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5})
+    zc = ch.mish_points(ch.ChebyshevParameters(0, 1e4, 64, 43))
+    T = 280.0
+    rho = (1000e2 / (T * M.Rd)) * np.exp(-M.gravity * zc / (M.Rd * T))
+    xibar = np.log(rho / M.rho_d0)
+    sbar = M.Cvd * np.log(T / M.T_0) - M.Rd * np.log(rho / M.rho_d0)
+    mubar = 2e-3 * np.exp(-zc / 3e3) - 5e-4
+    ref = M.exact_reference_state_from_profiles(gp, sbar, xibar, mubar, mubar)
+    x, z = G.createGrid(gp).getGridpoints().T
+    ic = np.zeros((x.size, 5))
+    ic[:, 0] = 2.0 * np.exp(-((x) ** 2 + (z - 3e3) ** 2) / 2e3 ** 2)
+    ic[:, 2] = 1e-4 * np.exp(-((x - 2e3) ** 2 + (z - 2e3) ** 2) / 2e3 ** 2)
+    ic[:, 3] = 1.0 * np.sin(z / 2e3)
+    cases["Euler_test_semiimplicit_C3_334cells_z64"] = dict(gp=gp, eq="Euler_test", prm={"K": 50.0}, ts=1.0, n=4, ic=ic,
+                                                            tiles=(1, 2), ref=ref,
+                                                            opts={"semiimplicit": True, "exact_reference_state": True})
+    return cases
+
+
 def run_oracle(case, ntiles=1):
     opts = case.get("opts", {"semiimplicit": False})
     mp = M.ModelParameters(ts=case["ts"], integration_time=case["ts"] * case["n"], equation_set=case["eq"],

@@ -86,3 +86,57 @@ def _dims_only(gp):
 def test_too_many_tiles_is_a_domain_error(lib):
     with pytest.raises(S.DomainError):
         S.calcTileSizes(S.GridParameters(geometry="R", xmin=0, xmax=1, num_cells=8), 3, lib=lib)
+
+
+# ---------------------------------------------------------------- the Julia shim (shim/src/ScytheB200.jl) vs the header
+SHIM = (ROOT / "shim" / "src" / "ScytheB200.jl").read_text()
+
+
+def _split_top(argstr):
+    """split a comma list at nesting depth 0"""
+    out, depth, cur = [], 0, ""
+    for ch in argstr:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _header_arity():
+    ar = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(sb_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", HEADER, re.S):
+        args = m.group(2).strip()
+        ar[m.group(1)] = 0 if args in ("", "void") else len(_split_top(args))
+    return ar
+
+
+def test_julia_shim_binds_only_exported_symbols(lib):
+    """Julia is not in the image, so the shim cannot run here; what can be checked on CPU is that every `ccall` names a
+    symbol the library exports and passes as many arguments as the header declares, and that the three mirrored structs
+    have the header's field counts."""
+    arity = _header_arity()
+    calls = re.findall(r"ccall\(sym\(:(sb_[a-z_0-9]+)\),\s*\w+,\s*\(([^)]*(?:\{[^}]*\}[^)]*)*)\)", SHIM)
+    assert len(calls) >= 25
+    for name, types in calls:
+        assert hasattr(lib.dll, name), f"shim calls {name}, which the library does not export"
+        n = len([t for t in _split_top(types) if t])
+        assert n == arity[name], f"shim passes {n} arguments to {name}, header declares {arity[name]}"
+
+    def julia_fields(struct):
+        body = re.search(r"struct " + struct + r"\b[^\n]*\n(.*?)\nend", SHIM, re.S).group(1)
+        return len([ln for ln in body.splitlines() if "::" in ln])
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct " + struct + r" \{(.*?)\} " + struct + ";", HEADER, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return sum(len(stmt.split(",")) for stmt in body.split(";") if stmt.strip())
+    assert julia_fields("GridParamsC") == c_fields("sb_grid_params") == 16
+    assert julia_fields("GridInfoC") == c_fields("sb_grid_info") == 13
+    assert julia_fields("ModelParamsC") == c_fields("sb_model_params") == 14

@@ -16,12 +16,17 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.mark.parametrize("case_name,ntiles,exchange", [("LinearAdvection1D", 2, "torch"), ("LinearAdvection1D", 2, "columns"),
-                                                       ("LinearAdvectionRLZ", 2, "columns"), ("LinearAdvectionRZ", 4, "columns")])
+                                                       ("LinearAdvectionRLZ", 2, "columns"), ("LinearAdvectionRZ", 4, "columns"),
+                                                       ("LinearAdvectionRL", 2, "columns-p2p")])
 def test_two_ranks_match_single_process_and_oracle(case_name, ntiles, exchange, emu_lib, tmp_path):
     out = tmp_path / "out"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + os.getpid() % 2000), OMP_NUM_THREADS="1")
     if case_name == "LinearAdvection1D":     # also: Model.cycle_host == set_state/cycle/get_state across two ranks
         env["SB_TEST_HOST_PIPELINE"] = "1"
+    if case_name == "LinearAdvectionRLZ":    # also: checkpoint() on every rank with one path, restore(), exact continuation
+        env["SB_TEST_CHECKPOINT"] = "1"
+    if exchange == "columns-p2p":            # peer mapping fails on rank 1 only: all ranks must agree to fall back before enabling
+        env.update(SB_P2P_FALLBACK="1", SB_TEST_P2P_FAIL_RANK="1")
     nsteps = min(model_cases()[case_name]["n"], 4)
     env["SB_TEST_STEPS"] = str(nsteps)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import scythe_jl_b200 as S
-from helpers import (STATE_TOL, TRANSFORM_TOL, check_model, check_needed_slots, check_transforms, model_cases, pkg_model,
+from helpers import (STATE_TOL, TRANSFORM_TOL, benchmarked_shape_cases, check_model, check_needed_slots, check_transforms, model_cases, pkg_model,
                      rel_err, slot_errs, to_pkg, transform_cases)
 from oracle import grids as G
 from oracle import splines as spl
@@ -12,6 +12,7 @@ from oracle import splines as spl
 pytestmark = pytest.mark.gpu
 T_CASES = transform_cases()
 M_CASES = model_cases()
+B_CASES = benchmarked_shape_cases()
 
 
 def test_native_library_is_the_product_build(gpu_lib):
@@ -29,6 +30,13 @@ def test_transforms_match_oracle(name, gpu_lib):
 @pytest.mark.parametrize("name", sorted(M_CASES))
 def test_timestep_matches_oracle(name, gpu_lib):
     assert check_model(M_CASES[name], gpu_lib) <= STATE_TOL
+
+
+@pytest.mark.parametrize("name", sorted(B_CASES))
+def test_timestep_matches_oracle_at_benchmarked_shapes(name, gpu_lib):
+    """N-step state vs the oracle at the shapes that are timed: C2 (100 cells), C3 (334 cells x 64 levels, semi-implicit
+    Euler_test), the TC boundary-layer set and the fused LinearAdvectionRLZ kernel at 64 levels."""
+    assert check_model(B_CASES[name], gpu_lib) <= STATE_TOL
 
 
 @pytest.mark.parametrize("name", sorted(M_CASES))
@@ -337,3 +345,48 @@ def test_error_behaviour(gpu_lib):
     with pytest.raises(S.ScytheError, match="NaN found in variable q at index6"):
         S.checkCFL(g)
     g.close()
+
+
+def test_checkpoint_restart_is_exact_on_device(gpu_lib, tmp_path):
+    """Model.checkpoint / restore on the real device (fused K3+K4 default path, 16 levels; and the semi-implicit set with
+    its impdot history): 4 steps straight == 2 steps, checkpoint, restore into a fresh model, 2 more steps, bit for bit."""
+    for name, ntiles in (("LinearAdvectionRLZ_z16_fused", 2), ("Euler_test_semiimplicit", 1)):
+        case = M_CASES[name]
+        a = pkg_model(case, ntiles, gpu_lib)
+        a.initialize(case["ic"])
+        a.run(2)
+        a.checkpoint(tmp_path / f"{name}.npz")
+        a.run(2)
+        b = pkg_model(case, ntiles, gpu_lib)
+        b.restore(tmp_path / f"{name}.npz")
+        assert b.t == 2
+        b.run(2)
+        for i in range(ntiles):
+            for k in ("var_np1", "expdot_nm1", "expdot_nm2"):
+                assert np.array_equal(a.state(i, k), b.state(i, k)), (name, i, k)
+        a.close(); b.close()
+    other = pkg_model(M_CASES["LinearAdvectionRLZ"], 2, gpu_lib)
+    with pytest.raises(ValueError):          # a checkpoint of another grid is refused before anything is written
+        other.restore(tmp_path / "LinearAdvectionRLZ_z16_fused.npz")
+    other.close()
+
+
+def test_multi_gpu_exchange_modes(gpu_lib):
+    """Two ranks on two GPUs under torchrun/NCCL (tests/dist_gpu_check.py): every exchange transport incl. the default
+    CUDA-IPC peer stores gives identical tile states, those match the oracle, and an injected one-sided IPC failure
+    makes every rank fall back.  Needs >= 2 GPUs (the single-GPU box of the round-end run skips it; bench.py's
+    multi-rank preflight covers the default path there)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    if gpu_lib.sb_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    port = str(29500 + os.getpid() % 2000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", port, str(root / "tests" / "dist_gpu_check.py")],
+                       env=dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port), capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "vs oracle rel_err" in r.stdout
