@@ -18,7 +18,7 @@ REPO = ROOT.parent
 LIB = ROOT / "libscythe_b200.so"
 EMU_DIR = REPO / "tests" / "_emu"
 EMU_LIB = EMU_DIR / "libscythe_b200_emu.so"
-SOURCES = ["sb_transforms.cu", "sb_ringfft.cu", "sb_ringfft2.cu", "sb_chebmma.cu", "sb_model.cu", "sb_api.cpp", "sb_tables.cpp"]
+SOURCES = ["sb_transforms.cu", "sb_ringfft.cu", "sb_ringfft2.cu", "sb_ringfft4.cu", "sb_chebmma.cu", "sb_model.cu", "sb_api.cpp", "sb_tables.cpp"]
 HEADERS = ["sb_internal.hpp", "sb_fftcore.hpp", "sb_eqcore.hpp", "cuda_emu.h", "../../include/scythe_b200.h"]
 
 NVCC_FLAGS = ["-O3", *os.environ.get("SB_NVCC_EXTRA", "").split(), "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -15,6 +15,7 @@ std::vector<std::unique_ptr<FiberBarrier>> g_warp_barriers;
 double g_warp_buf[64][32];
 double g_warp_buf2[64][32];
 unsigned char* g_dyn_smem = nullptr;
+uint32_t g_tmem[128][512];
 
 static std::unique_ptr<FiberBarrier> g_named[16];
 void named_barrier(int id, int nthreads) {

@@ -169,6 +169,51 @@ static inline void sb_cp_async8(void* dst, const void* src) { std::memcpy(dst, s
 static inline void sb_prefetch_l2(const void*) {}
 static inline void sb_cp_commit() {}
 template <int N> static inline void sb_cp_wait() {}
+// ---- Blackwell data movement used by sb_ringfft4.cu / sb_chebmma.cu, emulated ------------------------------------
+// Tensor Memory (tcgen05.alloc / st / ld, 32x32b shape): 128 lanes x 512 columns of 32 bits per CTA; warp w reaches lanes
+// 32 (w % 4) .. +31, thread l of the warp its lane 32 (w % 4) + l.  One block is live at a time, so one static array.
+namespace sbemu { extern uint32_t g_tmem[128][512]; }
+static inline uint32_t sb_tmem_alloc(uint32_t* smem_slot, int ncols) { (void)ncols; *smem_slot = 0u; return 0u; }   // warp 0 only
+static inline void sb_tmem_dealloc(uint32_t, int) {}
+static inline uint32_t sb_tmem_warp_base(uint32_t base) { return base + ((uint32_t)(32 * ((sbemu::t_lin / 32) & 3)) << 16); }
+static inline void sb_tmem_st4(uint32_t addr, const uint32_t (&r)[4]) {
+  const int lane = (int)(addr >> 16) + sbemu::t_lin % 32, col = (int)(addr & 0xffffu);
+  for (int q = 0; q < 4; ++q) sbemu::g_tmem[lane][col + q] = r[q];
+}
+static inline void sb_tmem_ld4(uint32_t addr, uint32_t (&r)[4]) {
+  const int lane = (int)(addr >> 16) + sbemu::t_lin % 32, col = (int)(addr & 0xffffu);
+  for (int q = 0; q < 4; ++q) r[q] = sbemu::g_tmem[lane][col + q];
+}
+static inline void sb_tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  const int lane = (int)(addr >> 16) + sbemu::t_lin % 32, col = (int)(addr & 0xffffu);
+  for (int q = 0; q < 16; ++q) r[q] = sbemu::g_tmem[lane][col + q];
+}
+static inline void sb_tmem_wait_st() {}
+static inline void sb_tmem_wait_ld4(uint32_t (&)[4]) {}
+static inline void sb_tmem_wait_ld16(uint32_t (&)[16]) {}
+static inline void sb_tmem_fence_before_sync() {}
+static inline void sb_tmem_fence_after_sync() {}
+// mbarrier + bulk asynchronous copy (cp.async.bulk, SASS UBLKCP): the emulation copies at issue, so a wait never blocks;
+// a copy issued before every reader of the destination has passed a barrier corrupts the emulated run exactly as it
+// could on the device (fibers run to the next barrier one after another), which is what the tests are for.
+// state: low 32 bits = completed phases, high 32 bits = bytes still expected in the current phase (one arriving thread)
+struct sb_mbar_t { unsigned long long state; };
+static inline void sb_mbar_init(sb_mbar_t* b, int) { b->state = 0; }
+static inline void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) { b->state += (unsigned long long)bytes << 32; }
+static inline void sb_mbar_wait(sb_mbar_t* b, unsigned parity) {      // returns once the phase of that parity has completed
+  while (((unsigned)b->state & 1u) == (parity & 1u)) sbemu::fiber_yield();
+}
+static inline void sb_fence_mbar_init() {}
+static inline void sb_fence_proxy_async() {}
+static inline void sb_bulk_g2s(void* dst, const void* src, unsigned bytes, sb_mbar_t* b) {
+  std::memcpy(dst, src, bytes);
+  b->state -= (unsigned long long)bytes << 32;
+  if ((b->state >> 32) == 0) b->state = (unsigned)b->state + 1u;     // all expected bytes have arrived: next phase
+}
+static inline void sb_bulk_s2g(void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
+static inline void sb_bulk_commit() {}
+template <int N> static inline void sb_bulk_wait_read() {}
+template <int N> static inline void sb_bulk_wait_all() {}
 // named barrier for a subset of the block (bar.sync id, nthreads)
 namespace sbemu { void named_barrier(int id, int nthreads); }
 static inline void sb_bar_sync(int id, int nthreads) { sbemu::named_barrier(id, nthreads); }
@@ -197,6 +242,72 @@ template <int N> __device__ __forceinline__ void sb_cp_wait() { asm volatile("cp
 __device__ __forceinline__ void sb_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// ---- Blackwell data movement: Tensor Memory as per-thread table storage, mbarrier + bulk asynchronous copies ----------
+// tcgen05.alloc / st / ld (SASS UTCALLOC? / STTM / LDTM), 32x32b shape: thread l of warp w reads / writes lane
+// 32 (w % 4) + l, consecutive columns.  All of them are warp-collective (.sync.aligned): call from converged warps only.
+__device__ __forceinline__ uint32_t sb_tmem_alloc(uint32_t* smem_slot, int ncols) {   // one warp; result lands in *smem_slot
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  return 0u;
+}
+__device__ __forceinline__ void sb_tmem_dealloc(uint32_t addr, int ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ uint32_t sb_tmem_warp_base(uint32_t base) { return base + ((uint32_t)(32 * ((threadIdx.x >> 5) & 3)) << 16); }
+__device__ __forceinline__ void sb_tmem_st4(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void sb_tmem_ld4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sb_tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sb_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// the loaded registers are in/out operands of the wait, so nothing that reads them can be scheduled above it
+__device__ __forceinline__ void sb_tmem_wait_ld4(uint32_t (&r)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
+}
+__device__ __forceinline__ void sb_tmem_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+__device__ __forceinline__ void sb_tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sb_tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// mbarrier (SASS SYNCS) + cp.async.bulk (SASS UBLKCP): one thread arms the barrier with the byte count and issues the
+// copy; the copy engine moves the bytes with no register or LSU instruction per element and completes the barrier
+struct sb_mbar_t { unsigned long long state; };
+__device__ __forceinline__ void sb_mbar_init(sb_mbar_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void sb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_wait(sb_mbar_t* b, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "SB_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SB_MBAR_DONE;\n\t"
+      "bra SB_MBAR_WAIT;\n\t"
+      "SB_MBAR_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sb_bulk_g2s(void* dst, const void* src, unsigned bytes, sb_mbar_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void sb_bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void sb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 #define SB_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char _sb_dyn_smem[];   \

@@ -721,6 +721,20 @@ struct sb_model {
   double* d_barrier = nullptr;
   int rank = 0, nranks = 1;
   long long extra_launches = 0;
+  // CUDA graphs of three consecutive AB3 steps (sb_model_run on launch-bound grids): after three steps the history
+  // pointer rotation is back where it started, so one graph per rotation phase replays for the rest of the run
+  struct StepGraph {
+#ifndef SB_EMU
+    cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+#endif
+    long long launches[3] = {0, 0, 0};
+    int k3_slots[3] = {-1, -1, -1};
+    bool failed = false;
+    long long replays = 0;
+  } graph;
+  int rot_phase = 0;                        // number of history rotations so far, mod 3
   // ---- distributed spline solve by z-mode planes (sb_model_colsolve_*)
   struct ColSolve {
     bool on = false;
@@ -938,8 +952,14 @@ static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first
   return M.release();
 }
 
+#ifndef SB_EMU
+static void step_graph_free(sb_model* M);
+#endif
 static void model_free(sb_model* M) {
   if (!M) return;
+#ifndef SB_EMU
+  step_graph_free(M);
+#endif
   if (M->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(M->comm);
 #ifndef SB_EMU
   for (void* p : M->cs.ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1031,6 +1051,7 @@ static void tiles_physics(sb_model* M, int64_t t) {
     std::rotate(T.expd, T.expd + 2, T.expd + 3);
     if (M->semiimplicit) std::rotate(T.impd, T.impd + 2, T.impd + 3);
   }
+  M->rot_phase = (M->rot_phase + 1) % 3;
 }
 
 // second half: calcTendency (K1) + own block / halo into the shared B buffer
@@ -1071,6 +1092,102 @@ static void model_step(sb_model* M, int64_t t) {
   if (!M->cs.on) grid_spline(M->patch, M->patch->spectralB);  // splineTransform! :285
 }
 
+
+// ====================================================================================== CUDA graphs of the step
+// Small grids are launch bound (C2, the reference's production configuration: 22 launches of a few microseconds per
+// step): sb_model_run replays three AB3 steps as one graph launch.  Only for a single process (no communicator), with
+// the profiler off, on grids below SB_GRAPH_MAX_POINTS points x variables (default 2^25; SB_GRAPH=0 switches it off).
+static bool step_graph_usable(sb_model* M) {
+#ifdef SB_EMU
+  (void)M;
+  return false;
+#else
+  static const bool off = std::getenv("SB_GRAPH") && std::atoi(std::getenv("SB_GRAPH")) == 0;
+  static const long long maxpts = std::getenv("SB_GRAPH_MAX_POINTS") ? std::atoll(std::getenv("SB_GRAPH_MAX_POINTS")) : (1LL << 25);
+  if (off || M->graph.failed || M->nranks > 1 || M->comm || (M->cs.on && M->cs.nranks > 1)) return false;
+  if (M->patch->dg.N * M->patch->dg.V > maxpts) return false;
+  if (M->patch->prof.on) return false;
+  for (auto& T : M->tiles)
+    if (T.grid->prof.on || T.pipe.on) return false;
+  return true;
+#endif
+}
+
+#ifndef SB_EMU
+static void step_graph_free(sb_model* M) {
+  auto& g = M->graph;
+  for (int k = 0; k < 3; ++k)
+    if (g.exec[k]) { cudaGraphExecDestroy(g.exec[k]); g.exec[k] = nullptr; }
+  if (g.ev_in) cudaEventDestroy(g.ev_in);
+  if (g.ev_out) cudaEventDestroy(g.ev_out);
+  if (g.stream) cudaStreamDestroy(g.stream);
+  g.ev_in = g.ev_out = nullptr;
+  g.stream = nullptr;
+}
+
+// three steps t, t+1, t+2 (all AB3: t >= 3) through the graph of the current rotation phase; captured on first use
+static void step_graph_run3(sb_model* M, int64_t t) {
+  auto& g = M->graph;
+  const int ph = M->rot_phase;
+  if (!g.stream) {
+    CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g.ev_out, cudaEventDisableTiming));
+  }
+  if (g.exec[ph] && g.k3_slots[ph] != M->k3_slots) { cudaGraphExecDestroy(g.exec[ph]); g.exec[ph] = nullptr; }
+  bool first = false;
+  if (!g.exec[ph]) {
+    // capture: every launch of the three steps goes to the capture stream instead of the model's stream
+    std::vector<sb_grid*> grids{M->patch};
+    for (auto& T : M->tiles) grids.push_back(T.grid);
+    std::vector<cudaStream_t> saved;
+    for (sb_grid* G : grids) { saved.push_back(G->stream); G->stream = g.stream; }
+    cudaStream_t saved_m = M->stream;
+    M->stream = g.stream;
+    std::vector<TileState> tiles_before = M->tiles;
+    const int phase_before = M->rot_phase;
+    long long l0 = sb_model_launch_count(M);
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    std::string why = "cudaStreamBeginCapture failed";
+    if (ok) {
+      try {
+        for (int k = 0; k < 3; ++k) model_step(M, t + k);
+      } catch (const std::exception& e) { ok = false; why = e.what(); }
+      cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+      if (ce != cudaSuccess || !graph) { ok = false; if (why.empty() || why == "cudaStreamBeginCapture failed") why = cudaGetErrorString(ce); }
+    }
+    if (ok && cudaGraphInstantiate(&g.exec[ph], graph, 0) != cudaSuccess) { ok = false; why = "cudaGraphInstantiate failed"; g.exec[ph] = nullptr; }
+    if (graph) cudaGraphDestroy(graph);
+    for (size_t i = 0; i < grids.size(); ++i) grids[i]->stream = saved[i];
+    M->stream = saved_m;
+    if (!ok) {                       // nothing ran: put the host-side state back and step eagerly from now on
+      cudaGetLastError();
+      for (size_t i = 0; i < M->tiles.size(); ++i) {
+        for (int k = 0; k < 3; ++k) { M->tiles[i].expd[k] = tiles_before[i].expd[k]; M->tiles[i].impd[k] = tiles_before[i].impd[k]; }
+      }
+      M->rot_phase = phase_before;
+      g.failed = true;
+      for (int k = 0; k < 3; ++k) model_step(M, t + k);
+      return;
+    }
+    g.launches[ph] = sb_model_launch_count(M) - l0;   // counted once by the capture itself
+    g.k3_slots[ph] = M->k3_slots;
+    first = true;
+  } else {
+    // host-side state of three steps: three pointer rotations = identity; slot0_src as model_step leaves it
+    for (auto& T : M->tiles) T.grid->slot0_src = T.var_np1;
+    M->extra_launches += g.launches[ph];
+  }
+  (void)first;
+  CU(cudaEventRecord(g.ev_in, M->stream));
+  CU(cudaStreamWaitEvent(g.stream, g.ev_in, 0));
+  CU(cudaGraphLaunch(g.exec[ph], g.stream));
+  CU(cudaEventRecord(g.ev_out, g.stream));
+  CU(cudaStreamWaitEvent(M->stream, g.ev_out, 0));
+  ++g.replays;
+}
+#endif
 
 // ====================================================================================== plane-distributed K2
 // The global spline solve couples all radii but not the (z-mode, wavenumber) columns, so the columns
@@ -1591,7 +1708,14 @@ int sb_model_step(sb_model_t m, int64_t t) {
 int sb_model_run(sb_model_t m, int64_t t0, int64_t nsteps) {
   try {
     if (!m || t0 < 1 || nsteps < 0) return fail(SB_EINVAL, "bad argument");
-    for (int64_t t = t0; t < t0 + nsteps; ++t) model_step(m, t);
+    int64_t t = t0;
+    while (t < t0 + nsteps) {
+#ifndef SB_EMU
+      if (t >= 4 && t0 + nsteps - t >= 3 && step_graph_usable(m)) { step_graph_run3(m, t); t += 3; continue; }
+#endif
+      model_step(m, t);
+      ++t;
+    }
     return SB_OK;
   } catch (const CommError& e) { return fail(SB_ECOMM, e.what());
   } catch (const std::exception& e) { return fail(SB_ECUDA, e.what()); }

@@ -1,0 +1,453 @@
+// sb_ringfft4.cu -- ring FFT v4 (inverse): the v2 Bluestein convolution (sb_ringfft2.cu) with Blackwell data movement.
+//
+// What ncu and the probes under profiles/microbench/ showed about v2 (k_inv_l2, 42 % of the C4 step):
+//   * the kernel is co-limited by the FP64 pipe and the shared-memory pipe (both ~50 % busy, the round takes about the
+//     SUM of the two), with 21 % of the stall samples on the global loads of the prologue (spectrum row + the ring's
+//     P/Q tables) -- and neither a register nor a byte of shared memory was left to stage anything ahead;
+//   * 54 of the 180 16-byte shared-memory accesses per thread and sequence are TABLE reads whose index depends on the
+//     thread only (pass twiddles W_L^{k tl}, the pre-transformed chirp FH[e T + tl], the chirp, P/Q): thread-private data;
+//   * Tensor Memory (256 KB per SM, unused by a non-MMA kernel) is exactly per-thread-private storage: with the 32x32b
+//     shape of tcgen05.ld / tcgen05.st, thread l of warp w owns lane 32 (w % 4) + l and 512 32-bit columns of it.  Probe
+//     (profiles/microbench/tmem_probe.cu, fp64_lds_probe.cu): >= 570 B/cycle/SM of TMEM reads, and a radix-16 pass whose
+//     twiddles come from TMEM costs 2860 cycles against 3100 with the twiddles in shared memory (2815 with none at all).
+// So here
+//   * every per-thread table lives in Tensor Memory (class twiddles for the whole kernel; FH, chirp and P/Q per ring),
+//     read with tcgen05.ld (SASS LDTM) in batches of four complex values;
+//   * the 78 KB of shared memory this frees hold one staging row per team, filled by the bulk-copy engine
+//     (cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS): the NEXT sequence's spectrum row is requested by one thread right
+//     after the first exchange barrier of the current convolution and lands while the FP64 pipe works; no register, no
+//     LSU instruction, no long-scoreboard stall in the prologue;
+//   * the second-pass twiddles come from their table again (v2 rebuilt them with 14 complex multiplies per pass to spare
+//     shared-memory wavefronts).
+// Same arithmetic as v2 wherever a value is produced (butterflies, table values, operation order), so the result is
+// bit-identical to v2 except for the second-pass twiddles (table instead of product tree: <= 1 ulp apart).
+//
+// Lengths: L = 512 .. 4096 (two strided radix-16 passes + a register-local final pass).  L = 4096 has teams of 256
+// threads = two threads per TMEM lane: two table sets of 224 columns, and P/Q stay in global memory for that class.
+#include "sb_internal.hpp"
+#include "sb_fftcore.hpp"
+
+#include <cstdlib>
+#include <stdexcept>
+
+namespace sb {
+
+template <int LOG2L>
+struct R4Cfg {
+  static constexpr int L = 1 << LOG2L;
+  static constexpr int T = L / 16;                       // threads per team (one complex sequence)
+  static constexpr int NFULL = (LOG2L - 1) / 4;          // strided radix-16 passes (2 for every supported length)
+  static constexpr int RF = 1 << (LOG2L - 4 * NFULL);    // register-local final radix
+  static constexpr int LP = L + L / 16;                  // padded team buffer (complex)
+  static constexpr int NT = 512;
+  static constexpr int NTEAMS = NT / T;
+  static constexpr int MS1 = L >> 8;                     // stride of the second pass
+  static constexpr int SETS = T > 128 ? T / 128 : 1;     // threads per TMEM lane
+  // Tensor Memory columns of one table set (one complex double = 4 columns)
+  static constexpr int C_TW0 = 0;                        // [16] pass-0 twiddles W_L^{k tl} (entry 0 unused)
+  static constexpr int C_TW1 = 64;                       // [16] pass-1 twiddles
+  static constexpr int C_FH = 128;                       // [16] FH[e T + tl]
+  static constexpr int C_CH = 192;                       // [8]  chirp[n1 T + tl]
+  static constexpr int C_PQ = 224;                       // [2 halves][8][P, Q]
+  static constexpr bool PQ_TMEM = SETS == 1;
+  static constexpr int SETCOLS = PQ_TMEM ? 352 : 224;
+  static constexpr int NFILL = SETS == 1 ? 128 : T;      // threads that write the tables (whole warps, every lane / set)
+  static constexpr int STG = L + 16;                     // staging doubles per team: a spectrum row (<= L - 1 doubles) + slack
+  static constexpr size_t SMEM = sizeof(double2) * (size_t)NTEAMS * LP + sizeof(double) * (size_t)NTEAMS * STG + 16 * NTEAMS;
+  static_assert(NFULL == 2, "v4 covers the lengths with two strided passes");
+  static_assert(SETS * SETCOLS <= 512, "Tensor Memory has 512 columns");
+};
+
+__device__ __forceinline__ double sb_u2d(uint32_t lo, uint32_t hi) {
+#ifdef SB_EMU
+  const unsigned long long b = ((unsigned long long)hi << 32) | lo;
+  double d;
+  std::memcpy(&d, &b, 8);
+  return d;
+#else
+  return __hiloint2double((int)hi, (int)lo);
+#endif
+}
+__device__ __forceinline__ void sb_d2u(double d, uint32_t& lo, uint32_t& hi) {
+#ifdef SB_EMU
+  unsigned long long b;
+  std::memcpy(&b, &d, 8);
+  lo = (uint32_t)b; hi = (uint32_t)(b >> 32);
+#else
+  lo = (uint32_t)__double2loint(d); hi = (uint32_t)__double2hiint(d);
+#endif
+}
+__device__ __forceinline__ double2 tm_c(const uint32_t (&r)[16], int q) {
+  return make_double2(sb_u2d(r[4 * q], r[4 * q + 1]), sb_u2d(r[4 * q + 2], r[4 * q + 3]));
+}
+__device__ __forceinline__ void tm_put(uint32_t addr, double2 z) {     // one complex value -> 4 columns of this thread's lane
+  uint32_t r[4];
+  sb_d2u(z.x, r[0], r[1]);
+  sb_d2u(z.y, r[2], r[3]);
+  sb_tmem_st4(addr, r);
+}
+
+template <int T>
+__device__ __forceinline__ void team_sync4(int team) {
+  if (T >= 64) sb_bar_sync(1 + team, T);
+  else __syncwarp();
+}
+
+// v[k] *= W[k] (CONJ: conj(W[k])), k = 1..15, W = 16 complex values at TMEM columns taddr..taddr+63.  Four batches of
+// four; the next batch is requested before the current one is used.
+template <bool CONJ>
+__device__ __forceinline__ void tm_twiddle(double2 (&v)[16], uint32_t taddr) {
+  uint32_t r0[16], r1[16];
+  sb_tmem_ld16(taddr, r0);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    uint32_t(&cur)[16] = (b & 1) ? r1 : r0;
+    uint32_t(&nxt)[16] = (b & 1) ? r0 : r1;
+    sb_tmem_wait_ld16(cur);
+    if (b < 3) sb_tmem_ld16(taddr + 16 * (b + 1), nxt);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 4 * b + q;
+      if (k) v[k] = CONJ ? cmc(v[k], tm_c(cur, q)) : cm(v[k], tm_c(cur, q));
+    }
+  }
+}
+
+// circular convolution with the pre-transformed chirp; tables from Tensor Memory (tb = this thread's table set).
+// In: v[n1] = element n1*T + tl, n1 < 8 (upper half zero).  Out: v[n1] = element n1*T + tl of the result, n1 < 8.
+// `after_first_exchange` runs once, after the first team barrier: by then every thread of the team has finished the
+// prologue that precedes the call (the staging row may be overwritten).
+template <int LOG2L, class Hook>
+__device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t tb, int tl, int team, bool active, Hook&& after_first_exchange) {
+  typedef R4Cfg<LOG2L> C;
+  constexpr int T = C::T, M1 = C::MS1, LB1 = M1 << 4;
+  const int b1 = tl / M1, j1 = tl - b1 * M1, base1 = padi(b1 * LB1 + j1), base0 = padi(tl);
+  // ---- forward pass 0 (stride T): pruned radix-16, twiddle, store
+  if (active) {
+    fft16_fwd_lo8(v);
+    tm_twiddle<false>(v, tb + C::C_TW0);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[base0 + k * T + ((k * T) >> 4)] = v[k];
+  }
+  team_sync4<T>(team);
+  after_first_exchange();
+  // ---- forward pass 1 (stride M1)
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {          // butterfly order: the first radix-4 can start after four loads
+      const int n = (i >> 2) + 4 * (i & 3);
+      v[n] = buf[base1 + n * M1 + ((n * M1) >> 4)];
+    }
+    fft16<false>(v);
+    tm_twiddle<false>(v, tb + C::C_TW1);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) buf[base1 + k * M1 + ((k * M1) >> 4)] = v[k];
+  }
+  team_sync4<T>(team);
+  // ---- final forward pass, pointwise product with FH, first inverse pass: all in registers
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = buf[tl * 17 + e];
+    fft_final<false>(v, C::RF);
+    {
+      uint32_t r0[16], r1[16];
+      sb_tmem_ld16(tb + C::C_FH, r0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint32_t(&cur)[16] = (b & 1) ? r1 : r0;
+        uint32_t(&nxt)[16] = (b & 1) ? r0 : r1;
+        sb_tmem_wait_ld16(cur);
+        if (b < 3) sb_tmem_ld16(tb + C::C_FH + 16 * (b + 1), nxt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[4 * b + q] = cm(v[4 * b + q], tm_c(cur, q));
+      }
+    }
+    fft_final<true>(v, C::RF);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) buf[tl * 17 + e] = v[e];
+  }
+  team_sync4<T>(team);
+  // ---- inverse pass 1
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = (i >> 2) + 4 * (i & 3);
+      v[k] = buf[base1 + k * M1 + ((k * M1) >> 4)];
+    }
+    tm_twiddle<true>(v, tb + C::C_TW1);
+    fft16<true>(v);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) buf[base1 + n * M1 + ((n * M1) >> 4)] = v[n];
+  }
+  team_sync4<T>(team);
+  // ---- inverse pass 0: result stays in registers
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = (i >> 2) + 4 * (i & 3);
+      v[k] = buf[base0 + k * T + ((k * T) >> 4)];
+    }
+    tm_twiddle<true>(v, tb + C::C_TW0);
+    fft16<true>(v);
+  }
+}
+
+// =====================================================================================
+// inverse: spectra (value, d/dr, d2/dr2) -> 5 real rows; rows of a ring are rho = zb*5 + f
+// =====================================================================================
+template <int LOG2L>
+__global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
+                                                   const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
+                                                   const double* __restrict__ blob, const double* __restrict__ in,
+                                                   long long in_fs, long long in_vs, double* __restrict__ out,
+                                                   long long out_fs, long long out_vs, int out_is_phys, int var0,
+                                                   unsigned lmask) {
+  typedef R4Cfg<LOG2L> C;
+  constexpr int L = C::L, T = C::T;
+  SB_DYN_SMEM(double2, sm);
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
+  double2* const buf = sm + (size_t)team * C::LP;
+  double* const stg_all = reinterpret_cast<double*>(sm + (size_t)C::NTEAMS * C::LP);
+  double* const stg = stg_all + (size_t)team * C::STG;                                   // 16-byte aligned (STG even)
+  sb_mbar_t* const mbar = reinterpret_cast<sb_mbar_t*>(stg_all + (size_t)C::NTEAMS * C::STG) + 2 * team;   // 16 bytes apart
+  if (tid < 32) sb_tmem_alloc(&s_tmem, 512);
+  if (tl == 0) sb_mbar_init(mbar, 1);
+  sb_fence_mbar_init();
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  sb_tmem_fence_after_sync();
+  const int set = (C::SETS > 1) ? tl / 128 : 0;
+  const uint32_t tb = sb_tmem_warp_base(s_tmem) + (uint32_t)(set * C::SETCOLS);
+  // ---- class twiddles -> Tensor Memory (once per CTA): thread tid < NFILL writes lane tid % 128, set tid / 128
+  if (tid < C::NFILL) {
+    const int tf = tid % T;                       // the tl whose tables this (lane, set) holds
+    const uint32_t tf_b = sb_tmem_warp_base(s_tmem) + (uint32_t)((C::SETS > 1 ? tid / 128 : 0) * C::SETCOLS);
+    const double2* tw1 = twp + 15 * T;
+    tm_put(tf_b + C::C_TW0, make_double2(1.0, 0.0));
+    tm_put(tf_b + C::C_TW1, make_double2(1.0, 0.0));
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      tm_put(tf_b + C::C_TW0 + 4 * k, twp[(k - 1) * T + tf]);
+      tm_put(tf_b + C::C_TW1 + 4 * k, tw1[(k - 1) * C::MS1 + (tf % C::MS1)]);
+    }
+    sb_tmem_wait_st();
+  }
+  unsigned phase = 0;                             // parity of the team's staging barrier
+  int cur_ring = -1;
+  const int total = nwork * nvars;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int item = w / nvars, v_ = w - item * nvars;
+    const LWork wk = work[item];
+    const RingPlan pl = plans[wk.r];
+    const int n = pl.n, m = pl.m;
+    const double2* chirp_g = reinterpret_cast<const double2*>(blob + pl.off);
+    const double2* FH_g = chirp_g + 3 * m;
+    const double2* PQ = reinterpret_cast<const double2*>(blob + pl.off2);
+    if (wk.r != cur_ring) {          // ring tables -> Tensor Memory
+      sb_tmem_fence_before_sync();
+      __syncthreads();               // nobody is still reading the previous ring's tables
+      sb_tmem_fence_after_sync();
+      if (tid < C::NFILL) {
+        const int tf = tid % T;
+        const uint32_t tf_b = sb_tmem_warp_base(s_tmem) + (uint32_t)((C::SETS > 1 ? tid / 128 : 0) * C::SETCOLS);
+#pragma unroll
+        for (int e0 = 0; e0 < 16; e0 += 8) {
+          double2 x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = FH_g[(e0 + e) * T + tf];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tm_put(tf_b + C::C_FH + 4 * (e0 + e), x[e]);
+        }
+        {
+          double2 x[8];
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) { const int a0 = n1 * T + tf; x[n1] = chirp_g[a0 < m ? a0 : m - 1]; }
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) tm_put(tf_b + C::C_CH + 4 * n1, x[n1]);
+        }
+        if (C::PQ_TMEM) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double2 p[8], q[8];
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+              const int k0 = n1 * T + tf, k = k0 < m ? k0 : m - 1;
+              p[n1] = PQ[(size_t)(2 * h) * m + k];
+              q[n1] = PQ[(size_t)(2 * h + 1) * m + k];
+            }
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+              tm_put(tf_b + C::C_PQ + 4 * ((h * 8 + n1) * 2), p[n1]);
+              tm_put(tf_b + C::C_PQ + 4 * ((h * 8 + n1) * 2 + 1), q[n1]);
+            }
+          }
+        }
+        sb_tmem_wait_st();
+      }
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      cur_ring = wk.r;
+    }
+    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const int nseq = 2 * wk.nrows;
+    // spectrum row of sequence s (rows f = 0, 3, 4 read the value spectrum)
+    auto row_of = [&](int s) -> const double* {
+      const int rho = wk.row0 + (s >> 1), zb = rho / 5, f = rho - zb * 5;
+      return in + (long long)(f < 3 ? f : 0) * in_fs + (long long)v_ * in_vs + (long long)zb * g.W + woff;
+    };
+    auto wanted = [&](int s) { const int rho = wk.row0 + (s >> 1); return ((lmask >> (rho % 5)) & 1u) != 0u; };
+    // one thread asks the copy engine for a row: from the 16-byte boundary at or below its first double, a multiple of
+    // 16 bytes (the row has 2m-1 doubles and starts at an arbitrary double; at most one foreign double on either side is
+    // copied along -- both lie inside the SL scratch array)
+    auto request = [&](int s) {
+      const double* sp = row_of(s);
+      const int sh = (int)(((uintptr_t)sp >> 3) & 1);
+      const unsigned bytes = (unsigned)(((sh + 2 * m - 1) * 8 + 15) & ~15);
+      sb_fence_proxy_async();
+      sb_mbar_expect_tx(mbar, bytes);
+      sb_bulk_g2s(stg, sp - sh, bytes, mbar);
+    };
+    // first wanted sequence of this team in the item
+    int s = team;
+    while (s < nseq && !wanted(s)) s += C::NTEAMS;
+    team_sync4<T>(team);                 // the team's previous sequence (previous item) has left the staging row and buf
+    if (s < nseq && tl == 0) request(s);
+    // every team runs the same number of loop trips, so that whole warps stay together at the warp-collective TMEM loads
+    for (int trip = team; trip - team < nseq; trip += C::NTEAMS) {
+      const bool active = s < nseq;
+      int s_next = nseq;
+      if (active) {
+        s_next = s + C::NTEAMS;
+        while (s_next < nseq && !wanted(s_next)) s_next += C::NTEAMS;
+      }
+      const int row = s >> 1, half = s & 1;
+      const int rho = wk.row0 + row;
+      const int zb = rho / 5, f = rho - zb * 5;
+      double2 v[16];
+      if (active) {
+        sb_mbar_wait(mbar, phase);       // the row has landed in the staging buffer
+        phase ^= 1u;
+        const double* st = stg + (int)(((uintptr_t)row_of(s) >> 3) & 1);
+        const double2* Ph = PQ + (size_t)(2 * half) * m;
+        const double2* Qh = Ph + m;
+#pragma unroll
+        for (int h4 = 0; h4 < 4; ++h4) {           // two spectrum elements per batch: P, Q of both in one TMEM load
+          uint32_t r[16];
+          double2 Pk[2], Qk[2];
+          if (C::PQ_TMEM) {
+            sb_tmem_ld16(tb + C::C_PQ + 4 * ((half * 8 + 2 * h4) * 2), r);
+          }
+          double cx[2], cy[2], qx[2], qy[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k0 = (h4 * 2 + j) * T + tl;
+            const int k = k0 < m ? k0 : m - 1;
+            const int km = k ? m - k : 0;
+            cx[j] = st[k ? 2 * k - 1 : 0]; cy[j] = st[2 * k];
+            qx[j] = st[km ? 2 * km - 1 : 0]; qy[j] = st[2 * km];
+            if (!C::PQ_TMEM) { Pk[j] = Ph[k]; Qk[j] = Qh[k]; }
+          }
+          if (C::PQ_TMEM) {
+            sb_tmem_wait_ld16(r);
+            Pk[0] = tm_c(r, 0); Qk[0] = tm_c(r, 1); Pk[1] = tm_c(r, 2); Qk[1] = tm_c(r, 3);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k0 = (h4 * 2 + j) * T + tl;
+            const int k = k0 < m ? k0 : m - 1;
+            const int km = k ? m - k : 0;
+            const double2 ck = make_double2(cx[j], k ? cy[j] : 0.0);
+            const double2 cq = make_double2(qx[j], km ? qy[j] : 0.0);
+            // derivative factor D(q): 1 | i q | -q^2 ;  X = conj(c_k D_k), Y = c_km D_km
+            double2 X, Y;
+            if (f < 3) {
+              X = make_double2(ck.x, -ck.y);
+              Y = cq;
+            } else if (f == 3) {
+              const double dk = (double)k, dq = (double)km;
+              X = make_double2(-dk * ck.y, -dk * ck.x);
+              Y = make_double2(-dq * cq.y, dq * cq.x);
+            } else {
+              const double sk = -(double)k * (double)k, sq = -(double)km * (double)km;
+              X = make_double2(sk * ck.x, -sk * ck.y);
+              Y = make_double2(sq * cq.x, sq * cq.y);
+            }
+            const double2 u = cm(X, Pk[j]) + cm(Y, Qk[j]);
+            v[h4 * 2 + j] = k0 < m ? u : make_double2(0.0, 0.0);
+          }
+        }
+      }
+      conv4<LOG2L>(v, buf, tb, tl, team, active, [&]() {
+        if (tl == 0 && s_next < nseq) request(s_next);     // lands while this convolution runs
+      });
+      if (active) {
+        double* orow;
+        if (out_is_phys)
+          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
+        else
+          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+        uint32_t r0[16], r1[16];
+        sb_tmem_ld16(tb + C::C_CH, r0);
+        sb_tmem_ld16(tb + C::C_CH + 16, r1);
+        sb_tmem_wait_ld16(r0);
+        sb_tmem_wait_ld16(r1);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a = n1 * T + tl;
+          const double2 ch = n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3);
+          if (a < m) {
+            const double2 Y = cm(v[n1], ch);
+            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+          }
+        }
+      }
+      team_sync4<T>(team);            // the team has finished reading buf (inverse pass 0) before the next forward pass 0 writes it
+      s = s_next;
+    }
+  }
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+bool fft4_supported(int L, bool forward) {
+  static const char* env = std::getenv("SB_FFT4");
+  if (env && std::atoi(env) == 0) return false;   // A/B switch: v2 kernels
+  if (forward) return false;                      // the forward transform stays on v2 for now
+  return L == 512 || L == 1024 || L == 2048 || L == 4096;
+}
+
+template <int LOG2L>
+static void launch_inv4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, const double* twp,
+                        const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs,
+                        long long in_vs, double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
+  const size_t smem = R4Cfg<LOG2L>::SMEM;
+  cudaError_t e = cudaFuncSetAttribute(k_inv_l4<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
+  SB_LAUNCH(k_inv_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
+            c.need.lmask);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l4 launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+void launch_inv_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
+                   double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
+  switch (L) {
+    case 512: launch_inv4<9>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
+    case 1024: launch_inv4<10>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
+    case 2048: launch_inv4<11>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
+    case 4096: launch_inv4<12>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
+    default: throw std::runtime_error("launch_inv_l4: unsupported convolution length");
+  }
+}
+
+}  // namespace sb

@@ -656,6 +656,11 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                     out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
+    if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty() && fft4_supported(L, false)) {
+      launch_inv_l4(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+                    out, out_fstride, out_vstride, out_is_phys, var0);
+      continue;
+    }
     if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty()) {
       launch_inv_l2(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
                     out, out_fstride, out_vstride, out_is_phys, var0);

@@ -77,6 +77,15 @@ def transform_cases():
         "RL_tile_fft3": G.GridParameters(geometry="RL", xmin=171, xmax=174, num_cells=3, vars={"h": 1, "u": 2}, spectralIndexL=172),
         "RLZ_tile_fft3": G.GridParameters(geometry="RLZ", xmin=171, xmax=173, num_cells=2, zmin=0, zmax=5, zDim=8,
                                           vars={"h": 1}, spectralIndexL=172),
+        # outer-tile rings in every power-of-two convolution class of the v4 kernels (Tensor-Memory tables, bulk-copy staging):
+        # m = ri + 1 = 181..183 (L = 512), 301..303 (1024), 871..876 (2048; odd and even row offsets), 1801..1803 (4096: two
+        # table sets per TMEM lane)
+        "RL_tile_fft4_L512": G.GridParameters(geometry="RL", xmin=60, xmax=61, num_cells=1, vars={"h": 1, "u": 2}, spectralIndexL=61),
+        "RL_tile_fft4_L1024": G.GridParameters(geometry="RL", xmin=100, xmax=101, num_cells=1, vars={"h": 1}, spectralIndexL=101),
+        "RL_tile_fft4_L2048": G.GridParameters(geometry="RL", xmin=290, xmax=292, num_cells=2, vars={"h": 1, "u": 2}, spectralIndexL=291),
+        "RLZ_tile_fft4_L2048": G.GridParameters(geometry="RLZ", xmin=290, xmax=291, num_cells=1, zmin=0, zmax=5, zDim=8,
+                                                vars={"h": 1}, spectralIndexL=291),
+        "RL_tile_fft4_L4096": G.GridParameters(geometry="RL", xmin=600, xmax=601, num_cells=1, vars={"h": 1}, spectralIndexL=601),
         "RZ_z32_nobc": G.GridParameters(geometry="RZ", xmin=0, xmax=10, num_cells=13, zmin=0, zmax=5, zDim=32,
                                         vars={"s": 1, "w": 2}),
     }

@@ -390,3 +390,26 @@ def test_multi_gpu_exchange_modes(gpu_lib):
                        timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "vs oracle rel_err" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["Oneway_ShallowWater_Slab", "LinearAdvection1D", "Euler_test_semiimplicit", "LinearAdvectionRLZ_z16_fused"])
+def test_graph_replayed_steps_are_bit_identical(name, gpu_lib):
+    """sb_model_run replays three AB3 steps per CUDA-graph launch on launch-bound grids (one graph per phase of the
+    history pointer rotation); Model.step() launches every kernel eagerly.  Same bits after 14 steps, with run() entered
+    at different rotation phases."""
+    case = M_CASES[name]
+    nt = case["tiles"][-1]
+    a = pkg_model(case, nt, gpu_lib)
+    a.initialize(case["ic"])
+    for _ in range(14):
+        a.step()
+    b = pkg_model(case, nt, gpu_lib)
+    b.initialize(case["ic"])
+    b.run(7)          # steps 1-3 eager, 4-6 one graph, 7 eager
+    b.run(4)          # phase shifted by one: a second graph
+    b.run(3)          # third phase
+    assert b.launch_count() == a.launch_count()
+    for i in range(nt):
+        for k in ("var_np1", "expdot_nm1", "expdot_nm2"):
+            assert np.array_equal(a.state(i, k), b.state(i, k)), (i, k)
+    a.close(); b.close()
