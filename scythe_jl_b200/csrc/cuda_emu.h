@@ -196,19 +196,23 @@ static inline void sb_tmem_fence_after_sync() {}
 // mbarrier + bulk asynchronous copy (cp.async.bulk, SASS UBLKCP): the emulation copies at issue, so a wait never blocks;
 // a copy issued before every reader of the destination has passed a barrier corrupts the emulated run exactly as it
 // could on the device (fibers run to the next barrier one after another), which is what the tests are for.
-// state: low 32 bits = completed phases, high 32 bits = bytes still expected in the current phase (one arriving thread)
-struct sb_mbar_t { unsigned long long state; };
-static inline void sb_mbar_init(sb_mbar_t* b, int) { b->state = 0; }
-static inline void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) { b->state += (unsigned long long)bytes << 32; }
+// (the emulated barrier object is 16 bytes; kernels place barriers 16 bytes apart)
+struct sb_mbar_t { uint32_t phases, count, pending, tx; };
+static inline void sbemu_mbar_check(sb_mbar_t* b) {
+  if (b->pending == 0 && b->tx == 0) { ++b->phases; b->pending = b->count; }      // phase complete: re-arm
+}
+static inline void sb_mbar_init(sb_mbar_t* b, int count) { b->phases = 0; b->count = b->pending = (uint32_t)count; b->tx = 0; }
+static inline void sb_mbar_arrive(sb_mbar_t* b) { --b->pending; sbemu_mbar_check(b); }
+static inline void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) { b->tx += bytes; --b->pending; }   // arrive + expect
 static inline void sb_mbar_wait(sb_mbar_t* b, unsigned parity) {      // returns once the phase of that parity has completed
-  while (((unsigned)b->state & 1u) == (parity & 1u)) sbemu::fiber_yield();
+  while ((b->phases & 1u) == (parity & 1u)) sbemu::fiber_yield();
 }
 static inline void sb_fence_mbar_init() {}
 static inline void sb_fence_proxy_async() {}
 static inline void sb_bulk_g2s(void* dst, const void* src, unsigned bytes, sb_mbar_t* b) {
   std::memcpy(dst, src, bytes);
-  b->state -= (unsigned long long)bytes << 32;
-  if ((b->state >> 32) == 0) b->state = (unsigned)b->state + 1u;     // all expected bytes have arrived: next phase
+  b->tx -= bytes;
+  sbemu_mbar_check(b);
 }
 static inline void sb_bulk_s2g(void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
 static inline void sb_bulk_commit() {}
@@ -286,6 +290,9 @@ __device__ __forceinline__ void sb_mbar_init(sb_mbar_t* b, int count) {
 }
 __device__ __forceinline__ void sb_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void sb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sb_mbar_arrive(sb_mbar_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
 __device__ __forceinline__ void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
 }

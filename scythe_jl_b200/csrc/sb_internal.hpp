@@ -169,6 +169,9 @@ bool fft4_supported(int L, bool forward);
 void launch_inv_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
                    const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
                    double* out, long long out_fs, long long out_vs, int out_is_phys, int var0);
+void launch_fwd_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs);
 bool fft2_supported(int L, bool forward);
 int fft2_rows_per_item(int L, bool forward);
 void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,

@@ -55,6 +55,7 @@ struct R4Cfg {
   static constexpr int STG = L + 16;                     // staging doubles per team: a spectrum row (<= L - 1 doubles) + slack
   static constexpr size_t SMEM = sizeof(double2) * (size_t)NTEAMS * LP + sizeof(double) * (size_t)NTEAMS * STG + 16 * NTEAMS;
   static_assert(NFULL == 2, "v4 covers the lengths with two strided passes");
+  static_assert(MS1 <= 16 && 32 % MS1 == 0, "second-pass blocks must stay inside a warp");
   static_assert(SETS * SETCOLS <= 512, "Tensor Memory has 512 columns");
 };
 
@@ -131,6 +132,7 @@ __device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t t
   }
   team_sync4<T>(team);
   after_first_exchange();
+  __syncwarp();                 // the hook is one thread's work: the warp is whole again before the warp-collective TMEM loads
   // ---- forward pass 1 (stride M1)
   if (active) {
 #pragma unroll
@@ -143,7 +145,9 @@ __device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t t
 #pragma unroll
     for (int k = 0; k < 16; ++k) buf[base1 + k * M1 + ((k * M1) >> 4)] = v[k];
   }
-  team_sync4<T>(team);
+  // the second pass works on blocks of 16 M1 elements owned by M1 <= 16 consecutive threads, and so do the final pass
+  // and the first inverse pass: these two exchanges never leave a warp
+  __syncwarp();
   // ---- final forward pass, pointwise product with FH, first inverse pass: all in registers
   if (active) {
 #pragma unroll
@@ -166,7 +170,7 @@ __device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t t
 #pragma unroll
     for (int e = 0; e < 16; ++e) buf[tl * 17 + e] = v[e];
   }
-  team_sync4<T>(team);
+  __syncwarp();
   // ---- inverse pass 1
   if (active) {
 #pragma unroll
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
   double2* const buf = sm + (size_t)team * C::LP;
   double* const stg_all = reinterpret_cast<double*>(sm + (size_t)C::NTEAMS * C::LP);
   double* const stg = stg_all + (size_t)team * C::STG;                                   // 16-byte aligned (STG even)
-  sb_mbar_t* const mbar = reinterpret_cast<sb_mbar_t*>(stg_all + (size_t)C::NTEAMS * C::STG) + 2 * team;   // 16 bytes apart
+  sb_mbar_t* const mbar = reinterpret_cast<sb_mbar_t*>(reinterpret_cast<char*>(stg_all + (size_t)C::NTEAMS * C::STG) + 16 * team);
   if (tid < 32) sb_tmem_alloc(&s_tmem, 512);
   if (tl == 0) sb_mbar_init(mbar, 1);
   sb_fence_mbar_init();
@@ -235,8 +239,12 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
   }
   unsigned phase = 0;                             // parity of the team's staging barrier
   int cur_ring = -1;
+  // contiguous share of the work list (items are ordered by ring): a CTA changes ring -- and reloads the ring's tables --
+  // once every few items instead of at every item
   const int total = nwork * nvars;
-  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+  const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  for (int w = w_begin; w < w_end; ++w) {
     const int item = w / nvars, v_ = w - item * nvars;
     const LWork wk = work[item];
     const RingPlan pl = plans[wk.r];
@@ -412,13 +420,226 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
   if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
 }
 
+
+// =====================================================================================
+// forward: real ring rows -> retained coefficients k = 0..ri.  Teams work in pairs (the two packed sequences of one
+// row).  The row (n = 4m doubles, contiguous and 32-byte aligned) is staged once per pair by the bulk-copy engine; the
+// pair's "full" barrier tells both teams it has landed, its "consumed" barrier (one arrival per team, after the team's
+// first exchange barrier) tells the requesting thread that the staging buffer may be refilled with the next row.  The
+// raw convolution outputs are parked in the teams' own buffers and the pair combines them with the pre-combined tables
+// A0..A3, which live in Tensor Memory like every other per-thread table (both halves' entries in every lane).
+// =====================================================================================
+template <int LOG2L>
+struct R4FCfg : R4Cfg<LOG2L> {
+  typedef R4Cfg<LOG2L> B;
+  static constexpr int NPAIRS = B::NTEAMS / 2;
+  static constexpr int STGF = 2 * B::L;                  // staging doubles per pair: one real row (n = 4m <= 2L)
+  static constexpr size_t SMEMF = sizeof(double2) * (size_t)B::NTEAMS * B::LP + sizeof(double) * (size_t)NPAIRS * STGF + 16 * B::NTEAMS;
+};
+
+template <int T>
+__device__ __forceinline__ void pair_sync4(int pair) {
+  if (2 * T >= 64) sb_bar_sync((T >= 64 ? 9 : 1) + pair, 2 * T);
+  else __syncwarp();
+}
+
+template <int LOG2L>
+__global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
+                                                   const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
+                                                   const double* __restrict__ blob, const double* __restrict__ in,
+                                                   long long in_vs, double* __restrict__ mirror, long long mirror_vs,
+                                                   double* __restrict__ out, long long out_vs) {
+  typedef R4FCfg<LOG2L> C;
+  constexpr int T = C::T, NPAIRS = C::NPAIRS;
+  SB_DYN_SMEM(double2, sm);
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
+  const int pair = team >> 1, half = team & 1;
+  double2* const buf = sm + (size_t)team * C::LP;
+  const double2* const buf0 = sm + (size_t)(2 * pair) * C::LP;
+  const double2* const buf1 = buf0 + C::LP;
+  double* const stg_all = reinterpret_cast<double*>(sm + (size_t)C::NTEAMS * C::LP);
+  const double* const stg = stg_all + (size_t)pair * C::STGF;                                 // 16-byte aligned
+  char* const mb = reinterpret_cast<char*>(stg_all + (size_t)NPAIRS * C::STGF) + 32 * pair;
+  sb_mbar_t* const full = reinterpret_cast<sb_mbar_t*>(mb);
+  sb_mbar_t* const consumed = reinterpret_cast<sb_mbar_t*>(mb + 16);
+  if (tid < 32) sb_tmem_alloc(&s_tmem, 512);
+  if (half == 0 && tl == 0) { sb_mbar_init(full, 1); sb_mbar_init(consumed, 2); }
+  sb_fence_mbar_init();
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  sb_tmem_fence_after_sync();
+  const int set = (C::SETS > 1) ? tl / 128 : 0;
+  const uint32_t tb = sb_tmem_warp_base(s_tmem) + (uint32_t)(set * C::SETCOLS);
+  if (tid < C::NFILL) {          // class twiddles -> Tensor Memory (as k_inv_l4)
+    const int tf = tid % T;
+    const uint32_t tf_b = sb_tmem_warp_base(s_tmem) + (uint32_t)((C::SETS > 1 ? tid / 128 : 0) * C::SETCOLS);
+    const double2* tw1 = twp + 15 * T;
+    tm_put(tf_b + C::C_TW0, make_double2(1.0, 0.0));
+    tm_put(tf_b + C::C_TW1, make_double2(1.0, 0.0));
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      tm_put(tf_b + C::C_TW0 + 4 * k, twp[(k - 1) * T + tf]);
+      tm_put(tf_b + C::C_TW1 + 4 * k, tw1[(k - 1) * C::MS1 + (tf % C::MS1)]);
+    }
+    sb_tmem_wait_st();
+  }
+  unsigned ph_full = 0, ph_cons = 0;
+  int cur_ring = -1;
+  const int total = nwork * nvars;
+  const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  for (int w = w_begin; w < w_end; ++w) {
+    const int item = w / nvars, v_ = w - item * nvars;
+    const LWork wk = work[item];
+    const RingPlan pl = plans[wk.r];
+    const int n = pl.n, m = pl.m;
+    const double2* chirp_g = reinterpret_cast<const double2*>(blob + pl.off);
+    const double2* FH_g = chirp_g + 3 * m;
+    const double2* AF = reinterpret_cast<const double2*>(blob + pl.off2) + (size_t)4 * m;
+    if (wk.r != cur_ring) {          // ring tables -> Tensor Memory
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      if (tid < C::NFILL) {
+        const int tf = tid % T;
+        const uint32_t tf_b = sb_tmem_warp_base(s_tmem) + (uint32_t)((C::SETS > 1 ? tid / 128 : 0) * C::SETCOLS);
+#pragma unroll
+        for (int e0 = 0; e0 < 16; e0 += 8) {
+          double2 x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = FH_g[(e0 + e) * T + tf];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tm_put(tf_b + C::C_FH + 4 * (e0 + e), x[e]);
+        }
+        {
+          double2 x[8];
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) { const int a0 = n1 * T + tf; x[n1] = chirp_g[a0 < m ? a0 : m - 1]; }
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) tm_put(tf_b + C::C_CH + 4 * n1, x[n1]);
+        }
+        if (C::PQ_TMEM) {            // A0..A3 at k = h T + tf + 2 T i, h = 0, 1, i = 0..3
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k0 = h * T + tf + 2 * T * i, k = k0 < m ? k0 : m - 1;
+              double2 a[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) a[q] = AF[(size_t)q * m + k];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) tm_put(tf_b + C::C_PQ + 4 * ((h * 4 + i) * 4 + q), a[q]);
+            }
+          }
+        }
+        sb_tmem_wait_st();
+      }
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      cur_ring = wk.r;
+    }
+    const long long hoff = g.ring_hoff[wk.r];
+    const double* src = in + (long long)v_ * in_vs + (long long)g.bz * hoff;
+    double* mir = mirror ? mirror + (long long)v_ * mirror_vs + (long long)g.bz * hoff : nullptr;
+    double* dst = out + (long long)v_ * out_vs + g.ring_woff[wk.r];
+    auto request = [&](int row) {          // the whole real row: n doubles, 32-byte aligned
+      sb_fence_proxy_async();
+      sb_mbar_expect_tx(full, (unsigned)n * 8u);
+      sb_bulk_g2s(const_cast<double*>(stg), src + (long long)(wk.row0 + row) * n, (unsigned)n * 8u, full);
+    };
+    pair_sync4<T>(pair);             // the pair's previous row (previous item) has left the staging row and the buffers
+    if (half == 1 && tl == 0 && pair < wk.nrows) request(pair);
+    for (int row = pair; row - pair < wk.nrows; row += NPAIRS) {
+      const bool active = row < wk.nrows;
+      double2 v[16];
+      if (active) {
+        sb_mbar_wait(full, ph_full);
+        ph_full ^= 1u;
+        double* mp = mir ? mir + (long long)(wk.row0 + row) * n + 2 * half : nullptr;
+        const double* rp = stg + 2 * half;
+        uint32_t r0[16], r1[16];
+        sb_tmem_ld16(tb + C::C_CH, r0);
+        sb_tmem_ld16(tb + C::C_CH + 16, r1);
+        double2 x[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a0 = n1 * T + tl, a = a0 < m ? a0 : m - 1;
+          x[n1] = *reinterpret_cast<const double2*>(rp + 4 * a);
+        }
+        sb_tmem_wait_ld16(r0);
+        sb_tmem_wait_ld16(r1);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a0 = n1 * T + tl, a = a0 < m ? a0 : m - 1;
+          if (mp && a0 < m) *reinterpret_cast<double2*>(mp + 4 * a) = x[n1];
+          const double2 y = cm(x[n1], n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3));
+          v[n1] = a0 < m ? y : make_double2(0.0, 0.0);
+        }
+      }
+      conv4<LOG2L>(v, buf, tb, tl, team, active, [&]() {
+        // this team has finished reading the staged row; when both teams have, the next row may overwrite it
+        if (active && tl == 0) {
+          sb_mbar_arrive(consumed);
+          if (half == 1) {
+            sb_mbar_wait(consumed, ph_cons);
+            ph_cons ^= 1u;
+            if (row + NPAIRS < wk.nrows) request(row + NPAIRS);
+          }
+        }
+      });
+      team_sync4<T>(team);            // every thread of the team has read its last-pass inputs
+      if (active) {
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int a = n1 * T + tl;
+          if (a < m) buf[a] = v[n1];
+        }
+      }
+      pair_sync4<T>(pair);
+      if (active) {
+        double* o = dst + (long long)(wk.row0 + row) * g.W;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = half * T + tl + 2 * T * i;
+          uint32_t r[16];
+          double2 A0, A1, A2, A3;
+          if (C::PQ_TMEM) {
+            sb_tmem_ld16(tb + C::C_PQ + 4 * ((half * 4 + i) * 4), r);
+            sb_tmem_wait_ld16(r);
+            A0 = tm_c(r, 0); A1 = tm_c(r, 1); A2 = tm_c(r, 2); A3 = tm_c(r, 3);
+          }
+          if (k < m) {
+            if (!C::PQ_TMEM) { A0 = AF[k]; A1 = AF[m + k]; A2 = AF[2 * m + k]; A3 = AF[3 * m + k]; }
+            const int km = k ? m - k : 0;
+            const double2 b0 = buf0[k], b0m = buf0[km], b1 = buf1[k], b1m = buf1[km];
+            double2 X = cm(b0, A0) + cm(make_double2(b0m.x, -b0m.y), A1);
+            X = X + cm(b1, A2) + cm(make_double2(b1m.x, -b1m.y), A3);
+            if (k == 0) {
+              o[0] = X.x;
+            } else {
+              o[2 * k - 1] = X.x;
+              o[2 * k] = X.y;
+            }
+          }
+        }
+      }
+      pair_sync4<T>(pair);            // the pair has finished combining out of buf0 / buf1 before the next row's first pass writes them
+    }
+  }
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
+}
+
 // =====================================================================================
 // launchers
 // =====================================================================================
 bool fft4_supported(int L, bool forward) {
   static const char* env = std::getenv("SB_FFT4");
   if (env && std::atoi(env) == 0) return false;   // A/B switch: v2 kernels
-  if (forward) return false;                      // the forward transform stays on v2 for now
+  (void)forward;
   return L == 512 || L == 1024 || L == 2048 || L == 4096;
 }
 
@@ -447,6 +668,34 @@ void launch_inv_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
     case 2048: launch_inv4<11>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
     case 4096: launch_inv4<12>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
     default: throw std::runtime_error("launch_inv_l4: unsupported convolution length");
+  }
+}
+
+
+template <int LOG2L>
+static void launch_fwd4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, const double* twp,
+                        const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs,
+                        double* mirror, long long mirror_vs, double* out, long long out_vs) {
+  const size_t smem = R4FCfg<LOG2L>::SMEMF;
+  cudaError_t e = cudaFuncSetAttribute(k_fwd_l4<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
+  SB_LAUNCH(k_fwd_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_l4 launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+void launch_fwd_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs) {
+  switch (L) {
+    case 512: launch_fwd4<9>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs); break;
+    case 1024: launch_fwd4<10>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs); break;
+    case 2048: launch_fwd4<11>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs); break;
+    case 4096: launch_fwd4<12>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs); break;
+    default: throw std::runtime_error("launch_fwd_l4: unsupported convolution length");
   }
 }
 

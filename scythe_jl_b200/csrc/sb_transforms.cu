@@ -533,6 +533,12 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                     mirror_vstride, out, out_vstride, fft3_scratch);
       continue;
     }
+    if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty() && fft4_supported(L, true) && (uintptr_t)in % 16 == 0 &&
+        in_vstride % 2 == 0) {   // rows are bulk-copied: 16-byte aligned
+      launch_fwd_l4(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+                    mirror_vstride, out, out_vstride);
+      continue;
+    }
     if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty()) {
       launch_fwd_l2(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
                     mirror_vstride, out, out_vstride);
