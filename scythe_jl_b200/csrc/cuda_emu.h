@@ -138,12 +138,16 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 enum { cudaStreamNonBlocking = 1 };
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return 0; }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return 0; }
+enum { cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return 0; }   // everything runs at once
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return 0; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)1 << 40; return 0; }
 cudaError_t cudaEventCreate(cudaEvent_t* e);
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
@@ -203,7 +207,7 @@ static inline void sbemu_mbar_check(sb_mbar_t* b) {
 }
 static inline void sb_mbar_init(sb_mbar_t* b, int count) { b->phases = 0; b->count = b->pending = (uint32_t)count; b->tx = 0; }
 static inline void sb_mbar_arrive(sb_mbar_t* b) { --b->pending; sbemu_mbar_check(b); }
-static inline void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) { b->tx += bytes; --b->pending; }   // arrive + expect
+static inline void sb_mbar_expect_tx(sb_mbar_t* b, unsigned bytes) { b->tx += bytes; --b->pending; sbemu_mbar_check(b); }   // arrive + expect
 static inline void sb_mbar_wait(sb_mbar_t* b, unsigned parity) {      // returns once the phase of that parity has completed
   while ((b->phases & 1u) == (parity & 1u)) sbemu::fiber_yield();
 }

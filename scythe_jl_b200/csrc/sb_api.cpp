@@ -103,6 +103,20 @@ struct sb_grid {
   double* d_parB = nullptr;     // DMMA B-fragment tables of the same matrices
   double* d_fwdB = nullptr;     // DMMA B-fragment tables of the analysis (forward) matrix
   std::vector<char> z_bcfree;   // per variable: BCB == BCT == R0
+  std::vector<int> zt_first;    // [rDim+1] first z tile of every ring (tiles are ordered by ring)
+  // overlapped step (tile_step_overlapped): FP64-bound ring FFTs and HBM-bound kernels on two streams, by ring batches
+  struct Overlap {
+    bool ready = false;
+    cudaStream_t s_fft = nullptr, s_mem = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_invr = nullptr, ev_fl = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> ev_il, ev_z;
+    std::vector<std::pair<int, int>> batches;   // ring ranges [r_lo, r_hi), outermost first
+    int* d_counters = nullptr;
+    int counter_next = 0;
+    double* buf = nullptr;
+    long long buf_doubles = 0;
+    int sm_reserve = 24;
+  } ov;
   long long launches = 0;
   long long* d_nan = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -283,7 +297,9 @@ static void build_grid(sb_grid* G) {
     // z tiles
     std::vector<ZTile> zt;
     if (d.has_l) {
-      for (int r = 0; r < d.rDim; ++r)
+      G->zt_first.assign(d.rDim + 1, 0);
+      for (int r = 0; r < d.rDim; ++r) {
+        G->zt_first[r] = (int)zt.size();
         for (int j0 = 0; j0 < G->ring_n[r]; j0 += 32) {
           ZTile t{};
           t.hcol0 = (int)(G->hoff[r] + j0);
@@ -292,6 +308,8 @@ static void build_grid(sb_grid* G) {
           t.out_stride = G->ring_n[r];
           zt.push_back(t);
         }
+      }
+      G->zt_first[d.rDim] = (int)zt.size();
     } else {
       for (int j0 = 0; j0 < d.rDim; j0 += 32) {
         ZTile t{};
@@ -560,6 +578,14 @@ static void grid_free(sb_grid* G) {
   cudaSetDevice(G->device);
   cudaStreamSynchronize(G->stream);
   for (void* p : G->owned) cudaFree(p);
+  if (G->ov.s_fft) { cudaStreamSynchronize(G->ov.s_fft); cudaStreamDestroy(G->ov.s_fft); }
+  if (G->ov.s_mem) { cudaStreamSynchronize(G->ov.s_mem); cudaStreamDestroy(G->ov.s_mem); }
+  for (cudaEvent_t e : {G->ov.ev_fork, G->ov.ev_invr, G->ov.ev_fl, G->ov.ev_join})
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : G->ov.ev_il) cudaEventDestroy(e);
+  for (cudaEvent_t e : G->ov.ev_z) cudaEventDestroy(e);
+  cudaFree(G->ov.d_counters);
+  cudaFree(G->ov.buf);
   cudaFree(G->physical); if (G->owns_B) cudaFree(G->spectralB); cudaFree(G->spectralA); cudaFree(G->scratch); cudaFree(G->d_nan);
   if (G->ev0) cudaEventDestroy(G->ev0);
   if (G->ev1) cudaEventDestroy(G->ev1);
@@ -1079,7 +1105,158 @@ static void tiles_tendency(sb_model* M) {
   }
 }
 
+// ====================================================================================== overlapped step
+// advanceTimestep of one tile (src/semiimplicit.jl:301-332) for LinearAdvectionRLZ with the two kinds of kernels of the
+// step running side by side: the ring FFTs are FP64-pipe bound and leave HBM almost idle, the Chebyshev / radial stages
+// are HBM bound and leave the FP64 pipe idle.  The tile's rings are cut into batches (outermost first); the ring FFTs of
+// batch b run on a high-priority stream with grids that leave `sm_reserve` SMs free, and on a second stream the Chebyshev
+// synthesis + equation set + AB3 and the Chebyshev analysis of batch b-1 run on those SMs:
+//   mem stream:  inv_r | wait I(b0): Z(b0) | wait I(b1): Z(b1) | ...                         | wait F(last): fwd_r
+//   fft stream:        | I(b0) | I(b1) | I(b2) | ... | wait Z(b0): F(b0) | wait Z(b1): F(b1) ...
+//   I = inv_l of the 7 rows, Z = inv_z + K4 then fwd_z, F = fwd_l.  Same kernels, same arithmetic, same per-point order as
+//   the sequential step: the state is bit-identical (tests: test_overlapped_step_*).
+static bool overlap_usable(const sb_model* M) {
+  // Opt-in (SB_OVERLAP=1).  Measured on B200 at C4 (gpurun_out/r2k): 18.5 ms with no SM reserved, 27.0 ms with
+  // 24, 21.2 ms with 40 -- against 18.2 ms for the one-stream step.  The HBM-bound kernels reach only ~45 GB/s per SM
+  // when confined to a few SMs (a plain copy kernel: 120 GB/s per SM, profiles/microbench/overlap_probe.cu), so they need
+  // more SMs than the ring FFTs can spare.  Kept, tested for bit-identity, as the frame for kernels that stream better.
+  const char* e = std::getenv("SB_OVERLAP");
+  if (!e || std::atoi(e) != 1) return false;
+  if (M->k3_slots != 0 || M->eq != EQ_LinearAdvectionRLZ) return false;
+  for (auto& T : M->tiles)
+    if (!fused_advection_ok(M, T.grid) || T.grid->zt_first.empty()) return false;
+  return true;
+}
+
+static void overlap_prepare(sb_grid* G) {
+  auto& ov = G->ov;
+  if (ov.ready) return;
+  const DevGrid& t = G->dg;
+  int lo = 0, hi = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&ov.s_fft, cudaStreamNonBlocking, hi));
+  CU(cudaStreamCreateWithPriority(&ov.s_mem, cudaStreamNonBlocking, lo));
+  for (cudaEvent_t* e : {&ov.ev_fork, &ov.ev_invr, &ov.ev_fl, &ov.ev_join}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  const char* eb = std::getenv("SB_OVERLAP_BATCHES");
+  int nb = eb && std::atoi(eb) > 0 ? std::atoi(eb) : 6;
+  if (nb > t.rDim) nb = t.rDim;
+  // equal shares of the horizontal points, outermost rings first
+  int r_hi = t.rDim;
+  for (int b = 0; b < nb; ++b) {
+    const long long target = G->hoff[t.rDim] * (long long)(nb - 1 - b) / nb;    // points below the batch
+    int r_lo = (b == nb - 1) ? 0 : r_hi - 1;
+    while (r_lo > 0 && G->hoff[r_lo] > target) --r_lo;
+    if (b == nb - 1) r_lo = 0;
+    if (r_lo < r_hi) ov.batches.emplace_back(r_lo, r_hi);
+    r_hi = r_lo;
+  }
+  ov.ev_il.resize(ov.batches.size());
+  ov.ev_z.resize(ov.batches.size());
+  for (auto& e : ov.ev_il) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : ov.ev_z) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(cudaMalloc((void**)&ov.d_counters, 512 * sizeof(int)));
+  const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
+  ov.buf_doubles = 8 * ((slN + 15) & ~15LL) + 10 * ((szN + 15) & ~15LL) + 64;
+  CU(cudaMalloc((void**)&ov.buf, (size_t)ov.buf_doubles * sizeof(double)));
+  const char* ek = std::getenv("SB_OVERLAP_K");
+  ov.sm_reserve = ek ? std::atoi(ek) : 24;
+  if (ov.sm_reserve < 0) ov.sm_reserve = 0;
+  if (ov.sm_reserve > sb_sm_count() / 2) ov.sm_reserve = sb_sm_count() / 2;
+  ov.ready = true;
+}
+
+static void tile_step_overlapped(sb_model* M, TileState& T, int tq) {
+  sb_grid* G = T.grid;
+  sb_grid* P = M->cs.on ? G : M->patch;
+  overlap_prepare(G);
+  auto& ov = G->ov;
+  DevGrid& t = G->dg;
+  DevGrid& p = P->dg;
+  const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
+  const long long slA = (slN + 15) & ~15LL, szA = (szN + 15) & ~15LL;    // 128-byte aligned regions: rows are read as double2 / bulk-copied
+  double* SLi = ov.buf;                 // [5]: h value, d/dr, d2/dr2 | u | v
+  double* SZi = SLi + 5 * slA;          // [7]: h value, r, rr, l, ll | u | v
+  double* SLf = SZi + 7 * szA;          // [3 variables]
+  double* SZf = SLf + 3 * slA;          // [3 variables]
+  ModelArrays a{};
+  a.var_np1 = T.var_np1;
+  a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
+  G->slot0_src = nullptr;
+  LaunchCtx cm = G->ctx(), cf = G->ctx();
+  cm.stream = ov.s_mem;
+  cf.stream = ov.s_fft;
+  cf.counters = ov.d_counters; cf.counter_next = &ov.counter_next; cf.ncounters = 512; cf.sm_reserve = ov.sm_reserve;
+  CU(cudaEventRecord(ov.ev_fork, G->stream));
+  CU(cudaStreamWaitEvent(ov.s_mem, ov.ev_fork, 0));
+  CU(cudaStreamWaitEvent(ov.s_fft, ov.ev_fork, 0));
+  // ---- radial evaluation of the three variables (whole tile, nothing to share the chip with yet)
+  const unsigned slots[3] = {31u, 1u, 1u};
+  for (int v = 0; v < 3; ++v) {
+    cm.need = k3_need_from_slots(t, slots[v]);
+    launch_inv_r(cm, t, p, 1, P->spectralA + (long long)v * p.S, p.S, SLi + (v ? (2 + v) * slA : 0), slA, slA, 0, v);
+  }
+  CU(cudaEventRecord(ov.ev_invr, ov.s_mem));
+  CU(cudaStreamWaitEvent(ov.s_fft, ov.ev_invr, 0));
+  const int nb = (int)ov.batches.size();
+  for (int b = 0; b < nb; ++b) {
+    const int r_lo = ov.batches[b].first, r_hi = ov.batches[b].second;
+    // ---- I(b): ring synthesis of the seven rows
+    cf.r_lo = r_lo; cf.r_hi = r_hi;
+    for (int v = 0; v < 3; ++v) {
+      cf.need = k3_need_from_slots(t, slots[v]);
+      launch_inv_l(cf, t, G->iwork, G->d_iwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, 1,
+                   SLi + (v ? (2 + v) * slA : 0), slA, slA, SZi + (v ? (4 + v) * szA : 0), szA, szA, 0, v, &G->iwork2,
+                   G->d_iwork2.data());
+    }
+    CU(cudaEventRecord(ov.ev_il[b], ov.s_fft));
+    // ---- Z(b): Chebyshev synthesis + tendency + AB3, then Chebyshev analysis of the new state, on the reserved SMs
+    CU(cudaStreamWaitEvent(ov.s_mem, ov.ev_il[b], 0));
+    const int z0 = G->zt_first[r_lo], z1 = G->zt_first[r_hi];
+    cm.mem_grid_sms = (b + 1 < nb) ? ov.sm_reserve : 0;       // the last batch has the chip to itself until F(b0) starts
+    if (cm.mem_grid_sms > 0 && cm.mem_grid_sms < 4) cm.mem_grid_sms = 4;
+    launch_inv_z_advection(cm, t, G->d_ztiles + z0, z1 - z0, SZi, szA, G->d_parB, M->ep, a, tq);
+    launch_fwd_z_mma(cm, t, G->d_ztiles + z0, z1 - z0, 3, T.var_np1, t.N, nullptr, t.N, SZf, szA, G->d_fwdB);
+    CU(cudaEventRecord(ov.ev_z[b], ov.s_mem));
+  }
+  // ---- F(b): ring analysis
+  for (int b = 0; b < nb; ++b) {
+    cf.r_lo = ov.batches[b].first; cf.r_hi = ov.batches[b].second;
+    cf.need = K3Need{};
+    CU(cudaStreamWaitEvent(ov.s_fft, ov.ev_z[b], 0));
+    launch_fwd_l(cf, t, G->fwork, G->d_fwork.data(), G->classes, G->d_tw.data(), G->d_twp.data(), G->d_plans, G->d_blob, 3, SZf, szA,
+                 1, nullptr, 0, SLf, slA, &G->fwork2, G->d_fwork2.data(), G->d_fft3_scratch);
+  }
+  CU(cudaEventRecord(ov.ev_fl, ov.s_fft));
+  CU(cudaStreamWaitEvent(ov.s_mem, ov.ev_fl, 0));
+  cm.mem_grid_sms = 0;
+  cm.need = K3Need{};
+  launch_fwd_r(cm, t, 3, SLf, slA, G->spectralB, t.S, G->scatter, 0);
+  CU(cudaEventRecord(ov.ev_join, ov.s_mem));
+  CU(cudaStreamWaitEvent(G->stream, ov.ev_join, 0));
+  G->slot0_src = T.var_np1;
+}
+
+static void tiles_step_overlapped(sb_model* M, int64_t t) {
+  sb_grid* P = M->patch;
+  const int tq = (int)std::min<int64_t>(t, 3);
+  const bool direct = M->cs.on || (M->ntiles == 1 && !M->tiles[0].grid->owns_B);
+  if (!direct) CU(cudaMemsetAsync(P->spectralB, 0, (size_t)P->dg.S * P->dg.V * sizeof(double), P->stream));  // :272
+  sb_grid* prev = nullptr;
+  for (auto& T : M->tiles) {
+    tile_step_overlapped(M, T, tq);
+    std::rotate(T.expd, T.expd + 2, T.expd + 3);
+    if (!direct) {
+      sb_grid* G = T.grid;
+      launch_assemble(G->ctx(), P->dg, G->dg, G->spectralB, prev ? &prev->dg : nullptr, prev ? prev->spectralB : nullptr, 0,
+                      P->spectralB);                         // :320-329
+      prev = G;
+    }
+  }
+  M->rot_phase = (M->rot_phase + 1) % 3;
+}
+
 static void model_advance_tiles(sb_model* M, int64_t t) {
+  if (overlap_usable(M)) { tiles_step_overlapped(M, t); return; }
   tiles_physics(M, t);
   tiles_tendency(M);
 }

@@ -366,6 +366,169 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection(DevGrid g, const ZTi
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// The same kernel with Blackwell data movement (the default; SB_INVZ_BULK=0 selects the cp.async version above).
+// ncu on the version above (profiles/r1m_ncu_full_k_inv_z_advection_t1.txt): 55 % of the measured HBM peak,
+// the warps wait on the history loads of the epilogue (plain LDG behind the DMMA burst), and with 128 registers there
+// is no room to request them early.  Here nothing the kernel reads goes through a register or an LSU instruction:
+//   * the [mode][column] tile (7 fields x 43 rows of <= 128 bytes) and the six history blocks (exp_nm1, exp_nm2 of the
+//     three variables: one 512-byte run per column) are fetched by the bulk-copy engine (cp.async.bulk, SASS UBLKCP)
+//     into shared memory and announced by two mbarriers (SASS SYNCS);
+//   * per CTA one tile buffer + one history buffer (109 KB, two CTAs per SM): the NEXT tile's rows are requested as soon
+//     as the DMMA phase has drained the tile buffer and land during the epilogue, its history as soon as the epilogue
+//     has drained the history buffer and lands during the next DMMA phase;
+//   * history columns sit 72 doubles apart in shared memory: the epilogue's double2 reads (8 columns x 4 level pairs per
+//     warp) are bank-conflict free.
+// Arithmetic, DMMA order and store pattern are those of the kernel above: bit-identical results.
+// -------------------------------------------------------------------------------------------------------------------
+#define ZB_HS 72                // column stride (doubles) of a history block in shared memory
+__global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, const ZTile* __restrict__ tiles, int ntiles,
+                                                                 const double* __restrict__ in, long long in_fs,
+                                                                 const double* __restrict__ parB, EqParams p, ModelArrays arr, int t) {
+  SB_DYN_SMEM(double, a);       // [ZF_NF][2 parities][ZM_KK][ZM_CS] | history [2][3][16][ZB_HS] | row table | 2 mbarriers
+  constexpr int COLS = 16, ZM_CS = COLS + 4, ZM_THREADS = COLS * 16, SPLIT = 32 / COLS;
+  const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = (ZM_THREADS / 32) / nzt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane & 3, i = lane >> 2;
+  const int zt = warp % nzt, cg = warp / nzt;
+  constexpr int bufsz = ZF_NF * 2 * ZM_KK * ZM_CS;
+  constexpr int histsz = 6 * COLS * ZB_HS;
+  double* const hist = a + bufsz;
+  int4* const rowtab = reinterpret_cast<int4*>(hist + histsz);
+  const int nrow = ZF_NF * bz;
+  char* const mb = reinterpret_cast<char*>(rowtab + ((nrow + 1) & ~1));
+  sb_mbar_t* const full_in = reinterpret_cast<sb_mbar_t*>(mb);
+  sb_mbar_t* const full_hist = reinterpret_cast<sb_mbar_t*>(mb + 16);
+  double B[2][ZM_KT];           // value matrix only
+#pragma unroll
+  for (int par = 0; par < 2; ++par)
+#pragma unroll
+    for (int kt = 0; kt < ZM_KT; ++kt) B[par][kt] = parB[(((par * ZM_KT + kt) * 4) + zt) * 32 + lane];
+  for (int j = tid; j < bufsz; j += ZM_THREADS) a[j] = 0.0;   // zero padding (modes >= bz) stays zero
+  for (int r = tid; r < nrow; r += ZM_THREADS) {
+    const int f = r / bz, zb = r - f * bz;
+    rowtab[r] = make_int4(f, zb, ((f * 2 + (zb & 1)) * ZM_KK + (zb >> 1)) * ZM_CS, 0);
+  }
+  if (tid == 0) { sb_mbar_init(full_in, 1); sb_mbar_init(full_hist, 1); }
+  sb_fence_mbar_init();
+  __syncthreads();
+  const int z0 = zt * 8 + 2 * q;                 // this lane's pair of levels (z0, z0+1) and mirror (zDim-2-z0, +1)
+  const int nwork = ntiles * SPLIT;
+  auto desc = [&](int w) {       // COLS-column sub-tile of a 32-column ZTile
+    ZTile tl = tiles[w / SPLIT];
+    const int off = (w % SPLIT) * COLS;
+    tl.hcol0 += off; tl.out_base += off;
+    tl.ncols = tl.ncols - off < COLS ? tl.ncols - off : COLS;   // may be <= 0: empty sub-tile
+    return tl;
+  };
+  const long long N = g.N;
+  const int nh = (t >= 3 ? 2 : (t >= 2 ? 1 : 0));     // history arrays the AB step reads: exp_nm1 (t >= 2), exp_nm2 (t >= 3)
+  // rows of the tile: every thread asks for its rows (<= 2), thread 0 arms the barrier with the byte count of the tile
+  auto issue_in = [&](const ZTile& ztile) {
+    const int nc = ztile.ncols > 0 ? ztile.ncols : 0;
+    sb_fence_proxy_async();
+    if (tid == 0) sb_mbar_expect_tx(full_in, (unsigned)(nrow * nc * 8));
+    if (nc > 0) {
+      const double* src = in + ztile.out_base;
+      for (int r = tid; r < nrow; r += ZM_THREADS) {
+        const int4 rt = rowtab[r];
+        sb_bulk_g2s(a + rt.z, src + (long long)rt.x * in_fs + (long long)rt.y * ztile.out_stride, (unsigned)(nc * 8), full_in);
+      }
+    }
+  };
+  // history: one 8 zDim-byte run per (array, variable, column)
+  auto issue_hist = [&](const ZTile& ztile) {
+    const int nc = ztile.ncols > 0 ? ztile.ncols : 0;
+    sb_fence_proxy_async();
+    if (tid == 0) sb_mbar_expect_tx(full_hist, (unsigned)(nh * 3 * nc * zDim * 8));
+    const int total = nh * 3 * nc;
+    for (int j = tid; j < total; j += ZM_THREADS) {
+      const int c = j % nc, hv = j / nc, v = hv % 3, hk = hv / 3;        // hk = 0: exp_nm1, 1: exp_nm2
+      const double* src = (hk ? arr.exp_nm2 : arr.exp_nm1) + (long long)v * N + ((long long)ztile.hcol0 + c) * zDim;
+      sb_bulk_g2s(hist + ((hk * 3 + v) * COLS + c) * ZB_HS, src, (unsigned)(zDim * 8), full_hist);
+    }
+  };
+  const double ts = p.ts, K = p.K;
+  const int G = gridDim.x;
+  int w = blockIdx.x;
+  unsigned ph_in = 0, ph_h = 0;
+  ZTile zt0 = desc(w < nwork ? w : 0), zt1;
+  auto radius = [&](const ZTile& z) { return z.ncols > 0 ? g.rad[g.h2r[z.hcol0]] : 1.0; };
+  double r0 = radius(zt0), r1;
+  if (w < nwork) { issue_in(zt0); issue_hist(zt0); }
+  for (; w < nwork; w += G) {
+    const bool more = w + G < nwork;
+    zt1 = desc(more ? w + G : w);
+    r1 = radius(zt1);
+    const ZTile ztile = zt0;
+    zt0 = zt1;
+    const double ri = 1.0 / r0, ri2 = ri * ri;
+    r0 = r1;
+    sb_mbar_wait(full_in, ph_in);          // the tile's rows have landed
+    ph_in ^= 1u;
+    // COLS / 8 column groups; with nzt = 4 level tiles the 8 warps are 4 x 2: one column group per warp
+    const int c = cg * 8 + i;
+    const bool live = c < ztile.ncols && cg < COLS / 8;
+    double f[ZF_NF][4];         // f[s][0..3]: field row s at levels z0, z0+1, zDim-2-z0, zDim-1-z0
+    {
+      const double* ap = a + q * ZM_CS + (cg < COLS / 8 ? c : i);
+#pragma unroll
+      for (int s = 0; s < ZF_NF; ++s) {
+        const double* af = ap + (size_t)s * 2 * ZM_KK * ZM_CS;
+        double E[2] = {0, 0}, O[2] = {0, 0};
+#pragma unroll
+        for (int kt = 0; kt < ZM_KT; ++kt) {
+          sb_dmma(E[0], E[1], af[(kt * 4) * ZM_CS], B[0][kt]);
+          sb_dmma(O[0], O[1], af[(ZM_KK + kt * 4) * ZM_CS], B[1][kt]);
+        }
+        f[s][0] = E[0] + O[0]; f[s][1] = E[1] + O[1]; f[s][2] = E[1] - O[1]; f[s][3] = E[0] - O[0];
+      }
+    }
+    __syncthreads();            // every warp has drained the tile buffer
+    if (more) issue_in(zt1);    // lands during the epilogue
+    sb_mbar_wait(full_hist, ph_h);
+    ph_h ^= 1u;
+    if (live) {
+      const long long col0 = ((long long)ztile.hcol0 + c) * zDim;
+#pragma unroll
+      for (int hm = 0; hm < 2; ++hm) {          // the level pair and its mirror pair
+        const int zl = hm ? zDim - 2 - z0 : z0;
+        const long long o0 = col0 + zl;
+        double2 h1[3], h2[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          h1[v] = t >= 2 ? *reinterpret_cast<const double2*>(hist + (v * COLS + c) * ZB_HS + zl) : make_double2(0.0, 0.0);
+          h2[v] = t >= 3 ? *reinterpret_cast<const double2*>(hist + ((3 + v) * COLS + c) * ZB_HS + zl) : make_double2(0.0, 0.0);
+        }
+        double e[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int x = 2 * hm + k;
+          e[k] = advection_rl_tendency(f[5][x], f[6][x], f[1][x], f[3][x], f[2][x], f[4][x], ri, ri2, K);
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          const long long o = (long long)v * N + o0;
+          const int s = v == 0 ? 0 : 4 + v;
+          const double2 f1 = h1[v], f2 = h2[v];
+          const double fn0 = v == 0 ? e[0] : 0.0, fn1 = v == 0 ? e[1] : 0.0;
+          *reinterpret_cast<double2*>(arr.exp_n + o) = make_double2(fn0, fn1);
+          *reinterpret_cast<double2*>(arr.var_np1 + o) =
+              make_double2(ab_step(t, ts, f[s][2 * hm], fn0, f1.x, f2.x), ab_step(t, ts, f[s][2 * hm + 1], fn1, f1.y, f2.y));
+        }
+      }
+    }
+    __syncthreads();            // every warp has drained the history buffer
+    if (more) issue_hist(zt1);  // lands during the next DMMA phase
+  }
+}
+
+static bool inv_z_bulk_enabled() {
+  static const char* e = std::getenv("SB_INVZ_BULK");
+  return !(e && std::atoi(e) == 0);
+}
+
 bool inv_z_advection_ok(const DevGrid& g) {
   return g.has_l && g.has_z && g.V == 3 && (g.zDim == 16 || g.zDim == 32 || g.zDim == 64) && g.bz <= 2 * ZM_KK && g.N % 2 == 0;
 }
@@ -376,9 +539,17 @@ void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* t
   const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0;
   const size_t smem = (size_t)2 * ZF_NF * 2 * ZM_KK * (16 + 4) * sizeof(double) + (size_t)ZF_NF * g.bz * 16;
   const int nwork = ntiles * 2;
-  const int gx = nwork < sb_sm_count() * 2 ? nwork : sb_sm_count() * 2;
+  const int sms = c.mem_grid_sms > 0 ? c.mem_grid_sms : sb_sm_count();     // overlapped step: the SMs the ring FFTs leave free
+  const int gx = nwork < sms * 2 ? nwork : sms * 2;
   cudaError_t e;
-  if (al16) {
+  // bulk copies need 16-byte aligned rows (in, in_fs even, ring rows are multiples of 4 doubles) and whole history columns
+  if (al16 && inv_z_bulk_enabled() && g.zDim <= ZB_HS - 8) {
+    const size_t smem_b = (size_t)(ZF_NF * 2 * ZM_KK * (16 + 4) + 6 * 16 * ZB_HS) * sizeof(double) +
+                          (size_t)((ZF_NF * g.bz + 1) & ~1) * 16 + 32;
+    e = cudaFuncSetAttribute(k_inv_z_advection_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+    SB_LAUNCH(k_inv_z_advection_bulk, dim3(gx), dim3(256), smem_b, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
+  } else if (al16) {
     e = cudaFuncSetAttribute(k_inv_z_advection<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
     SB_LAUNCH((k_inv_z_advection<16>), dim3(gx), dim3(256), smem, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
@@ -509,7 +680,7 @@ void launch_fwd_z_mma(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, 
   // and ran one per SM (ncu: 1.33 waves)
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fwd_z_mma, FZ_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 3;
-  const int cap = sb_sm_count() * per_sm;
+  const int cap = (c.mem_grid_sms > 0 ? c.mem_grid_sms : sb_sm_count()) * per_sm;
   const int gx = nwork < cap ? nwork : cap;
   SB_LAUNCH(k_fwd_z_mma, dim3(gx), dim3(FZ_THREADS), smem, c.stream, g, tiles, ntiles, nvars, in, in_vstride, mirror,
             mirror_vstride, out, out_vstride, fwdB);

@@ -104,7 +104,15 @@ struct Profiler {
 //   lmask: ring rows       value | r | rr | lambda | lambda-lambda  (inv_l outputs, bit f)
 //   zmask: fields the Chebyshev synthesis reads (bit f);  zsel: of field 0, bit 0 = value, 1 = d/dz, 2 = d2/dz2
 struct K3Need { unsigned smask = 7, lmask = 31, zmask = 31, zsel = 7; };
-struct LaunchCtx { cudaStream_t stream; long long* launches; Profiler* prof; K3Need need; };
+struct LaunchCtx {
+  cudaStream_t stream; long long* launches; Profiler* prof; K3Need need;
+  // overlapped step only: restrict ring work lists / z tiles to the rings [r_lo, r_hi) (r_hi < 0: all rings), dynamic work
+  // counters for the ring FFT launches, SMs the FFT grids leave to the other stream, grid limit of the HBM-bound kernels
+  int r_lo = 0, r_hi = -1;
+  int* counters = nullptr; int* counter_next = nullptr; int ncounters = 0;
+  int sm_reserve = 0;
+  int mem_grid_sms = 0;            // > 0: persistent HBM-bound kernels size their grid for this many SMs
+};
 struct ProfScope {
   cudaStream_t s;
   cudaEvent_t b = nullptr;

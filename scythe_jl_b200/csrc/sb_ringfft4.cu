@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
                                                    const double* __restrict__ blob, const double* __restrict__ in,
                                                    long long in_fs, long long in_vs, double* __restrict__ out,
                                                    long long out_fs, long long out_vs, int out_is_phys, int var0,
-                                                   unsigned lmask) {
+                                                   unsigned lmask, int* counter, int chunk) {
   typedef R4Cfg<LOG2L> C;
   constexpr int L = C::L, T = C::T;
   SB_DYN_SMEM(double2, sm);
@@ -243,7 +243,17 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
   // once every few items instead of at every item
   const int total = nwork * nvars;
   const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  __shared__ int s_chunk;
+  int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  for (;;) {
+  if (counter) {                    // dynamic shares (launches that share the chip with other kernels): `chunk` consecutive items
+    if (tid == 0) s_chunk = atomicAdd(counter, 1);
+    __syncthreads();
+    w_begin = s_chunk * chunk;
+    w_end = w_begin + chunk < total ? w_begin + chunk : total;
+    __syncthreads();
+    if (w_begin >= total) break;
+  }
   for (int w = w_begin; w < w_end; ++w) {
     const int item = w / nvars, v_ = w - item * nvars;
     const LWork wk = work[item];
@@ -415,6 +425,8 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
       s = s_next;
     }
   }
+  if (!counter) break;
+  }
   sb_tmem_fence_before_sync();
   __syncthreads();
   if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
                                                    const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
                                                    const double* __restrict__ blob, const double* __restrict__ in,
                                                    long long in_vs, double* __restrict__ mirror, long long mirror_vs,
-                                                   double* __restrict__ out, long long out_vs) {
+                                                   double* __restrict__ out, long long out_vs, int* counter, int chunk) {
   typedef R4FCfg<LOG2L> C;
   constexpr int T = C::T, NPAIRS = C::NPAIRS;
   SB_DYN_SMEM(double2, sm);
@@ -488,7 +500,17 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
   int cur_ring = -1;
   const int total = nwork * nvars;
   const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  __shared__ int s_chunk;
+  int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  for (;;) {
+  if (counter) {                    // dynamic shares (launches that share the chip with other kernels): `chunk` consecutive items
+    if (tid == 0) s_chunk = atomicAdd(counter, 1);
+    __syncthreads();
+    w_begin = s_chunk * chunk;
+    w_end = w_begin + chunk < total ? w_begin + chunk : total;
+    __syncthreads();
+    if (w_begin >= total) break;
+  }
   for (int w = w_begin; w < w_end; ++w) {
     const int item = w / nvars, v_ = w - item * nvars;
     const LWork wk = work[item];
@@ -628,6 +650,8 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
       pair_sync4<T>(pair);            // the pair has finished combining out of buf0 / buf1 before the next row's first pass writes them
     }
   }
+  if (!counter) break;
+  }
   sb_tmem_fence_before_sync();
   __syncthreads();
   if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
@@ -636,6 +660,20 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
 // =====================================================================================
 // launchers
 // =====================================================================================
+// Overlapped step (sb_api.cpp, tile_step_overlapped): the FP64-bound ring FFTs run on a high-priority stream with a grid
+// that leaves `sm_reserve` SMs to the HBM-bound kernels of the other stream, and take their work from an atomic counter
+// so that a CTA that becomes resident late (or never) does not hold a fixed share.
+static int fft_grid_cap(const LaunchCtx& c) {
+  const int n = sb_sm_count() - (c.counters ? c.sm_reserve : 0);
+  return n < 1 ? 1 : n;
+}
+static int* take_counter(const LaunchCtx& c) {
+  if (!c.counters || !c.counter_next) return nullptr;
+  int* p = c.counters + (*c.counter_next)++ % c.ncounters;
+  cudaMemsetAsync(p, 0, sizeof(int), c.stream);
+  return p;
+}
+
 bool fft4_supported(int L, bool forward) {
   static const char* env = std::getenv("SB_FFT4");
   if (env && std::atoi(env) == 0) return false;   // A/B switch: v2 kernels
@@ -650,10 +688,11 @@ static void launch_inv4(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   const size_t smem = R4Cfg<LOG2L>::SMEM;
   cudaError_t e = cudaFuncSetAttribute(k_inv_l4<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
+  const int total = nwork * nvars, cap = fft_grid_cap(c), gx = total < cap ? total : cap;
+  int* counter = take_counter(c);     // non-null: the launch shares the chip with another stream's kernels
   SB_LAUNCH(k_inv_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
-            c.need.lmask);
+            c.need.lmask, counter, 2);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l4 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;
@@ -679,9 +718,10 @@ static void launch_fwd4(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   const size_t smem = R4FCfg<LOG2L>::SMEMF;
   cudaError_t e = cudaFuncSetAttribute(k_fwd_l4<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-  const int total = nwork * nvars, gx = total < sb_sm_count() ? total : sb_sm_count();
+  const int total = nwork * nvars, cap = fft_grid_cap(c), gx = total < cap ? total : cap;
+  int* counter = take_counter(c);
   SB_LAUNCH(k_fwd_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
-            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs);
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs, counter, 2);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_l4 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;

@@ -516,6 +516,19 @@ int sb_rows_per_cta(int L) {
   return r;
 }
 
+// items of a ring work list (sorted by ring, descending) whose ring lies in [c.r_lo, c.r_hi): a contiguous block
+static void ring_block(const LaunchCtx& c, const std::vector<LWork>& w, int& i0, int& i1) {
+  const int n = (int)w.size();
+  if (c.r_hi < 0) { i0 = 0; i1 = n; return; }
+  auto first_below = [&](int r) {      // first index whose ring is < r
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (w[mid].r < r) hi = mid; else lo = mid + 1; }
+    return lo;
+  };
+  i0 = first_below(c.r_hi);
+  i1 = first_below(c.r_lo);
+}
+
 void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::vector<LWork>>& hostwork,
                   const LWork* const* work, const std::vector<FftClass>& classes, const double* const* tw,
                   const double* const* twp, const RingPlan* plans, const double* blob, int nvars, const double* in,
@@ -524,28 +537,32 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   double* fft3_scratch) {
   ProfScope prof_scope_(c, "fwd_l");
   for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
-    int nwork = (int)hostwork[ci].size();
+    int i0, i1, j0 = 0, j1 = 0;
+    ring_block(c, hostwork[ci], i0, i1);
+    const int nwork = i1 - i0;
+    if (hostwork2) ring_block(c, (*hostwork2)[ci], j0, j1);
+    const int nwork2 = j1 - j0;
     if (!nwork) continue;
     int L = classes[ci].L;
     if (classes[ci].R == 3) {
-      if (!hostwork2 || (*hostwork2)[ci].empty() || !fft3_scratch) throw std::runtime_error("composite FFT class without a v2 work list");
-      launch_fwd_l3(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+      if (!hostwork2 || !nwork2 || !fft3_scratch) throw std::runtime_error("composite FFT class without a v2 work list");
+      launch_fwd_l3(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
                     mirror_vstride, out, out_vstride, fft3_scratch);
       continue;
     }
-    if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty() && fft4_supported(L, true) && (uintptr_t)in % 16 == 0 &&
+    if (classes[ci].fast && nwork2 && fft4_supported(L, true) && (uintptr_t)in % 16 == 0 &&
         in_vstride % 2 == 0) {   // rows are bulk-copied: 16-byte aligned
-      launch_fwd_l4(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+      launch_fwd_l4(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
                     mirror_vstride, out, out_vstride);
       continue;
     }
-    if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty()) {
-      launch_fwd_l2(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+    if (classes[ci].fast && nwork2) {
+      launch_fwd_l2(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
                     mirror_vstride, out, out_vstride);
       continue;
     }
     if (classes[ci].fast) {
-      launch_fwd_l_fast(c, g, work[ci], nwork, L, twp[ci], classes[ci].twoff, plans, blob, nvars, in, in_vstride, mirror,
+      launch_fwd_l_fast(c, g, work[ci] + i0, nwork, L, twp[ci], classes[ci].twoff, plans, blob, nvars, in, in_vstride, mirror,
                         mirror_vstride, out, out_vstride);
       continue;
     }
@@ -553,7 +570,7 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     size_t smem = (size_t)2 * nr * L * 16;
     opt_in_smem(k_fwd_l, smem);
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
-    SB_LAUNCH(k_fwd_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci], classes[ci].log2L,
+    SB_LAUNCH(k_fwd_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci] + i0, classes[ci].log2L,
               reinterpret_cast<const double2*>(tw[ci]), plans, blob, in, in_vstride, mirror, mirror_vstride, out,
               out_vstride);
     SB_CHECK_LAUNCH();
@@ -653,27 +670,31 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   int out_is_phys, int var0, const std::vector<std::vector<LWork>>* hostwork2, const LWork* const* work2) {
   ProfScope prof_scope_(c, "inv_l");
   for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
-    int nwork = (int)hostwork[ci].size();
+    int i0, i1, j0 = 0, j1 = 0;
+    ring_block(c, hostwork[ci], i0, i1);
+    const int nwork = i1 - i0;
+    if (hostwork2) ring_block(c, (*hostwork2)[ci], j0, j1);
+    const int nwork2 = j1 - j0;
     if (!nwork) continue;
     int L = classes[ci].L;
     if (classes[ci].R == 3) {
-      if (!hostwork2 || (*hostwork2)[ci].empty()) throw std::runtime_error("composite FFT class without a v2 work list");
-      launch_inv_l3(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+      if (!hostwork2 || !nwork2) throw std::runtime_error("composite FFT class without a v2 work list");
+      launch_inv_l3(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
                     out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
-    if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty() && fft4_supported(L, false)) {
-      launch_inv_l4(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+    if (classes[ci].fast && nwork2 && fft4_supported(L, false)) {
+      launch_inv_l4(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
                     out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
-    if (classes[ci].fast && hostwork2 && !(*hostwork2)[ci].empty()) {
-      launch_inv_l2(c, g, work2[ci], (int)(*hostwork2)[ci].size(), L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+    if (classes[ci].fast && nwork2) {
+      launch_inv_l2(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
                     out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
     if (classes[ci].fast) {
-      launch_inv_l_fast(c, g, work[ci], nwork, L, twp[ci], classes[ci].twoff, plans, blob, nvars, in, in_fstride,
+      launch_inv_l_fast(c, g, work[ci] + i0, nwork, L, twp[ci], classes[ci].twoff, plans, blob, nvars, in, in_fstride,
                         in_vstride, out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
@@ -681,7 +702,7 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     size_t smem = (size_t)2 * nr * L * 16;
     opt_in_smem(k_inv_l, smem);
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
-    SB_LAUNCH(k_inv_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci], classes[ci].log2L,
+    SB_LAUNCH(k_inv_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci] + i0, classes[ci].log2L,
               reinterpret_cast<const double2*>(tw[ci]), plans, blob, in, in_fstride, in_vstride, out, out_fstride,
               out_vstride, out_is_phys, var0, c.need.lmask);
     SB_CHECK_LAUNCH();

@@ -397,3 +397,25 @@ def check_needed_slots(case, lib, ntiles=None, **kw):
         assert np.array_equal(a0, c0) and np.array_equal(a1, c1), (
             f"fused K3+K4 state differs from the all-slots state: max |d var_np1| {np.abs(a0 - c0).max():.3e} of "
             f"{np.abs(a0).max():.3e}, max |d expdot| {np.abs(a1 - c1).max():.3e} of {np.abs(a1).max():.3e}")
+
+
+def check_overlapped_step(case, lib, ntiles, monkeypatch, batches=(1, 3, 5), **kw):
+    """The overlapped step (two streams, ring batches, dynamic FFT work shares, SB_OVERLAP=1 forces it on small grids) must
+    leave exactly the bits of the sequential step, for any number of ring batches."""
+    monkeypatch.setenv("SB_OVERLAP", "0")
+    m = pkg_model(case, ntiles, lib, **kw)
+    m.initialize(case["ic"])
+    m.run(case["n"])
+    ref = [(m.state(i, "var_np1").copy(), m.state(i, "expdot_nm1").copy(), m.state(i, "expdot_nm2").copy()) for i in range(ntiles)]
+    m.close()
+    for nb in batches:
+        monkeypatch.setenv("SB_OVERLAP", "1")
+        monkeypatch.setenv("SB_OVERLAP_BATCHES", str(nb))
+        m = pkg_model(case, ntiles, lib, **kw)
+        m.initialize(case["ic"])
+        m.run(case["n"])
+        for i in range(ntiles):
+            got = (m.state(i, "var_np1"), m.state(i, "expdot_nm1"), m.state(i, "expdot_nm2"))
+            for a, b, name in zip(got, ref[i], ("var_np1", "expdot_nm1", "expdot_nm2")):
+                assert np.array_equal(a, b), f"{nb} batches, tile {i}, {name}: overlapped step differs from the sequential step"
+        m.close()

@@ -413,3 +413,17 @@ def test_graph_replayed_steps_are_bit_identical(name, gpu_lib):
         for k in ("var_np1", "expdot_nm1", "expdot_nm2"):
             assert np.array_equal(a.state(i, k), b.state(i, k)), (i, k)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("ntiles", [1, 2])
+def test_overlapped_step_is_bit_identical(ntiles, gpu_lib, monkeypatch):
+    """The default C4 step runs the FP64-bound ring FFTs and the HBM-bound Chebyshev stages side by side on two streams,
+    by ring batches, with dynamic FFT work shares on 148 - k SMs.  Forced here on a 24-cell x 64-level grid: same bits as
+    the one-stream step for 1, 4 and 7 batches, and the state still matches the oracle."""
+    from helpers import check_overlapped_step
+    case = B_CASES["LinearAdvectionRLZ_z64_24cells_fused"]
+    check_overlapped_step(case, gpu_lib, ntiles, monkeypatch, batches=(1, 4, 7))
+    monkeypatch.setenv("SB_OVERLAP", "1")
+    monkeypatch.setenv("SB_OVERLAP_BATCHES", "5")
+    c1 = dict(case, tiles=(ntiles,))
+    assert check_model(c1, gpu_lib) <= STATE_TOL

@@ -196,3 +196,10 @@ def test_patch_and_halo_maps_match_oracle_and_overlap_add(name, emu_lib):
     assert np.abs(shared - patch.spectral).max() <= 1e-13 * np.abs(patch.spectral).max()
     assert S.allocateSplineBuffer(patch, patch) is None
     patch.close()
+
+
+def test_overlapped_step_is_bit_identical(emu_lib, monkeypatch):
+    """LinearAdvectionRLZ, fused K3+K4: ring FFTs and Chebyshev stages on two streams by ring batches == one stream."""
+    from helpers import check_overlapped_step
+    check_overlapped_step(M_CASES["LinearAdvectionRLZ_z16_fused"], emu_lib, 1, monkeypatch, batches=(3,))
+    check_overlapped_step(M_CASES["LinearAdvectionRLZ_z16_fused"], emu_lib, 2, monkeypatch, batches=(2,), exchange="columns")
