@@ -422,7 +422,10 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
     // smooth lengths: 3/4 of the power of two is enough when 2m-1 <= 3 * 2^(a-2).  Measured on B200: 6144 beats 8192
     // by 1.4x and 3072 beats 4096 slightly; 1536 only ties 2048 (three short sub-FFTs lose the pruning and
     // the radix-8 final pass), so the default threshold is L >= 4096 (SB_FFT3_MINL overrides).
-    static const int minL = std::getenv("SB_FFT3_MINL") ? std::atoi(std::getenv("SB_FFT3_MINL")) : 4096;
+    // Since the v4 kernels (sb_ringfft4.cu: Tensor-Memory tables, bulk-staged rows; L <= 4096) the power of two wins up to
+    // 4096 (N = 2 weak-scaling outer tile, m <= 1417: inv_l 11.9 ms with L = 3072 composite against 7.1 ms for the inner
+    // tile's 2048 class), so the composite classes start where v4 stops: L = 6144 instead of 8192.
+    static const int minL = std::getenv("SB_FFT3_MINL") ? std::atoi(std::getenv("SB_FFT3_MINL")) : (fft4_supported(4096, false) ? 8192 : 4096);
     if (fft3_enabled() && fast_class_supported(L) && L >= minL && L >= 2048 && L <= 8192 && 2 * p.m - 1 <= 3 * (L / 4)) L = 3 * (L / 4);
     p.L = L;
     p.cls = class_of(L);
