@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-materialised", action="store_true", help="skip the secondary all-slots timing (ncu captures)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-of", default="", help="debug, one GPU: 'N:i' = own only tile i of the N-GPU weak-scaling patch (per-kernel "
+                                                  "times of an outer tile without N GPUs; the state is not meaningful)")
     ap.add_argument("--no-preflight", action="store_true", help="N > 1: skip the multi-rank parity preflight against the oracle")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling run (C4 itself cut into N tiles)")
     return ap.parse_args()
@@ -334,6 +336,11 @@ def run_ours(args):
     if distributed and not args.no_preflight:
         preflight = multi_rank_preflight(S, dist, rank, world, local_rank)
     ntiles = world
+    tile_of = None
+    if args.tile_of:
+        assert not distributed
+        ntiles, ti = (int(x) for x in args.tile_of.split(":"))
+        tile_of = ti
     cells_tile = args.cells or C4_CELLS
     total_cells = int(round(cells_tile * math.sqrt(ntiles)))
     DX = XMAX / C4_CELLS
@@ -353,7 +360,10 @@ def run_ours(args):
                               zDim=ZDIM, vars={"h": 1, "u": 2, "v": 3})
         mp = S.ModelParameters(ts=TS, integration_time=TS * 1000, equation_set="LinearAdvectionRLZ", grid_params=gp,
                                physical_params={"K": KDIFF})
-    m = S.Model(mp, num_tiles=ntiles, device=local_rank, distributed=distributed)
+    if tile_of is not None:
+        m = S.Model(mp, num_tiles=ntiles, tile_first=tile_of, tile_count=1, device=local_rank)
+    else:
+        m = S.Model(mp, num_tiles=ntiles, device=local_rank, distributed=distributed)
     cfg_exchange = m.exchange
     Sp = m.patch.S
     tp = m.tile_params

@@ -180,6 +180,13 @@ void launch_inv_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
 void launch_fwd_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
                    const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
                    long long mirror_vs, double* out, long long out_vs);
+bool fft5_supported(int L);                   // composite lengths 3072 / 6144 with the v4 data movement
+void launch_inv_l5(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
+                   double* out, long long out_fs, long long out_vs, int out_is_phys, int var0);
+void launch_fwd_l5(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs, double* scratch);
 bool fft2_supported(int L, bool forward);
 int fft2_rows_per_item(int L, bool forward);
 void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,

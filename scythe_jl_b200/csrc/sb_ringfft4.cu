@@ -118,14 +118,15 @@ __device__ __forceinline__ void tm_twiddle(double2 (&v)[16], uint32_t taddr) {
 // In: v[n1] = element n1*T + tl, n1 < 8 (upper half zero).  Out: v[n1] = element n1*T + tl of the result, n1 < 8.
 // `after_first_exchange` runs once, after the first team barrier: by then every thread of the team has finished the
 // prologue that precedes the call (the staging row may be overwritten).
-template <int LOG2L, class Hook>
-__device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t tb, int tl, int team, bool active, Hook&& after_first_exchange) {
+template <int LOG2L, class Hook, bool PRUNE = true>
+__device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t tb, int tl, int team, bool active, Hook&& after_first_exchange,
+                                      int fh_col = R4Cfg<LOG2L>::C_FH) {
   typedef R4Cfg<LOG2L> C;
   constexpr int T = C::T, M1 = C::MS1, LB1 = M1 << 4;
   const int b1 = tl / M1, j1 = tl - b1 * M1, base1 = padi(b1 * LB1 + j1), base0 = padi(tl);
   // ---- forward pass 0 (stride T): pruned radix-16, twiddle, store
   if (active) {
-    fft16_fwd_lo8(v);
+    if (PRUNE) fft16_fwd_lo8(v); else fft16<false>(v);
     tm_twiddle<false>(v, tb + C::C_TW0);
 #pragma unroll
     for (int k = 0; k < 16; ++k) buf[base0 + k * T + ((k * T) >> 4)] = v[k];
@@ -155,13 +156,13 @@ __device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t t
     fft_final<false>(v, C::RF);
     {
       uint32_t r0[16], r1[16];
-      sb_tmem_ld16(tb + C::C_FH, r0);
+      sb_tmem_ld16(tb + fh_col, r0);
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         uint32_t(&cur)[16] = (b & 1) ? r1 : r0;
         uint32_t(&nxt)[16] = (b & 1) ? r0 : r1;
         sb_tmem_wait_ld16(cur);
-        if (b < 3) sb_tmem_ld16(tb + C::C_FH + 16 * (b + 1), nxt);
+        if (b < 3) sb_tmem_ld16(tb + fh_col + 16 * (b + 1), nxt);
 #pragma unroll
         for (int q = 0; q < 4; ++q) v[4 * b + q] = cm(v[4 * b + q], tm_c(cur, q));
       }
@@ -657,6 +658,446 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
   if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
 }
 
+
+// =====================================================================================
+// composite convolution lengths L = 3 * L2 (L2 = 1024, 2048) with the v4 data movement: rings with L2 < m <= 1.5 L2 of the
+// outer tiles of a multi-GPU patch (m up to 3072), which a power of two would pad to 4 * L2.  Mathematics as k_inv_l3 /
+// k_fwd_l3 (sb_ringfft2.cu): radix-3 decimation in frequency of the zero-padded input over a group of three teams, each
+// convolving one residue class with its third of the pre-transformed chirp, recombination of the three results.  Per-thread
+// tables (pass twiddles, the three FH thirds, the chirp at this thread's outputs, W_L^{tl}, W_L^{2 tl}) live in Tensor
+// Memory; the spectrum row (inverse) / real row (forward) of the group's next sequence is staged by the bulk-copy engine.
+// =====================================================================================
+template <int LOG2L2>
+struct R5Cfg {
+  typedef R4Cfg<LOG2L2> B;
+  static constexpr int L2 = B::L, T = B::T;
+  static constexpr int NGROUPS = (512 / T) / 3;
+  static constexpr int NTEAMS = 3 * NGROUPS;
+  static constexpr int NT = NTEAMS * T;
+  static constexpr int C_FH3 = 128;                      // [3][16] FH thirds
+  static constexpr int C_CH3 = 320;                      // [3][8] chirp at the outputs of team r
+  static constexpr int C_WB = 416;                       // [2] W_L^{tl}, W_L^{2 tl}  (L = 3 L2)
+  static constexpr int STGI = 3 * L2 + 16;               // inverse staging doubles per group: spectrum row (2m-1 <= 3 L2 - 1)
+  static constexpr int STGF = 6 * L2;                    // forward staging doubles per group: real row (n = 4m <= 6 L2)
+  static constexpr int CH = 3 * L2 / 2;                  // parked outputs per half (forward)
+  static constexpr size_t SMEMI = sizeof(double2) * ((size_t)NTEAMS * B::LP + 32) + sizeof(double) * (size_t)NGROUPS * STGI + 16 * NGROUPS;
+  static constexpr size_t SMEMF = sizeof(double2) * ((size_t)NTEAMS * B::LP + 32) + sizeof(double) * (size_t)NGROUPS * STGF + 16 * NGROUPS;
+  static_assert(T <= 128 && 128 % T == 0, "one table set per TMEM lane");
+};
+
+template <int T>
+__device__ __forceinline__ void group_sync5(int grp) {
+  sb_bar_sync((T >= 64 ? 9 : 1) + grp, 3 * T);
+}
+
+#define W3R5 (-0.5)
+#define W3I5 (-0.86602540378443864676)   // w3 = exp(-2 pi i / 3)
+
+// class + ring tables of a composite class -> Tensor Memory (threads 0..127, lane tid, tl = tid % T)
+template <int LOG2L2>
+__device__ __forceinline__ void fill_class5(uint32_t s_tmem, const double2* __restrict__ twp, int tid) {
+  typedef R5Cfg<LOG2L2> C;
+  constexpr int T = C::T;
+  const int tf = tid % T;
+  const uint32_t tf_b = sb_tmem_warp_base(s_tmem);
+  const double2* tw1 = twp + 15 * T;
+  const double2* xt = tw1 + 15 * C::B::MS1;               // TWB1[T] TWB2[T] C1[16] C2[16]
+  tm_put(tf_b + C::B::C_TW0, make_double2(1.0, 0.0));
+  tm_put(tf_b + C::B::C_TW1, make_double2(1.0, 0.0));
+#pragma unroll
+  for (int k = 1; k < 16; ++k) {
+    tm_put(tf_b + C::B::C_TW0 + 4 * k, twp[(k - 1) * T + tf]);
+    tm_put(tf_b + C::B::C_TW1 + 4 * k, tw1[(k - 1) * C::B::MS1 + (tf % C::B::MS1)]);
+  }
+  tm_put(tf_b + C::C_WB, xt[tf]);
+  tm_put(tf_b + C::C_WB + 4, xt[T + tf]);
+  sb_tmem_wait_st();
+}
+template <int LOG2L2>
+__device__ __forceinline__ void fill_ring5(uint32_t s_tmem, const double2* __restrict__ FH_g, const double2* __restrict__ chirp_g, int m, int tid) {
+  typedef R5Cfg<LOG2L2> C;
+  constexpr int T = C::T, L2 = C::L2;
+  const int tf = tid % T;
+  const uint32_t tf_b = sb_tmem_warp_base(s_tmem);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int e0 = 0; e0 < 16; e0 += 8) {
+      double2 x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = FH_g[(size_t)r * L2 + (e0 + e) * T + tf];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tm_put(tf_b + C::C_FH3 + 64 * r + 4 * (e0 + e), x[e]);
+    }
+    double2 c[8];
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) {
+      const int a0 = (r == 2 ? L2 : 0) + (r == 1 ? L2 / 2 : 0) + n1 * T + tf;
+      c[n1] = chirp_g[a0 < m ? a0 : m - 1];
+    }
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) tm_put(tf_b + C::C_CH3 + 32 * r + 4 * n1, c[n1]);
+  }
+  sb_tmem_wait_st();
+}
+
+// W_L^{j r} for j = n1*T + tl (r = 1, 2): W_L^{r tl} from Tensor Memory times W_L^{r T n1} from the 32-entry shared table
+__device__ __forceinline__ double2 twid5(const double2 wb, const double2* __restrict__ ctab, int r, int n1) {
+  return cm(wb, ctab[(r - 1) * 16 + n1]);
+}
+
+// x thirds are in the group's buffers -> s_r -> convolution -> c_r' back in the buffers
+template <int LOG2L2>
+__device__ __forceinline__ void conv5(double2* const (&gb)[3], uint32_t tb, const double2* __restrict__ ctab, int r, int grp, int team, int tl) {
+  typedef R5Cfg<LOG2L2> C;
+  constexpr int L2 = C::L2, T = C::T;
+  double2 v[16];
+  double2 wb = make_double2(1.0, 0.0);
+  if (r) {
+    uint32_t q[4];
+    sb_tmem_ld4(tb + C::C_WB + 4 * (r - 1), q);
+    sb_tmem_wait_ld4(q);
+    wb = make_double2(sb_u2d(q[0], q[1]), sb_u2d(q[2], q[3]));
+  }
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const int j = n1 * T + tl;
+    double2 x0 = (n1 < 8) ? gb[0][j] : gb[1][j - L2 / 2];
+    if (n1 < 8) {
+      const double2 x1 = gb[2][j];
+      if (r == 0) x0 = x0 + x1;
+      else if (r == 1) x0 = x0 + make_double2(W3R5 * x1.x - W3I5 * x1.y, W3R5 * x1.y + W3I5 * x1.x);
+      else x0 = x0 + make_double2(W3R5 * x1.x + W3I5 * x1.y, W3R5 * x1.y - W3I5 * x1.x);       // w3^2 = conj(w3)
+    }
+    v[n1] = r ? cm(x0, twid5(wb, ctab, r, n1)) : x0;
+  }
+  group_sync5<T>(grp);              // every team has gathered its s_r: the buffers may be overwritten
+  conv4<LOG2L2, void (*)(), false>(v, gb[r], tb, tl, team, true, +[]() {}, C::C_FH3 + 64 * r);
+  team_sync4<T>(team);             // the team's last-pass loads are done
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) {
+    const double2 c = r ? cmc(v[n1], twid5(wb, ctab, r, n1)) : v[n1];
+    gb[r][n1 * T + tl] = c;
+  }
+  group_sync5<T>(grp);              // c_0, c_1', c_2' are in the three buffers
+}
+
+// this team's eight outputs: r = 0: a in [0, L2/2), r = 1: [L2/2, L2), r = 2: [L2, 3 L2/2)
+__device__ __forceinline__ double2 combine5(double2* const (&gb)[3], int r, int i) {
+  const double2 b0 = gb[0][i], b1 = gb[1][i], b2 = gb[2][i];
+  if (r < 2) return b0 + b1 + b2;
+  return b0 + make_double2(W3R5 * b1.x + W3I5 * b1.y, W3R5 * b1.y - W3I5 * b1.x) +
+         make_double2(W3R5 * b2.x - W3I5 * b2.y, W3R5 * b2.y + W3I5 * b2.x);
+}
+
+template <int LOG2L2>
+__global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
+                                                                const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
+                                                                const double* __restrict__ blob, const double* __restrict__ in,
+                                                                long long in_fs, long long in_vs, double* __restrict__ out,
+                                                                long long out_fs, long long out_vs, int out_is_phys, int var0,
+                                                                unsigned lmask, int* counter, int chunk) {
+  typedef R5Cfg<LOG2L2> C;
+  constexpr int L2 = C::L2, T = C::T;
+  SB_DYN_SMEM(double2, sm);
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_chunk;
+  const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
+  const int grp = team / 3, r = team - 3 * grp;
+  double2* const gb[3] = {sm + (size_t)(3 * grp) * C::B::LP, sm + (size_t)(3 * grp + 1) * C::B::LP, sm + (size_t)(3 * grp + 2) * C::B::LP};
+  double2* const ctab = sm + (size_t)C::NTEAMS * C::B::LP;                 // C1[16] C2[16]
+  double* const stg_all = reinterpret_cast<double*>(ctab + 32);
+  double* const stg = stg_all + (size_t)grp * C::STGI;
+  sb_mbar_t* const mbar = reinterpret_cast<sb_mbar_t*>(reinterpret_cast<char*>(stg_all + (size_t)C::NGROUPS * C::STGI) + 16 * grp);
+  if (tid < 32) sb_tmem_alloc(&s_tmem, 512);
+  if (r == 0 && tl == 0) sb_mbar_init(mbar, 1);
+  if (tid < 32) ctab[tid] = twp[15 * T + 15 * C::B::MS1 + 2 * T + tid];
+  sb_fence_mbar_init();
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  sb_tmem_fence_after_sync();
+  const uint32_t tb = sb_tmem_warp_base(s_tmem);
+  if (tid < 128) fill_class5<LOG2L2>(s_tmem, twp, tid);
+  unsigned phase = 0;
+  int cur_ring = -1;
+  const int total = nwork * nvars;
+  const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  for (;;) {
+  if (counter) {
+    if (tid == 0) s_chunk = atomicAdd(counter, 1);
+    __syncthreads();
+    w_begin = s_chunk * chunk;
+    w_end = w_begin + chunk < total ? w_begin + chunk : total;
+    __syncthreads();
+    if (w_begin >= total) break;
+  }
+  for (int w = w_begin; w < w_end; ++w) {
+    const int item = w / nvars, v_ = w - item * nvars;
+    const LWork wk = work[item];
+    const RingPlan pl = plans[wk.r];
+    const int n = pl.n, m = pl.m;
+    const double2* chirp_g = reinterpret_cast<const double2*>(blob + pl.off);
+    const double2* FH_g = chirp_g + 3 * m;
+    const double2* PQ = reinterpret_cast<const double2*>(blob + pl.off2);
+    if (wk.r != cur_ring) {
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      if (tid < 128) fill_ring5<LOG2L2>(s_tmem, FH_g, chirp_g, m, tid);
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      cur_ring = wk.r;
+    }
+    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const int nseq = 2 * wk.nrows;
+    auto row_of = [&](int s) -> const double* {
+      const int rho = wk.row0 + (s >> 1), zb = rho / 5, f = rho - zb * 5;
+      return in + (long long)(f < 3 ? f : 0) * in_fs + (long long)v_ * in_vs + (long long)zb * g.W + woff;
+    };
+    auto wanted = [&](int s) { const int rho = wk.row0 + (s >> 1); return ((lmask >> (rho % 5)) & 1u) != 0u; };
+    auto request = [&](int s) {
+      const double* sp = row_of(s);
+      const int sh = (int)(((uintptr_t)sp >> 3) & 1);
+      const unsigned bytes = (unsigned)(((sh + 2 * m - 1) * 8 + 15) & ~15);
+      sb_fence_proxy_async();
+      sb_mbar_expect_tx(mbar, bytes);
+      sb_bulk_g2s(stg, sp - sh, bytes, mbar);
+    };
+    int s = grp;
+    while (s < nseq && !wanted(s)) s += C::NGROUPS;
+    group_sync5<T>(grp);               // the group's previous sequence (previous item) has left the staging row and the buffers
+    if (s < nseq && r == 0 && tl == 0) request(s);
+    while (s < nseq) {
+      int s_next = s + C::NGROUPS;
+      while (s_next < nseq && !wanted(s_next)) s_next += C::NGROUPS;
+      const int row = s >> 1, half = s & 1;
+      const int rho = wk.row0 + row;
+      const int zb = rho / 5, f = rho - zb * 5;
+      sb_mbar_wait(mbar, phase);
+      phase ^= 1u;
+      {                              // prologue: this team's third of x (formula: k_inv_l4)
+        const double* st = stg + (int)(((uintptr_t)row_of(s) >> 3) & 1);
+        const double2* Ph = PQ + (size_t)(2 * half) * m;
+        const double2* Qh = Ph + m;
+#pragma unroll
+        for (int h4 = 0; h4 < 4; ++h4) {
+          double cx[2], cy[2], qx[2], qy[2];
+          double2 Pk[2], Qk[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k0 = r * (L2 / 2) + (h4 * 2 + j) * T + tl;
+            const int k = k0 < m ? k0 : m - 1;
+            const int km = k ? m - k : 0;
+            cx[j] = st[k ? 2 * k - 1 : 0]; cy[j] = st[2 * k];
+            qx[j] = st[km ? 2 * km - 1 : 0]; qy[j] = st[2 * km];
+            Pk[j] = Ph[k]; Qk[j] = Qh[k];
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int i = (h4 * 2 + j) * T + tl;
+            const int k0 = r * (L2 / 2) + i;
+            const int k = k0 < m ? k0 : m - 1;
+            const int km = k ? m - k : 0;
+            const double2 ck = make_double2(cx[j], k ? cy[j] : 0.0);
+            const double2 cq = make_double2(qx[j], km ? qy[j] : 0.0);
+            double2 X, Y;
+            if (f < 3) {
+              X = make_double2(ck.x, -ck.y);
+              Y = cq;
+            } else if (f == 3) {
+              const double dk = (double)k, dq = (double)km;
+              X = make_double2(-dk * ck.y, -dk * ck.x);
+              Y = make_double2(-dq * cq.y, dq * cq.x);
+            } else {
+              const double sk = -(double)k * (double)k, sq = -(double)km * (double)km;
+              X = make_double2(sk * ck.x, -sk * ck.y);
+              Y = make_double2(sq * cq.x, sq * cq.y);
+            }
+            const double2 u = cm(X, Pk[j]) + cm(Y, Qk[j]);
+            gb[r][i] = k0 < m ? u : make_double2(0.0, 0.0);
+          }
+        }
+      }
+      group_sync5<T>(grp);            // x is complete and the staging row has been read by all three teams
+      if (r == 0 && tl == 0 && s_next < nseq) request(s_next);
+      __syncwarp();
+      conv5<LOG2L2>(gb, tb, ctab, r, grp, team, tl);
+      {
+        double* orow;
+        if (out_is_phys)
+          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
+        else
+          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+        uint32_t r0[16], r1[16];
+        sb_tmem_ld16(tb + C::C_CH3 + 32 * r, r0);
+        sb_tmem_ld16(tb + C::C_CH3 + 32 * r + 16, r1);
+        sb_tmem_wait_ld16(r0);
+        sb_tmem_wait_ld16(r1);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int i = (r == 1 ? L2 / 2 : 0) + n1 * T + tl;
+          const int a = (r == 2 ? L2 : 0) + i;
+          const double2 ch = n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3);
+          if (a < m) {
+            const double2 Y = cm(combine5(gb, r, i), ch);
+            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+          }
+        }
+      }
+      group_sync5<T>(grp);            // the group's outputs have been read out of the buffers
+      s = s_next;
+    }
+  }
+  if (!counter) break;
+  }
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
+}
+
+// forward: both packed sequences of a row go through the group one after the other (the real row is staged once); their
+// raw convolution outputs are parked in a per-group global scratch line (L2-resident) and combined with A0..A3 at the end.
+template <int LOG2L2>
+__global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_fwd_l5(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
+                                                                const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
+                                                                const double* __restrict__ blob, const double* __restrict__ in,
+                                                                long long in_vs, double* __restrict__ mirror, long long mirror_vs,
+                                                                double* __restrict__ out, long long out_vs, double2* scratch,
+                                                                int* counter, int chunk) {
+  typedef R5Cfg<LOG2L2> C;
+  constexpr int L2 = C::L2, T = C::T;
+  SB_DYN_SMEM(double2, sm);
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_chunk;
+  const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
+  const int grp = team / 3, r = team - 3 * grp;
+  double2* const gb[3] = {sm + (size_t)(3 * grp) * C::B::LP, sm + (size_t)(3 * grp + 1) * C::B::LP, sm + (size_t)(3 * grp + 2) * C::B::LP};
+  double2* const ctab = sm + (size_t)C::NTEAMS * C::B::LP;
+  double* const stg_all = reinterpret_cast<double*>(ctab + 32);
+  const double* const stg = stg_all + (size_t)grp * C::STGF;
+  sb_mbar_t* const mbar = reinterpret_cast<sb_mbar_t*>(reinterpret_cast<char*>(stg_all + (size_t)C::NGROUPS * C::STGF) + 16 * grp);
+  double2* const park = scratch + ((size_t)blockIdx.x * C::NGROUPS + grp) * (2 * C::CH);   // [2 halves][CH]
+  if (tid < 32) sb_tmem_alloc(&s_tmem, 512);
+  if (r == 0 && tl == 0) sb_mbar_init(mbar, 1);
+  if (tid < 32) ctab[tid] = twp[15 * T + 15 * C::B::MS1 + 2 * T + tid];
+  sb_fence_mbar_init();
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  sb_tmem_fence_after_sync();
+  const uint32_t tb = sb_tmem_warp_base(s_tmem);
+  if (tid < 128) fill_class5<LOG2L2>(s_tmem, twp, tid);
+  unsigned phase = 0;
+  int cur_ring = -1;
+  const int total = nwork * nvars;
+  const int per_cta = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  int w_begin = (int)blockIdx.x * per_cta, w_end = w_begin + per_cta < total ? w_begin + per_cta : total;
+  for (;;) {
+  if (counter) {
+    if (tid == 0) s_chunk = atomicAdd(counter, 1);
+    __syncthreads();
+    w_begin = s_chunk * chunk;
+    w_end = w_begin + chunk < total ? w_begin + chunk : total;
+    __syncthreads();
+    if (w_begin >= total) break;
+  }
+  for (int w = w_begin; w < w_end; ++w) {
+    const int item = w / nvars, v_ = w - item * nvars;
+    const LWork wk = work[item];
+    const RingPlan pl = plans[wk.r];
+    const int n = pl.n, m = pl.m;
+    const double2* chirp_g = reinterpret_cast<const double2*>(blob + pl.off);
+    const double2* FH_g = chirp_g + 3 * m;
+    const double2* AF = reinterpret_cast<const double2*>(blob + pl.off2) + (size_t)4 * m;
+    if (wk.r != cur_ring) {
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      if (tid < 128) fill_ring5<LOG2L2>(s_tmem, FH_g, chirp_g, m, tid);
+      sb_tmem_fence_before_sync();
+      __syncthreads();
+      sb_tmem_fence_after_sync();
+      cur_ring = wk.r;
+    }
+    const long long hoff = g.ring_hoff[wk.r];
+    const double* src = in + (long long)v_ * in_vs + (long long)g.bz * hoff;
+    double* mir = mirror ? mirror + (long long)v_ * mirror_vs + (long long)g.bz * hoff : nullptr;
+    double* dst = out + (long long)v_ * out_vs + g.ring_woff[wk.r];
+    auto request = [&](int row) {
+      sb_fence_proxy_async();
+      sb_mbar_expect_tx(mbar, (unsigned)n * 8u);
+      sb_bulk_g2s(const_cast<double*>(stg), src + (long long)(wk.row0 + row) * n, (unsigned)n * 8u, mbar);
+    };
+    group_sync5<T>(grp);
+    if (r == 0 && tl == 0 && grp < wk.nrows) request(grp);
+    for (int row = grp; row < wk.nrows; row += C::NGROUPS) {
+      sb_mbar_wait(mbar, phase);
+      phase ^= 1u;
+      for (int half = 0; half < 2; ++half) {
+        group_sync5<T>(grp);          // the buffers are free (previous half's outputs parked)
+        {
+          const double* rp = stg + 2 * half;
+          double* mp = mir ? mir + (long long)(wk.row0 + row) * n + 2 * half : nullptr;
+          uint32_t r0[16], r1[16];
+          sb_tmem_ld16(tb + C::C_CH3 + 32 * r, r0);
+          sb_tmem_ld16(tb + C::C_CH3 + 32 * r + 16, r1);
+          double2 x[8];
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) {
+            const int a0 = (r == 2 ? L2 : 0) + (r == 1 ? L2 / 2 : 0) + n1 * T + tl, a = a0 < m ? a0 : m - 1;
+            x[n1] = *reinterpret_cast<const double2*>(rp + 4 * a);
+          }
+          sb_tmem_wait_ld16(r0);
+          sb_tmem_wait_ld16(r1);
+#pragma unroll
+          for (int n1 = 0; n1 < 8; ++n1) {
+            const int i = n1 * T + tl;
+            const int a0 = (r == 2 ? L2 : 0) + (r == 1 ? L2 / 2 : 0) + i, a = a0 < m ? a0 : m - 1;
+            if (mp && a0 < m) *reinterpret_cast<double2*>(mp + 4 * a) = x[n1];
+            const double2 y = cm(x[n1], n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3));
+            // team r holds x[r L2/2 + i] at gb[r][i]: thirds of L2/2 entries each... (layout of k_fwd_l3: third r at gb[r][0 .. L2/2))
+            gb[r][i] = a0 < m ? y : make_double2(0.0, 0.0);
+          }
+        }
+        group_sync5<T>(grp);          // x is complete
+        if (half == 1 && r == 0 && tl == 0 && row + C::NGROUPS < wk.nrows) request(row + C::NGROUPS);   // staging row read by all
+        __syncwarp();
+        conv5<LOG2L2>(gb, tb, ctab, r, grp, team, tl);
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+          const int i = (r == 1 ? L2 / 2 : 0) + n1 * T + tl;
+          const int a = (r == 2 ? L2 : 0) + i;
+          if (a < m) park[(size_t)half * C::CH + a] = combine5(gb, r, i);
+        }
+      }
+      group_sync5<T>(grp);            // both halves are parked (global writes of the group are ordered by the barrier)
+      {
+        double* o = dst + (long long)(wk.row0 + row) * g.W;
+        const double2* p0 = park;
+        const double2* p1 = park + C::CH;
+        for (int k = r * T + tl; k < m; k += 3 * T) {
+          const int km = k ? m - k : 0;
+          const double2 b0 = p0[k], b0m = p0[km], b1 = p1[k], b1m = p1[km];
+          double2 X = cm(b0, AF[k]) + cm(make_double2(b0m.x, -b0m.y), AF[m + k]);
+          X = X + cm(b1, AF[2 * m + k]) + cm(make_double2(b1m.x, -b1m.y), AF[3 * m + k]);
+          if (k == 0) {
+            o[0] = X.x;
+          } else {
+            o[2 * k - 1] = X.x;
+            o[2 * k] = X.y;
+          }
+        }
+      }
+    }
+  }
+  if (!counter) break;
+  }
+  sb_tmem_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) sb_tmem_dealloc(s_tmem, 512);
+}
+
 // =====================================================================================
 // launchers
 // =====================================================================================
@@ -736,6 +1177,67 @@ void launch_fwd_l4(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
     case 2048: launch_fwd4<11>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs); break;
     case 4096: launch_fwd4<12>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs); break;
     default: throw std::runtime_error("launch_fwd_l4: unsupported convolution length");
+  }
+}
+
+// ---- composite lengths with the v4 data movement
+bool fft5_supported(int L) {
+  static const char* env = std::getenv("SB_FFT4");
+  if (env && std::atoi(env) == 0) return false;
+  return L == 3072 || L == 6144;
+}
+
+template <int LOG2L2>
+static void launch_inv5(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, const double* twp,
+                        const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs,
+                        long long in_vs, double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
+  typedef R5Cfg<LOG2L2> C;
+  cudaError_t e = cudaFuncSetAttribute(k_inv_l5<LOG2L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEMI);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int total = nwork * nvars, cap = fft_grid_cap(c), gx = total < cap ? total : cap;
+  int* counter = take_counter(c);
+  SB_LAUNCH(k_inv_l5<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEMI, c.stream, g, work, nwork, nvars,
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
+            c.need.lmask, counter, 2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l5 launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+void launch_inv_l5(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs, long long in_vs,
+                   double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
+  switch (L / 3) {
+    case 1024: launch_inv5<10>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
+    case 2048: launch_inv5<11>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); break;
+    default: throw std::runtime_error("launch_inv_l5: unsupported convolution length");
+  }
+}
+
+template <int LOG2L2>
+static void launch_fwd5(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, const double* twp,
+                        const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs,
+                        double* mirror, long long mirror_vs, double* out, long long out_vs, double* scratch) {
+  typedef R5Cfg<LOG2L2> C;
+  cudaError_t e = cudaFuncSetAttribute(k_fwd_l5<LOG2L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEMF);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+  const int total = nwork * nvars, cap = fft_grid_cap(c), gx = total < cap ? total : cap;
+  int* counter = take_counter(c);
+  SB_LAUNCH(k_fwd_l5<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEMF, c.stream, g, work, nwork, nvars,
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs,
+            reinterpret_cast<double2*>(scratch), counter, 2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_l5 launch: ") + cudaGetErrorString(e));
+  if (c.launches) ++*c.launches;
+}
+
+void launch_fwd_l5(const LaunchCtx& c, const DevGrid& g, const LWork* work, int nwork, int L, const double* twp,
+                   const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_vs, double* mirror,
+                   long long mirror_vs, double* out, long long out_vs, double* scratch) {
+  switch (L / 3) {
+    case 1024: launch_fwd5<10>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs, scratch); break;
+    case 2048: launch_fwd5<11>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs, scratch); break;
+    default: throw std::runtime_error("launch_fwd_l5: unsupported convolution length");
   }
 }
 

@@ -546,8 +546,12 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     int L = classes[ci].L;
     if (classes[ci].R == 3) {
       if (!hostwork2 || !nwork2 || !fft3_scratch) throw std::runtime_error("composite FFT class without a v2 work list");
-      launch_fwd_l3(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
-                    mirror_vstride, out, out_vstride, fft3_scratch);
+      if (fft5_supported(L) && (uintptr_t)in % 16 == 0 && in_vstride % 2 == 0)
+        launch_fwd_l5(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+                      mirror_vstride, out, out_vstride, fft3_scratch);
+      else
+        launch_fwd_l3(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_vstride, mirror,
+                      mirror_vstride, out, out_vstride, fft3_scratch);
       continue;
     }
     if (classes[ci].fast && nwork2 && fft4_supported(L, true) && (uintptr_t)in % 16 == 0 &&
@@ -679,8 +683,12 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     int L = classes[ci].L;
     if (classes[ci].R == 3) {
       if (!hostwork2 || !nwork2) throw std::runtime_error("composite FFT class without a v2 work list");
-      launch_inv_l3(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
-                    out, out_fstride, out_vstride, out_is_phys, var0);
+      if (fft5_supported(L))
+        launch_inv_l5(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+                      out, out_fstride, out_vstride, out_is_phys, var0);
+      else
+        launch_inv_l3(c, g, work2[ci] + j0, nwork2, L, twp[ci], plans, blob, nvars, in, in_fstride, in_vstride,
+                      out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
     if (classes[ci].fast && nwork2 && fft4_supported(L, false)) {

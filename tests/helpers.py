@@ -86,6 +86,12 @@ def transform_cases():
         "RLZ_tile_fft4_L2048": G.GridParameters(geometry="RLZ", xmin=290, xmax=291, num_cells=1, zmin=0, zmax=5, zDim=8,
                                                 vars={"h": 1}, spectralIndexL=291),
         "RL_tile_fft4_L4096": G.GridParameters(geometry="RL", xmin=600, xmax=601, num_cells=1, vars={"h": 1}, spectralIndexL=601),
+        # composite lengths with the v4 data movement (k_inv_l5 / k_fwd_l5): m = 1030..1032 (L = 3072 = 3 x 1024, two groups of three
+        # teams) and m = 2071..2073 (L = 6144 = 3 x 2048, one group)
+        "RL_tile_fft5_L3072": G.GridParameters(geometry="RL", xmin=343, xmax=344, num_cells=1, vars={"h": 1, "u": 2}, spectralIndexL=344),
+        "RLZ_tile_fft5_L3072": G.GridParameters(geometry="RLZ", xmin=343, xmax=344, num_cells=1, zmin=0, zmax=5, zDim=8,
+                                                vars={"h": 1}, spectralIndexL=344),
+        "RL_tile_fft5_L6144": G.GridParameters(geometry="RL", xmin=690, xmax=691, num_cells=1, vars={"h": 1}, spectralIndexL=691),
         "RZ_z32_nobc": G.GridParameters(geometry="RZ", xmin=0, xmax=10, num_cells=13, zmin=0, zmax=5, zDim=32,
                                         vars={"s": 1, "w": 2}),
     }
