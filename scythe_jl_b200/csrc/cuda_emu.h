@@ -109,6 +109,8 @@ static inline double atomicAdd(double* p, double v) {  // blocks run serially, t
 }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static inline void __threadfence_block() {}
+static inline void __threadfence() {}
 using std::fma;
 using std::fabs;
 using std::sqrt;

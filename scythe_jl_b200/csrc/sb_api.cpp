@@ -104,6 +104,8 @@ struct sb_grid {
   double* d_fwdB = nullptr;     // DMMA B-fragment tables of the analysis (forward) matrix
   std::vector<char> z_bcfree;   // per variable: BCB == BCT == R0
   std::vector<int> zt_first;    // [rDim+1] first z tile of every ring (tiles are ordered by ring)
+  SmallRings small;             // merged launch of the generic-kernel ring classes
+  std::vector<SmallCls> h_smallcls;
   // overlapped step (tile_step_overlapped): FP64-bound ring FFTs and HBM-bound kernels on two streams, by ring batches
   struct Overlap {
     bool ready = false;
@@ -123,7 +125,21 @@ struct sb_grid {
   int ndims = 1;
 
   Profiler prof;
-  LaunchCtx ctx() { return LaunchCtx{stream, &launches, &prof}; }
+  LaunchCtx ctx() {
+    LaunchCtx c{stream, &launches, &prof};
+    static const bool merge_small = !(std::getenv("SB_MERGE_SMALL") && std::atoi(std::getenv("SB_MERGE_SMALL")) == 0);
+    if (merge_small && small.cls) c.small = &small;
+    // SB_FFT_DYNAMIC=<chunk>: ring FFT work shares from an atomic counter (<chunk> items at a time) instead of equal contiguous
+    // shares, on the ordinary one-stream step as well (A/B switch; the overlapped step always uses it)
+    static const int dyn = std::getenv("SB_FFT_DYNAMIC") ? std::atoi(std::getenv("SB_FFT_DYNAMIC")) : 0;
+    if (dyn > 0) {
+      if (!ov.d_counters) {
+        if (cudaMalloc((void**)&ov.d_counters, 512 * sizeof(int)) != cudaSuccess) ov.d_counters = nullptr;
+      }
+      if (ov.d_counters) { c.counters = ov.d_counters; c.counter_next = &ov.counter_next; c.ncounters = 512; c.fft_chunk = dyn; }
+    }
+    return c;
+  }
   template <class T> T* up(const std::vector<T>& h) { T* d = dev_upload(h); owned.push_back(d); return d; }
   long long slot_stride() const { return dg.N * dg.V; }
 
@@ -352,6 +368,26 @@ static void build_grid(sb_grid* G) {
         for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork2[cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
       }
     }
+    {   // merged work lists of the classes the generic kernels serve (not fast, not composite)
+      std::vector<LWork> iw, fw;
+      std::vector<SmallCls> sc(G->classes.size(), SmallCls{0, 0, nullptr});
+      size_t smem = 0;
+      for (size_t ci = G->classes.size(); ci-- > 0;) {
+        const FftClass& cl = G->classes[ci];
+        if (cl.fast || cl.R == 3) continue;
+        iw.insert(iw.end(), G->iwork[ci].begin(), G->iwork[ci].end());
+        fw.insert(fw.end(), G->fwork[ci].begin(), G->fwork[ci].end());
+        smem = std::max(smem, (size_t)2 * sb_rows_per_cta(cl.L) * cl.L * 16);
+      }
+      G->small.niwork = (int)iw.size();
+      G->small.nfwork = (int)fw.size();
+      G->small.smem = smem;
+      if (!iw.empty()) {
+        G->small.iwork = G->up(iw);
+        G->small.fwork = G->up(fw);
+      }
+      G->h_smallcls = sc;     // tw pointers are filled in below, once the class tables are on the device
+    }
     size_t f3 = 0;
     for (auto& cl : G->classes)
       if (cl.R == 3) f3 = std::max(f3, fft3_scratch_doubles(cl.L));
@@ -363,6 +399,13 @@ static void build_grid(sb_grid* G) {
       G->d_iwork.push_back(G->up(G->iwork[c]));
       G->d_tw.push_back(G->up(G->classes[c].tw));
       G->d_twp.push_back(G->up(G->classes[c].twp));
+    }
+    if (G->small.niwork > 0) {
+      for (size_t c = 0; c < G->classes.size(); ++c) {
+        G->h_smallcls[c].log2L = G->classes[c].log2L;
+        G->h_smallcls[c].tw = reinterpret_cast<const double2*>(G->d_tw[c]);
+      }
+      G->small.cls = G->up(G->h_smallcls);
     }
   }
   G->spectralB = dev_zeros(d.S * d.V, G->stream);
@@ -1154,7 +1197,7 @@ static void overlap_prepare(sb_grid* G) {
   ov.ev_z.resize(ov.batches.size());
   for (auto& e : ov.ev_il) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : ov.ev_z) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  CU(cudaMalloc((void**)&ov.d_counters, 512 * sizeof(int)));
+  if (!ov.d_counters) CU(cudaMalloc((void**)&ov.d_counters, 512 * sizeof(int)));
   const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
   ov.buf_doubles = 8 * ((slN + 15) & ~15LL) + 10 * ((szN + 15) & ~15LL) + 64;
   CU(cudaMalloc((void**)&ov.buf, (size_t)ov.buf_doubles * sizeof(double)));

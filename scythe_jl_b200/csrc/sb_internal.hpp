@@ -104,6 +104,14 @@ struct Profiler {
 //   lmask: ring rows       value | r | rr | lambda | lambda-lambda  (inv_l outputs, bit f)
 //   zmask: fields the Chebyshev synthesis reads (bit f);  zsel: of field 0, bit 0 = value, 1 = d/dz, 2 = d2/dz2
 struct K3Need { unsigned smask = 7, lmask = 31, zmask = 31, zsel = 7; };
+// all generic-kernel (L < 256) ring classes of a grid in ONE launch: merged work lists + per-class parameters
+struct SmallCls { int log2L; int pad; const double2* tw; };
+struct SmallRings {
+  const LWork* iwork = nullptr; int niwork = 0;      // inverse items of every small class, largest class first
+  const LWork* fwork = nullptr; int nfwork = 0;
+  const SmallCls* cls = nullptr;                     // device, indexed by RingPlan::cls
+  size_t smem = 0;                                   // largest per-class requirement
+};
 struct LaunchCtx {
   cudaStream_t stream; long long* launches; Profiler* prof; K3Need need;
   // overlapped step only: restrict ring work lists / z tiles to the rings [r_lo, r_hi) (r_hi < 0: all rings), dynamic work
@@ -111,7 +119,9 @@ struct LaunchCtx {
   int r_lo = 0, r_hi = -1;
   int* counters = nullptr; int* counter_next = nullptr; int ncounters = 0;
   int sm_reserve = 0;
+  int fft_chunk = 2;               // items per dynamic work share
   int mem_grid_sms = 0;            // > 0: persistent HBM-bound kernels size their grid for this many SMs
+  const SmallRings* small = nullptr;
 };
 struct ProfScope {
   cudaStream_t s;

@@ -721,6 +721,11 @@ bool fft2_supported(int L, bool forward) {
 }
 
 int fft2_rows_per_item(int L, bool forward) {
+  // experiment switch: SB_FFT_ITEM_ROWS_INV / _FWD = rows per work item for every class
+  static const int env_i = std::getenv("SB_FFT_ITEM_ROWS_INV") ? std::atoi(std::getenv("SB_FFT_ITEM_ROWS_INV")) : 0;
+  static const int env_f = std::getenv("SB_FFT_ITEM_ROWS_FWD") ? std::atoi(std::getenv("SB_FFT_ITEM_ROWS_FWD")) : 0;
+  if (!forward && env_i > 0) return env_i;
+  if (forward && env_f > 0) return env_f;
   if (L % 3 == 0) {               // composite: a group of three teams per sequence
     const int ngroups = (512 / (L / 48)) / 3;
     return forward ? 4 * ngroups : 8 * (ngroups > 1 ? ngroups / 2 + (ngroups & 1) : 1);

@@ -1133,7 +1133,7 @@ static void launch_inv4(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   int* counter = take_counter(c);     // non-null: the launch shares the chip with another stream's kernels
   SB_LAUNCH(k_inv_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
-            c.need.lmask, counter, 2);
+            c.need.lmask, counter, c.fft_chunk);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l4 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;
@@ -1162,7 +1162,7 @@ static void launch_fwd4(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   const int total = nwork * nvars, cap = fft_grid_cap(c), gx = total < cap ? total : cap;
   int* counter = take_counter(c);
   SB_LAUNCH(k_fwd_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
-            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs, counter, 2);
+            reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs, counter, c.fft_chunk);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_l4 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;
@@ -1198,7 +1198,7 @@ static void launch_inv5(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   int* counter = take_counter(c);
   SB_LAUNCH(k_inv_l5<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEMI, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
-            c.need.lmask, counter, 2);
+            c.need.lmask, counter, c.fft_chunk);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_inv_l5 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;
@@ -1225,7 +1225,7 @@ static void launch_fwd5(const LaunchCtx& c, const DevGrid& g, const LWork* work,
   int* counter = take_counter(c);
   SB_LAUNCH(k_fwd_l5<LOG2L2>, dim3(gx), dim3(C::NT), C::SMEMF, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_vs, mirror, mirror_vs, out, out_vs,
-            reinterpret_cast<double2*>(scratch), counter, 2);
+            reinterpret_cast<double2*>(scratch), counter, c.fft_chunk);
   e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("k_fwd_l5 launch: ") + cudaGetErrorString(e));
   if (c.launches) ++*c.launches;

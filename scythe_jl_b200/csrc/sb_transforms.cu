@@ -434,16 +434,19 @@ __device__ void bluestein_conv(double2* buf, int log2L, int ndft, const double2*
 // =====================================================================================
 // ring forward FFT: rows of n real points -> retained coefficients k = 0..ri (phase-corrected, /n)
 // =====================================================================================
-__global__ void __launch_bounds__(512) k_fwd_l(DevGrid g, const LWork* __restrict__ work, int log2L,
-                                               const double2* __restrict__ tw, const RingPlan* __restrict__ plans,
+__global__ void __launch_bounds__(512) k_fwd_l(DevGrid g, const LWork* __restrict__ work, int log2L_arg,
+                                               const double2* __restrict__ tw_arg, const RingPlan* __restrict__ plans,
                                                const double* __restrict__ blob, const double* __restrict__ in,
                                                long long in_vs, double* __restrict__ mirror, long long mirror_vs,
-                                               double* __restrict__ out, long long out_vs) {
+                                               double* __restrict__ out, long long out_vs, const SmallCls* __restrict__ cls) {
   SB_DYN_SMEM(double2, buf);
   const LWork wk = work[blockIdx.x];
   const int v = blockIdx.y;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const RingPlan pl = plans[wk.r];
+  // merged launch over all small classes (cls != null): the item's ring names its class
+  const int log2L = cls ? cls[pl.cls].log2L : log2L_arg;
+  const double2* __restrict__ tw = cls ? cls[pl.cls].tw : tw_arg;
   const int n = pl.n, m = pl.m, L = 1 << log2L;
   const double2* chirp = reinterpret_cast<const double2*>(blob + pl.off);
   const double2* wkk = chirp + m;
@@ -536,7 +539,9 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   long long out_vstride, const std::vector<std::vector<LWork>>* hostwork2, const LWork* const* work2,
                   double* fft3_scratch) {
   ProfScope prof_scope_(c, "fwd_l");
+  const bool merged = c.small && c.small->nfwork > 0 && c.r_hi < 0;   // every small (generic-kernel) class in one launch
   for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
+    if (merged && !classes[ci].fast && classes[ci].R != 3) continue;
     int i0, i1, j0 = 0, j1 = 0;
     ring_block(c, hostwork[ci], i0, i1);
     const int nwork = i1 - i0;
@@ -576,7 +581,14 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
     SB_LAUNCH(k_fwd_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci] + i0, classes[ci].log2L,
               reinterpret_cast<const double2*>(tw[ci]), plans, blob, in, in_vstride, mirror, mirror_vstride, out,
-              out_vstride);
+              out_vstride, nullptr);
+    SB_CHECK_LAUNCH();
+    count(c);
+  }
+  if (merged) {
+    opt_in_smem(k_fwd_l, c.small->smem);
+    SB_LAUNCH(k_fwd_l, dim3(c.small->nfwork, nvars), dim3(256), c.small->smem, c.stream, g, c.small->fwork, 0, nullptr, plans, blob,
+              in, in_vstride, mirror, mirror_vstride, out, out_vstride, c.small->cls);
     SB_CHECK_LAUNCH();
     count(c);
   }
@@ -586,17 +598,19 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
 // ring inverse FFT: spectra (value, d/dr, d2/dr2) -> 5 real rows (value, r, rr, lambda, lambda-lambda)
 // rows of one ring are indexed rho = zb*5 + f
 // =====================================================================================
-__global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restrict__ work, int log2L,
-                                               const double2* __restrict__ tw, const RingPlan* __restrict__ plans,
+__global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restrict__ work, int log2L_arg,
+                                               const double2* __restrict__ tw_arg, const RingPlan* __restrict__ plans,
                                                const double* __restrict__ blob, const double* __restrict__ in,
                                                long long in_fs, long long in_vs, double* __restrict__ out,
                                                long long out_fs, long long out_vs, int out_is_phys, int var0,
-                                               unsigned lmask) {
+                                               unsigned lmask, const SmallCls* __restrict__ cls) {
   SB_DYN_SMEM(double2, buf);
   const LWork wk = work[blockIdx.x];
   const int v = blockIdx.y;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const RingPlan pl = plans[wk.r];
+  const int log2L = cls ? cls[pl.cls].log2L : log2L_arg;
+  const double2* __restrict__ tw = cls ? cls[pl.cls].tw : tw_arg;
   const int n = pl.n, m = pl.m, L = 1 << log2L;
   const double2* chirp = reinterpret_cast<const double2*>(blob + pl.off);
   const double2* wkk = chirp + m;
@@ -673,7 +687,9 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                   long long in_fstride, long long in_vstride, double* out, long long out_fstride, long long out_vstride,
                   int out_is_phys, int var0, const std::vector<std::vector<LWork>>* hostwork2, const LWork* const* work2) {
   ProfScope prof_scope_(c, "inv_l");
+  const bool merged = c.small && c.small->niwork > 0 && c.r_hi < 0;
   for (size_t ci = classes.size(); ci-- > 0;) {   // largest convolution length first
+    if (merged && !classes[ci].fast && classes[ci].R != 3) continue;
     int i0, i1, j0 = 0, j1 = 0;
     ring_block(c, hostwork[ci], i0, i1);
     const int nwork = i1 - i0;
@@ -712,7 +728,14 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
     SB_LAUNCH(k_inv_l, dim3(nwork, nvars), dim3(threads), smem, c.stream, g, work[ci] + i0, classes[ci].log2L,
               reinterpret_cast<const double2*>(tw[ci]), plans, blob, in, in_fstride, in_vstride, out, out_fstride,
-              out_vstride, out_is_phys, var0, c.need.lmask);
+              out_vstride, out_is_phys, var0, c.need.lmask, nullptr);
+    SB_CHECK_LAUNCH();
+    count(c);
+  }
+  if (merged) {
+    opt_in_smem(k_inv_l, c.small->smem);
+    SB_LAUNCH(k_inv_l, dim3(c.small->niwork, nvars), dim3(256), c.small->smem, c.stream, g, c.small->iwork, 0, nullptr, plans, blob,
+              in, in_fstride, in_vstride, out, out_fstride, out_vstride, out_is_phys, var0, c.need.lmask, c.small->cls);
     SB_CHECK_LAUNCH();
     count(c);
   }
