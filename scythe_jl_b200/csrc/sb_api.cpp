@@ -1084,13 +1084,15 @@ static void grid_inverse_advection_fused(sb_grid* P, sb_grid* T, const EqParams&
   double* SZ = T->scratch + sz_off;         // [7][szN]   h: 5 rows | u | v
   T->slot0_src = nullptr;                   // the state the step starts from is synthesised in registers
   LaunchCtx c = T->ctx();
-  const unsigned slots[3] = {31u, 1u, 1u};
-  for (int v = 0; v < 3; ++v) {
-    c.need = k3_need_from_slots(t, slots[v]);
-    launch_inv_r(c, t, p, 1, P->spectralA + (long long)v * p.S, p.S, SL, slN, slN, 0, v);
-    launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, 1, SL, slN,
-                 slN, SZ + (v ? (4 + v) * szN : 0), szN, szN, 0, v, &T->iwork2, T->d_iwork2.data());
-  }
+  // h: five rows (value, r, rr, l, ll) from three spectra; u and v: the value row only, both in one pass (same masks)
+  c.need = k3_need_from_slots(t, 31u);
+  launch_inv_r(c, t, p, 1, P->spectralA, p.S, SL, slN, slN, 0, 0);
+  launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, 1, SL, slN,
+               slN, SZ, szN, szN, 0, 0, &T->iwork2, T->d_iwork2.data());
+  c.need = k3_need_from_slots(t, 1u);
+  launch_inv_r(c, t, p, 2, P->spectralA + p.S, p.S, SL, 2 * slN, slN, 0, 1);          // SL[0] = u spectrum, SL[1] = v spectrum
+  launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, 2, SL,
+               2 * slN, slN, SZ + 5 * szN, szN, szN, 0, 1, &T->iwork2, T->d_iwork2.data());
   launch_inv_z_advection(c, t, T->d_ztiles, T->nztiles, SZ, szN, T->d_parB, ep, a, tq);
 }
 
