@@ -588,16 +588,36 @@ def run_ours(args):
                "K4": ("k_pointwise",)}[top[:2]]      # ("K3+K4 ..." starts with K3: k_inv_z matches k_inv_z_advection too)
         rows = [v for k, v in pk.items() if any(s_ in k for s_ in sel)]
         traffic = 1e9 * sum(r["dram_read_GB"] + r["dram_write_GB"] for r in rows)
-        fft = [v for k, v in pk.items() if "k_inv_l2" in k]
+        fft = [v for k, v in pk.items() if "k_inv_l" in k]
         ncu_note = {"file": "profiles/" + prof_name, "kernel_src_sha16": src_hash,
-                    "k_inv_l2_fp64_pipe_pct": sum(r["fp64_pipe_pct"] * r["ms"] for r in fft) / max(sum(r["ms"] for r in fft), 1e-9),
-                    "k_inv_l2_share_of_step_under_ncu": sum(r["share"] for r in fft),
+                    "k_inv_l_fp64_pipe_pct": sum(r["fp64_pipe_pct"] * r["ms"] for r in fft) / max(sum(r["ms"] for r in fft), 1e-9),
+                    "k_inv_l_share_of_step_under_ncu": sum(r["share"] for r in fft),
                     "note": "the ring FFT inside K3 is FP64-pipe bound (Bluestein), not HBM bound; measured FP64 peak "
                             "36.7 TFLOP/s DFMA = DMMA (profiles/fp64_peak_b200.json)"}
+    # FP64-pipe roofline of the ring FFTs (they are bound by FP64 issue, not by HBM): FP64 instructions the Bluestein
+    # convolutions execute (16 complex values per thread, ~1256 instructions per thread and sequence for the classes with two
+    # strided radix-16 passes; counted from SASS, ncu inst_executed_pipe_fp64 agrees) against the measured peak
+    # of the pipe (profiles/fp64_peak_b200.json: 36.7 TFLOP/s DFMA = 1.835e13 FP64 instructions/s)
+    def fft_fp64(ms, rows_per_ring_zb):
+        if not ms or tcbl:
+            return None
+        ri = np.arange(1, 3 * tcells + 1) + (tsil - 1) * 3
+        m = ri + 1
+        L = np.array([1 << int(np.ceil(np.log2(max(2 * mm - 1, 4)))) for mm in m])
+        big = m > 64                                          # register-resident kernels (L >= 256); the rest is < 1 % of the work
+        thread_seqs = float(((L / 16.0) * big).sum()) * 43 * rows_per_ring_zb * 2
+        instr = thread_seqs * 1256.0
+        peak_i = 36.7e12 / 2.0
+        return {"bound": "fp64", "fp64_instructions": instr, "achieved_instr_per_s": instr / (ms / 1e3), "peak_instr_per_s": peak_i,
+                "frac": instr / (ms / 1e3) / peak_i, "peak_source": "profiles/fp64_peak_b200.json (measured DFMA peak of this pool)"}
+    fp64_roof = {"inv_l": fft_fp64(kern_ms.get("inv_l"), 7 if not (args.k3_slots == "all") else 15),
+                 "fwd_l": fft_fp64(kern_ms.get("fwd_l"), 3),
+                 "note": "the ring FFTs (Bluestein, exact for every ring length) are FP64-issue bound and move ~1.5 TB/s: their HBM "
+                         "fraction is low by construction; this is their own roofline"}
     roof = {"bound": "hbm", "kernel": top, "achieved": detail[top]["achieved_GBps"], "peak": peak, "unit": "GB/s",
             "frac": detail[top]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": detail[top]["algorithmic_GB"] * 1e9,
-            "share_of_step": detail[top]["ms_per_step"] / ms_step, "ncu": ncu_note}
+            "share_of_step": detail[top]["ms_per_step"] / ms_step, "ncu": ncu_note, "ring_fft_fp64": fp64_roof}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world, cells_tile, args.equation_set, NVARS), "clocks": clocks, "e2e": e2e,
