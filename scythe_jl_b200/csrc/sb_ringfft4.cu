@@ -623,6 +623,15 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
       pair_sync4<T>(pair);
       if (active) {
         double* o = dst + (long long)(wk.row0 + row) * g.W;
+        double2 Ag[C::PQ_TMEM ? 1 : 4][4];          // L = 4096: A0..A3 come from global memory, all sixteen loads up front
+        if (!C::PQ_TMEM) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k0 = half * T + tl + 2 * T * i, k = k0 < m ? k0 : m - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Ag[C::PQ_TMEM ? 0 : i][q] = AF[(size_t)q * m + k];
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int k = half * T + tl + 2 * T * i;
@@ -634,7 +643,7 @@ __global__ void __launch_bounds__(512, 1) k_fwd_l4(DevGrid g, const LWork* __res
             A0 = tm_c(r, 0); A1 = tm_c(r, 1); A2 = tm_c(r, 2); A3 = tm_c(r, 3);
           }
           if (k < m) {
-            if (!C::PQ_TMEM) { A0 = AF[k]; A1 = AF[m + k]; A2 = AF[2 * m + k]; A3 = AF[3 * m + k]; }
+            if (!C::PQ_TMEM) { A0 = Ag[C::PQ_TMEM ? 0 : i][0]; A1 = Ag[C::PQ_TMEM ? 0 : i][1]; A2 = Ag[C::PQ_TMEM ? 0 : i][2]; A3 = Ag[C::PQ_TMEM ? 0 : i][3]; }
             const int km = k ? m - k : 0;
             const double2 b0 = buf0[k], b0m = buf0[km], b1 = buf1[k], b1m = buf1[km];
             double2 X = cm(b0, A0) + cm(make_double2(b0m.x, -b0m.y), A1);
@@ -747,8 +756,11 @@ __device__ __forceinline__ double2 twid5(const double2 wb, const double2* __rest
 }
 
 // x thirds are in the group's buffers -> s_r -> convolution -> c_r' back in the buffers
+struct GB3 {                     // the three exchange buffers of a group and the calling team's own one
+  double2 *b0, *b1, *b2, *mine;
+};
 template <int LOG2L2>
-__device__ __forceinline__ void conv5(double2* const (&gb)[3], uint32_t tb, const double2* __restrict__ ctab, int r, int grp, int team, int tl) {
+__device__ __forceinline__ void conv5(const GB3& gb, uint32_t tb, const double2* __restrict__ ctab, int r, int grp, int team, int tl) {
   typedef R5Cfg<LOG2L2> C;
   constexpr int L2 = C::L2, T = C::T;
   double2 v[16];
@@ -762,9 +774,9 @@ __device__ __forceinline__ void conv5(double2* const (&gb)[3], uint32_t tb, cons
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) {
     const int j = n1 * T + tl;
-    double2 x0 = (n1 < 8) ? gb[0][j] : gb[1][j - L2 / 2];
+    double2 x0 = (n1 < 8) ? gb.b0[j] : gb.b1[j - L2 / 2];
     if (n1 < 8) {
-      const double2 x1 = gb[2][j];
+      const double2 x1 = gb.b2[j];
       if (r == 0) x0 = x0 + x1;
       else if (r == 1) x0 = x0 + make_double2(W3R5 * x1.x - W3I5 * x1.y, W3R5 * x1.y + W3I5 * x1.x);
       else x0 = x0 + make_double2(W3R5 * x1.x + W3I5 * x1.y, W3R5 * x1.y - W3I5 * x1.x);       // w3^2 = conj(w3)
@@ -772,19 +784,19 @@ __device__ __forceinline__ void conv5(double2* const (&gb)[3], uint32_t tb, cons
     v[n1] = r ? cm(x0, twid5(wb, ctab, r, n1)) : x0;
   }
   group_sync5<T>(grp);              // every team has gathered its s_r: the buffers may be overwritten
-  conv4<LOG2L2, void (*)(), false>(v, gb[r], tb, tl, team, true, +[]() {}, C::C_FH3 + 64 * r);
+  conv4<LOG2L2, void (*)(), false>(v, gb.mine, tb, tl, team, true, +[]() {}, C::C_FH3 + 64 * r);
   team_sync4<T>(team);             // the team's last-pass loads are done
 #pragma unroll
   for (int n1 = 0; n1 < 16; ++n1) {
     const double2 c = r ? cmc(v[n1], twid5(wb, ctab, r, n1)) : v[n1];
-    gb[r][n1 * T + tl] = c;
+    gb.mine[n1 * T + tl] = c;
   }
   group_sync5<T>(grp);              // c_0, c_1', c_2' are in the three buffers
 }
 
 // this team's eight outputs: r = 0: a in [0, L2/2), r = 1: [L2/2, L2), r = 2: [L2, 3 L2/2)
-__device__ __forceinline__ double2 combine5(double2* const (&gb)[3], int r, int i) {
-  const double2 b0 = gb[0][i], b1 = gb[1][i], b2 = gb[2][i];
+__device__ __forceinline__ double2 combine5(const GB3& gb, int r, int i) {
+  const double2 b0 = gb.b0[i], b1 = gb.b1[i], b2 = gb.b2[i];
   if (r < 2) return b0 + b1 + b2;
   return b0 + make_double2(W3R5 * b1.x + W3I5 * b1.y, W3R5 * b1.y - W3I5 * b1.x) +
          make_double2(W3R5 * b2.x - W3I5 * b2.y, W3R5 * b2.y + W3I5 * b2.x);
@@ -804,7 +816,9 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, cons
   __shared__ int s_chunk;
   const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
   const int grp = team / 3, r = team - 3 * grp;
-  double2* const gb[3] = {sm + (size_t)(3 * grp) * C::B::LP, sm + (size_t)(3 * grp + 1) * C::B::LP, sm + (size_t)(3 * grp + 2) * C::B::LP};
+  GB3 gb;
+  gb.b0 = sm + (size_t)(3 * grp) * C::B::LP; gb.b1 = gb.b0 + C::B::LP; gb.b2 = gb.b1 + C::B::LP;
+  gb.mine = gb.b0 + (size_t)r * C::B::LP;
   double2* const ctab = sm + (size_t)C::NTEAMS * C::B::LP;                 // C1[16] C2[16]
   double* const stg_all = reinterpret_cast<double*>(ctab + 32);
   double* const stg = stg_all + (size_t)grp * C::STGI;
@@ -916,7 +930,7 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, cons
               Y = make_double2(sq * cq.x, sq * cq.y);
             }
             const double2 u = cm(X, Pk[j]) + cm(Y, Qk[j]);
-            gb[r][i] = k0 < m ? u : make_double2(0.0, 0.0);
+            gb.mine[i] = k0 < m ? u : make_double2(0.0, 0.0);
           }
         }
       }
@@ -973,7 +987,9 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_fwd_l5(DevGrid g, cons
   __shared__ int s_chunk;
   const int tid = threadIdx.x, team = tid / T, tl = tid - team * T;
   const int grp = team / 3, r = team - 3 * grp;
-  double2* const gb[3] = {sm + (size_t)(3 * grp) * C::B::LP, sm + (size_t)(3 * grp + 1) * C::B::LP, sm + (size_t)(3 * grp + 2) * C::B::LP};
+  GB3 gb;
+  gb.b0 = sm + (size_t)(3 * grp) * C::B::LP; gb.b1 = gb.b0 + C::B::LP; gb.b2 = gb.b1 + C::B::LP;
+  gb.mine = gb.b0 + (size_t)r * C::B::LP;
   double2* const ctab = sm + (size_t)C::NTEAMS * C::B::LP;
   double* const stg_all = reinterpret_cast<double*>(ctab + 32);
   const double* const stg = stg_all + (size_t)grp * C::STGF;
@@ -1057,7 +1073,7 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_fwd_l5(DevGrid g, cons
             if (mp && a0 < m) *reinterpret_cast<double2*>(mp + 4 * a) = x[n1];
             const double2 y = cm(x[n1], n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3));
             // team r holds x[r L2/2 + i] at gb[r][i]: thirds of L2/2 entries each... (layout of k_fwd_l3: third r at gb[r][0 .. L2/2))
-            gb[r][i] = a0 < m ? y : make_double2(0.0, 0.0);
+            gb.mine[i] = a0 < m ? y : make_double2(0.0, 0.0);
           }
         }
         group_sync5<T>(grp);          // x is complete
