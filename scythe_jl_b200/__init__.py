@@ -8,3 +8,5 @@ from .api import (Chebyshev, Chebyshev1D, ChebyshevParameters, CubicBSpline, Dom
                   ReferenceState, ScytheError, UnsupportedError, allocateSplineBuffer, calcHaloMap, calcPatchMap, calcTileSizes, checkCFL, createGrid, dct_1st_derivative, dct_2nd_derivative, dct_matrix,
                   getGridpoints, gridTransform, integrate_model, num_columns, read_physical_grid,
                   spectralTransform, splineTransform, tileTransform, tile_grid_params, write_grid)
+from .modelfile import ModelFileError, load_model_file, parse_model_text  # noqa: F401,E402
+from .ncio import read_physical_grid_netcdf, write_grid_netcdf  # noqa: F401,E402

@@ -934,31 +934,69 @@ def write_grid(grid: Grid, output_dir: str, tag: str, physical: np.ndarray | Non
                header=",".join(coord[:pts.shape[1]] + names), comments="", fmt="%.17g")
 
 
+def _write_output(grid: Grid, model: ModelParameters, t: float, physical: np.ndarray):
+    """write_output (src/io.jl:3-13): ``physical_out_<t>.csv`` with ``<t> = string(round(t; digits=2))``; with
+    ``options[:output_format]`` = "netcdf" / "both" the record is (also) appended to ``<output_dir>/scythe_out.nc``."""
+    fmt = str(model.options.get("output_format", model.options.get(":output_format", "csv"))).lower()
+    if fmt not in ("csv", "netcdf", "both"):
+        raise ScytheError(_lib.SB_EINVAL, f"unknown output_format {fmt!r} (csv, netcdf, both)")
+    if fmt in ("csv", "both"):
+        write_grid(grid, model.output_dir, str(round(t, 2)), physical)
+    if fmt in ("netcdf", "both"):
+        from .ncio import write_grid_netcdf
+        write_grid_netcdf(grid, os.path.join(model.output_dir, "scythe_out.nc"), t, physical,
+                          attrs={"equation_set": model.equation_set, "ts": float(model.ts)})
+
+
 def integrate_model(model: ModelParameters, num_tiles: int = 1, ic: np.ndarray | None = None,
-                    ref_state: ReferenceState | None = None, write: bool = False, device: int = 0, lib=None):
-    """src/Scythe.jl:37-62 + model_loop (src/semiimplicit.jl:258-299).  Returns the final patch.physical."""
+                    ref_state: ReferenceState | None = None, write: bool = False, device: int = 0, lib=None,
+                    distributed: bool = False, checkpoint: str | None = None, checkpoint_interval: float = 0.0,
+                    restart: str | None = None):
+    """src/Scythe.jl:37-62 + model_loop (src/semiimplicit.jl:258-299).  Returns the final patch.physical.
+
+    ``distributed=True`` (under ``torch.distributed``): one tile per rank (the reference's one tile per worker), every rank
+    runs this function, rank 0 writes.  ``checkpoint`` / ``checkpoint_interval`` / ``restart``: exact restart files with the
+    AB3 history (`Model.checkpoint`), which the reference's CSV restart loses."""
     if num_tiles < 1:
         raise ScytheError(_lib.SB_EINVAL, "Need to add at least 1 worker process")
-    m = Model(model, num_tiles=num_tiles, device=device, ref_state=ref_state, lib=lib)
+    m = Model(model, num_tiles=num_tiles, device=device, ref_state=ref_state, lib=lib, distributed=distributed)
+    writer = write and m.rank == 0
     if ic is None:
-        read_physical_grid(model.initial_conditions, m.patch)
+        if str(model.initial_conditions).endswith(".nc"):
+            from .ncio import read_physical_grid_netcdf
+            read_physical_grid_netcdf(model.initial_conditions, m.patch)
+        else:
+            read_physical_grid(model.initial_conditions, m.patch)
         ic = m.patch.physical[:, :, 0]
     m.initialize(ic)
     num_ts = int(round(model.integration_time / model.ts))
     output_int = max(int(round(model.output_interval / model.ts)), 1)
-    if write:
-        write_grid(m.patch, model.output_dir, "0.0", m.output())
+    ckpt_int = max(int(round(checkpoint_interval / model.ts)), 1) if (checkpoint and checkpoint_interval > 0.0) else 0
     t = 0
+    if restart:
+        m.restore(restart)
+        t = m.t
+    elif write:
+        out0 = m.output()
+        if writer:
+            _write_output(m.patch, model, 0.0, out0)
     while t < num_ts:
         n = min(output_int - (t % output_int), num_ts - t)
+        if ckpt_int:
+            n = min(n, ckpt_int - (t % ckpt_int))
         m.run(n)
         t += n
         if t % output_int == 0:
             out = m.output(to_host=write)
-            if write:
-                write_grid(m.patch, model.output_dir, str(round(t * model.ts, 2)), out)
+            if writer:
+                _write_output(m.patch, model, t * model.ts, out)
+        if ckpt_int and t % ckpt_int == 0:
+            m.checkpoint(checkpoint)
     out = m.output()
-    if write:
-        write_grid(m.patch, model.output_dir, str(round(model.integration_time, 2)), out)
+    if writer and num_ts % output_int != 0:
+        # finalize_model (src/semiimplicit.jl:351-355) writes the final time again; only needed when the loop has not
+        _write_output(m.patch, model, model.integration_time, out)
+    if checkpoint and not ckpt_int:
+        m.checkpoint(checkpoint)
     m.close()
     return out

@@ -427,3 +427,11 @@ def test_overlapped_step_is_bit_identical(ntiles, gpu_lib, monkeypatch):
     monkeypatch.setenv("SB_OVERLAP_BATCHES", "5")
     c1 = dict(case, tiles=(ntiles,))
     assert check_model(c1, gpu_lib) <= STATE_TOL
+
+
+def test_launcher_on_device(gpu_lib, tmp_path, monkeypatch):
+    """python -m scythe_jl_b200.run (the run_Scythe.jl replacement) on the device: reference-style model file in, CSV + NetCDF
+    out, checkpoint + restart ending on the same bytes (tests/test_driver_io.py holds the checks)."""
+    from test_driver_io import check_launcher, check_netcdf_round_trip
+    check_netcdf_round_trip(gpu_lib, tmp_path)
+    check_launcher(gpu_lib, tmp_path, monkeypatch, nsteps=40)
