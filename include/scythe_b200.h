@@ -143,6 +143,7 @@ typedef struct sb_model_params {
   const double* ref_xibar;
   const double* ref_mubar;
   double Pxi_bar;
+  const double* ref_mu_lbar;      /* liquid-water reference profile of BF02_test (src/testModels.jl:291-293); NULL = zeros */
 } sb_model_params;
 
 /* initialize_model(model, workerids) (src/semiimplicit.jl:126-193) for the tiles this process owns:

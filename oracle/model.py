@@ -12,6 +12,8 @@ citations (paths relative to /root/reference):
 * equation sets                               -- src/testModels.jl:1-215, src/shallowWaterModels.jl:1-298,346-511
 * thermodynamic closure for Euler_test        -- src/thermodynamics.jl:2-17,31-32,67-80,184-269
 * reference state                             -- src/reference_state.jl:4-10,138-199
+* moist test sets BF02_test / rainfall_test   -- src/testModels.jl:217-385, 387-586
+* bulk microphysics + condensation_adjustment -- src/microphysics.jl:81-264, src/thermodynamics.jl:96-167
 
 The Distributed/SharedArray/RemoteChannel plumbing is replaced by an in-process loop over
 tiles that performs the same assignments in the same order (own block assigned, halo added).
@@ -119,6 +121,165 @@ def pressure_gradient(Tk, rho_d, q_v, s_x, xi_x, qv_x):
     return (P_s(Tk, rho_d, q_v) * s_x) + (P_xi(Tk, rho_d, q_v) * xi_x) + (P_qv(Tk, rho_d, q_v) * qv_x)
 
 
+# ---- moist thermodynamics / bulk microphysics (src/thermodynamics.jl:96-167, src/microphysics.jl:81-264)
+Eps = Rd / Rv
+Cpd = Cvd + Rd
+
+
+def entropy(Tk, rho_d, q_v):  # src/thermodynamics.jl:44-54 (q_v > 0)
+    qfactor = q_v * (Rv * np.log(q_v * rho_d / rho_v0) - (L_v(T_0) / T_0))
+    return ((Cvd + (q_v * Cvv)) * np.log(Tk / T_0)) - (Rd * np.log(rho_d / rho_d0)) - qfactor
+
+
+def bhyp(q_v):  # src/thermodynamics.jl:196-200
+    return 0.5 * ((q_v + q0) - (q0 * q0 / (q_v + q0)))
+
+
+def vapor_pressure(p, q_v):  # src/thermodynamics.jl:96-101
+    return (p * q_v) / (Eps + q_v)
+
+
+def _buck(Tk, phPa):  # shared pieces of src/thermodynamics.jl:108-150
+    Tc = Tk - 273.15
+    fw4 = 1.0 + 7.2e-4 + (phPa * (3.20e-6 + (5.9e-10 * (Tc * Tc))))
+    ew4 = 6.1121 * np.exp((18.729 - (Tc / 227.3)) * Tc / (Tc + 257.87))
+    return Tc, fw4, ew4
+
+
+def sat_pressure_liquid_buck(Tk, phPa):  # src/thermodynamics.jl:108-125
+    _, fw4, ew4 = _buck(Tk, phPa)
+    return fw4 * ew4
+
+
+def sat_pressure_liquid_buck_dT(Tk, phPa):  # src/thermodynamics.jl:127-150
+    Tc, fw4, ew4 = _buck(Tk, phPa)
+    d_fw4 = 2.0 * phPa * 5.9e-10 * Tc
+    b, c, d = 18.729, 257.87, 227.3
+    T1 = (d * b - (2.0 * Tc)) * (d * (Tc + c)) - d * ((d * b * Tc) - (Tc * Tc))
+    T2 = (d * (Tc + c)) * (d * (Tc + c))
+    d_ew4 = ew4 * T1 / T2
+    return ew4 * d_fw4 + fw4 * d_ew4
+
+
+def q_sat_liquid(Tk, phPa):  # src/thermodynamics.jl:171-178
+    ew = sat_pressure_liquid_buck(Tk, phPa)
+    return Eps * ew / (phPa - ew)
+
+
+def Q_s_factor(Tk, p, q_v, q_l):  # src/microphysics.jl:108-114
+    e_s = sat_pressure_liquid_buck(Tk, p)
+    dqsdT = sat_pressure_liquid_buck_dT(Tk, p) * Eps * p / ((p - e_s) * (p - e_s))
+    return L_v(Tk) * dqsdT / (Cpd + (q_v * Cpv) + (q_l * Cl))
+
+
+def dqsdp(Tk, p, rho_d, q_v, q_l):  # src/microphysics.jl:116-123
+    q_sat = q_sat_liquid(Tk, p)
+    e_s = sat_pressure_liquid_buck(Tk, p)
+    dqsdT = sat_pressure_liquid_buck_dT(Tk, p) * Eps * p / ((p - e_s) * (p - e_s))
+    return q_sat / (100.0 * (p - e_s)) - (dqsdT / (rho_d * (Cpd + (q_v * Cpv) + (q_l * Cl))))
+
+
+def vapor_diffusity(Tk, p):  # src/microphysics.jl:133-139
+    return 0.211 * (Tk / 273.15) ** 1.94 * (1013.25 / p)
+
+
+def invtau_condensation(Tk, p, N_c, r_c):  # src/microphysics.jl:125-131
+    return 4 * math.pi * vapor_diffusity(Tk, p) * N_c * (r_c * 1.0e-4)
+
+
+def q_condensation(qss, Tk, p, q_v, q_l, N_c, r_c):  # src/microphysics.jl:84-93 (scalar min / max)
+    q_cond = qss / (1.0 + Q_s_factor(Tk, p, q_v, q_l))
+    q_cond = np.minimum(q_v, q_cond)
+    q_cond = np.maximum(-q_l, q_cond)
+    return q_cond * invtau_condensation(Tk, p, N_c, r_c)
+
+
+def s_condensation(q_cond, Tk, rho_d, q_v, q_l, p):  # src/microphysics.jl:96-105
+    Cm = (q_l * Cl) / (Cvd + (q_v * Cvv) + (q_l * Cl))
+    e = vapor_pressure(p, q_v)
+    sat_e = sat_pressure_liquid_buck(Tk, p)
+    return q_cond * (((-L_v(Tk) * Cm) / Tk) - (Cl * np.log(Tk / T_0)) + (Rv * np.log(e / sat_e)))
+
+
+def autoconversion(q_c, rho_d):  # src/microphysics.jl:197-205
+    return np.maximum(0.001 * (q_c - 0.001), 0.0)
+
+
+def f_ice(Tk):  # src/microphysics.jl:217-225
+    return np.where(Tk < 273.15, 0.2 + 0.8 / np.cosh((273.15 - Tk) / 5.0), 1.0)
+
+
+def collection(q_c, q_r, rho_d, Tk):  # src/microphysics.jl:207-215
+    return np.maximum(2.20 * q_c * q_r ** 0.875 * f_ice(Tk), 0.0)
+
+
+def f_ventilation(q_r, rho_d, Tk):  # src/microphysics.jl:241-250
+    rho_r = q_r * rho_d
+    return np.maximum(1.6 + 30.39 * rho_r ** 0.2046 * f_ice(Tk) ** 1.5, 0.0)
+
+
+def rain_evaporation(q_r, rho_d, Tk, p):  # src/microphysics.jl:227-239
+    e_s = sat_pressure_liquid_buck(Tk, p)
+    rho_vs = e_s / (Rv * Tk)
+    rho_r = q_r * rho_d
+    q_evap = (f_ventilation(q_r, rho_d, Tk) * rho_r ** 0.525) / (1.0e4 * ((2.03 * rho_vs) + (3.337 / Tk)))
+    return np.maximum(q_evap, 0.0)
+
+
+def sedimentation(q_r, rho_d, Tk):  # src/microphysics.jl:252-264 -- the clamp `Vt < 0 -> 0` leaves Vt = 0 (or -0.0) always
+    rho_r = q_r * rho_d
+    Vt = -14.164 * rho_r ** 0.1364 * (rho_d0 / rho_d) ** 0.5 * f_ice(Tk)
+    return np.where(Vt < 0.0, 0.0, Vt)
+
+
+def _isless(a, b):
+    """Julia isless for Float64 (NaN is larger than everything, -0.0 < 0.0)."""
+    return np.where(np.isnan(a), False, np.where(np.isnan(b), True,
+                    (a < b) | ((a == b) & np.signbit(a) & ~np.signbit(b))))
+
+
+def _lex_less(A, B):
+    """Julia `isless(A::Vector, B::Vector)` per column: A, B are [ncols, nz]; lexicographic, first unequal element decides."""
+    neq = ~(((A == B) & (np.signbit(A) == np.signbit(B))) | (np.isnan(A) & np.isnan(B)))       # !isequal
+    first = np.argmax(neq, axis=1)
+    rows = np.arange(A.shape[0])
+    return neq.any(axis=1) & _isless(A[rows, first], B[rows, first])
+
+
+def condensation_adjustment(mtile, t):
+    """src/microphysics.jl:141-195.  `min(q_v, q_cond)` / `max(-q_c, q_cond)` (:185-187) are applied there to the column
+    VECTORS without a dot: Julia's generic min/max fall back to `isless`, which is lexicographic for vectors, so each
+    call returns one of its two arguments WHOLE, per column.  Restated as written."""
+    v = mtile.model.grid_params.vars
+    try:
+        si, xii, mui, mci, mri, qi = (v[k] - 1 for k in ("s", "xi", "mu", "mu_c", "mu_r", "qss"))
+    except KeyError as e:
+        raise KeyError(f"key {e.args[0]!r} not found") from None
+    nz = mtile.model.grid_params.zDim
+    ncols = mtile.tile.N // nz
+    ref = mtile.ref_state
+    rep = lambda a: np.tile(a, ncols)  # noqa: E731
+    np1 = mtile.var_np1
+    s, xi, mu, mu_c, mu_r, qss = (np1[:, i] for i in (si, xii, mui, mci, mri, qi))
+    mu_total = mu + rep(ref.mubar[:, 0])
+    q_v, rho_d, Tk, p = thermodynamic_tuple(s + rep(ref.sbar[:, 0]), xi + rep(ref.xibar[:, 0]), mu_total)
+    q_c = ahyp(mu_c)
+    q_r = ahyp(mu_r)
+    q_l = q_c + q_r
+    q_sat = q_sat_liquid(Tk, p)
+    Q_s = Q_s_factor(Tk, p, q_v, q_l)
+    tau_r = 0.25
+    q_cond = (q_v - q_sat - qss) / (1.0 + Q_s)
+    col = lambda a: a.reshape(ncols, nz)  # noqa: E731
+    qc2, qv2, nqc2 = col(q_cond), col(q_v), col(-q_c)
+    qc2 = np.where(_lex_less(qc2, qv2)[:, None], qc2, qv2)          # min(q_v, q_cond) = isless(q_cond, q_v) ? q_cond : q_v
+    qc2 = np.where(_lex_less(qc2, nqc2)[:, None], nqc2, qc2)        # max(-q_c, q_cond) = isless(q_cond, -q_c) ? -q_c : q_cond
+    q_cond = qc2.reshape(-1)
+    np1[:, mui] = mu - tau_r * dmudq(mu_total, q_v) * q_cond
+    np1[:, mci] = mu_c + tau_r * dmudq(mu_c, q_c) * q_cond
+    np1[:, si] = s + tau_r * s_condensation(q_cond, Tk, rho_d, q_v, q_l, p)
+
+
 @dataclass
 class ReferenceState:  # src/reference_state.jl:4-10
     sbar: np.ndarray = None
@@ -145,6 +306,66 @@ def exact_reference_state_from_profiles(gp, sbar, xibar, mubar, mu_lbar) -> Refe
     Pxi = P_xi(Tk, rho_d, q_v)
     Pxi_bar = float(np.mean(Pxi / (dry_density(x3[:, 0]) * (1.0 + ahyp(m3[:, 0])))))
     return ReferenceState(s3, x3, m3, l3, Pxi_bar)
+
+
+def interpolate_reference_file(gp, text: str, z: np.ndarray) -> ReferenceState:
+    """src/reference_state.jl:17-136 with the sounding file given as text (first line: surface pressure [hPa], theta [K],
+    q_v [g/kg]; then altitude [m], theta, q_v): interpolation to the model levels, hydrostatic integration, re-integration
+    through the Chebyshev column, entropy variables and their vertical derivatives."""
+    lines = text.split("\n")
+    first = lines[0].split()
+    sfc_pressure = float(first[0])
+    alt, theta_in, q_in = [0.0], [float(first[1])], [float(first[2])]
+    for ln in lines[1:]:
+        if not ln.strip():
+            break
+        a, th, q = ln.split()[:3]
+        alt.append(float(a)); theta_in.append(float(th)); q_in.append(float(q))
+    n = len(z)
+    theta, q_v = np.zeros(n), np.zeros(n)
+    theta[0], q_v[0] = theta_in[0], q_in[0]
+    for i in range(1, n):
+        found = False
+        for j in range(1, len(alt)):
+            if alt[j - 1] < z[i] and alt[j] > z[i]:
+                theta[i] = theta_in[j - 1] + (z[i] - alt[j - 1]) * (theta_in[j] - theta_in[j - 1]) / (alt[j] - alt[j - 1])
+                q_v[i] = q_in[j - 1] + (z[i] - alt[j - 1]) * (q_in[j] - q_in[j - 1]) / (alt[j] - alt[j - 1])
+                found = True
+            elif alt[j] == z[i]:
+                theta[i], q_v[i] = theta_in[j], q_in[j]
+                found = True
+        if not found:
+            raise ValueError(f"DomainError({i + 1}): Can't find an interpolating level for reference state")
+    q_v = q_v * 1.0e-3
+    Tk, p, rho_d, rho_t = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    p[0] = sfc_pressure
+    Tk[0] = theta[0] / (p_0 / p[0]) ** (Rd / Cpd)
+    rho_d[0] = 100.0 * (p[0] - vapor_pressure(p[0], q_v[0])) / (Tk[0] * Rd)
+    rho_t[0] = rho_d[0] * (1.0 + q_v[0])
+    dlnpdz = -gravity * rho_t[0] / (p[0] * 100.0)
+    for i in range(1, n):
+        p[i] = math.exp(math.log(p[i - 1]) + (dlnpdz * (z[i] - z[i - 1])))
+        Tk[i] = theta[i] / (p_0 / p[i]) ** (Rd / Cpd)
+        rho_d[i] = 100.0 * (p[i] - vapor_pressure(p[i], q_v[i])) / (Tk[i] * Rd)
+        rho_t[i] = rho_d[i] * (1.0 + q_v[i])
+        dlnpdz = -gravity * rho_t[i] / (p[i] * 100.0)
+    col = cheb.Chebyshev1D(cheb.ChebyshevParameters(gp.zmin, gp.zmax, gp.zDim, gp.b_zDim))
+    p_new = col.CIInttransform(col.CAtransform(col.CBtransform(-gravity * rho_t)), sfc_pressure * 100.0) / 100.0
+    Tk = theta / (p_0 / p_new) ** (Rd / Cpd)
+    rho_d = 100.0 * (p_new - vapor_pressure(p_new, q_v)) / (Tk * Rd)
+    s3 = transform_reference_state(gp, entropy_any(Tk, rho_d, q_v))
+    x3 = transform_reference_state(gp, np.log(rho_d / rho_d0))
+    m3 = transform_reference_state(gp, bhyp(q_v))
+    qq, rr, TT, _ = thermodynamic_tuple(s3[:, 0], x3[:, 0], m3[:, 0])
+    Pxi_bar = float(np.mean(P_xi(TT, rr, qq) / (dry_density(x3[:, 0]) * (1.0 + ahyp(m3[:, 0])))))
+    return ReferenceState(s3, x3, m3, np.zeros((n, 3)), Pxi_bar)
+
+
+def entropy_any(Tk, rho_d, q_v):  # src/thermodynamics.jl:44-54 including the q_v == 0 branch
+    q_v = np.asarray(q_v, dtype=np.float64)
+    safe = np.where(q_v != 0.0, q_v * rho_d / rho_v0, 1.0)
+    qfactor = np.where(q_v != 0.0, q_v * (Rv * np.log(safe) - (L_v(T_0) / T_0)), 0.0)
+    return ((Cvd + (q_v * Cvv)) * np.log(Tk / T_0)) - (Rd * np.log(rho_d / rho_d0)) - qfactor
 
 
 # ------------------------------------------------------------------ model tile
@@ -463,10 +684,108 @@ def Euler_test(mtile, t):  # src/testModels.jl:100-215
         semiimplicit_adjustment(mtile, t)
 
 
+def _moist_test(mtile, t, rain: bool):
+    """BF02_test (src/testModels.jl:217-385) and rainfall_test (:387-586): shared structure, restated term by term."""
+    K = mtile.model.physical_params["K"]
+    grid = mtile.tile
+    nz = mtile.model.grid_params.zDim
+    e, imp = mtile.expdot_n, mtile.impdot_n
+    ref = mtile.ref_state
+    ncols = grid.N // nz
+    rep = lambda a: np.tile(a, ncols)  # noqa: E731
+    s, s_x, s_xx, s_z, s_zz = _slots(grid, 0)
+    xi, xi_x, xi_xx, xi_z, xi_zz = _slots(grid, 1)
+    mu, mu_x, mu_xx, mu_z, mu_zz = _slots(grid, 2)
+    u, u_x, u_xx, u_z, u_zz = _slots(grid, 3)
+    w, w_x, w_xx, w_z, w_zz = _slots(grid, 4)
+    sbar, sbar_z = rep(ref.sbar[:, 0]), rep(ref.sbar[:, 1])
+    xibar, xibar_z = rep(ref.xibar[:, 0]), rep(ref.xibar[:, 1])
+    mubar, mubar_z = rep(ref.mubar[:, 0]), rep(ref.mubar[:, 1])
+    mu_total = mu + mubar
+    q_v, rho_d, Tk, p = thermodynamic_tuple(s + sbar, xi + xibar, mu_total)
+    if rain:
+        mu_c, mu_c_x, mu_c_xx, mu_c_z, mu_c_zz = _slots(grid, 5)
+        mu_r, mu_r_x, mu_r_xx, mu_r_z, mu_r_zz = _slots(grid, 6)
+        qss, qss_x, _, qss_z, _ = _slots(grid, 7)
+        q_c = ahyp(mu_c)
+        q_r = ahyp(mu_r)
+        q_l = q_c + q_r
+        q_t = q_v + q_l
+        rho_t = rho_d * (1.0 + q_t)
+        N_c = 100.0
+    else:
+        mu_l, mu_l_x, mu_l_xx, mu_l_z, mu_l_zz = _slots(grid, 5)
+        qss, qss_x, _, qss_z, _ = _slots(grid, 6)
+        mu_lbar, mu_lbar_z = rep(ref.mu_lbar[:, 0]), rep(ref.mu_lbar[:, 1])
+        q_l = ahyp(mu_l + mu_lbar)
+        rho_t = rho_d * (1.0 + q_v + q_l)
+        N_c = 500.0
+    r_c = 10.0
+    mu_factor = dmudq(mu_total, q_v)
+    qvp_x = mu_x / mu_factor
+    qvp_z = mu_z / mu_factor
+    rhobar = dry_density(xibar) * (1.0 + ahyp(mubar))
+    rho_p = rho_t - rhobar
+    Pxi_bar = ref.Pxi_bar
+    dpdx = pressure_gradient(Tk, rho_d, q_v, s_x, xi_x, qvp_x)
+    dpdz = pressure_gradient(Tk, rho_d, q_v, s_z, xi_z, qvp_z)
+    Cm = (q_l * Cl) / (Cvd + (q_v * Cvv) + (q_l * Cl))
+    s_div = Cm * (Rd + q_v * Rv) * (u_x + w_z)
+    q_cond = q_condensation(qss, Tk, p, q_v, q_l, N_c, r_c)
+    s_cond = s_condensation(q_cond, Tk, rho_d, q_v, q_l, p)
+    cloudtau = invtau_condensation(Tk, p, N_c, r_c)
+    lift = (u * dpdx) + (w * (dpdz - rhobar * gravity))
+    if rain:
+        raintau = rain_evaporation(q_r, rho_d, Tk, p)
+        q_evap = -qss * raintau
+        qss_cond = dqsdp(Tk, p, rho_d, q_v, q_l) * lift - qss * (cloudtau + raintau)
+        q_auto = autoconversion(q_c, rho_d)
+        q_coll = collection(q_c, q_r, rho_d, Tk)
+        Vt = sedimentation(q_r, rho_d, Tk)
+        col = grid.columns[mtile.model.grid_params.vars["mu_r"] - 1]     # :525-529
+        flux = (q_r * Vt).reshape(ncols, nz).T
+        Vt_flux = col.CIxtransform(col.CAtransform(col.CBtransform(flux))).T.reshape(-1) / rho_d
+    else:
+        qss_cond = dqsdp(Tk, p, rho_d, q_v, q_l) * lift - qss * cloudtau
+    e[:, 0] = ((-u * s_x) + (-w * (s_z + sbar_z))) + (s_cond + s_div) + (K * (s_xx + s_zz))
+    e[:, 1] = ((-u * xi_x) + (-w * (xi_z + xibar_z))) + (-u_x - w_z)
+    imp[:, 1] = -w_z
+    if rain:
+        e[:, 2] = ((-u * mu_x) + (-w * (mu_z + mubar_z))) + (mu_factor * (q_evap - q_cond)) + (K * (mu_xx + mu_zz))
+    else:
+        e[:, 2] = ((-u * mu_x) + (-w * (mu_z + mubar_z))) + (-q_cond * mu_factor) + (K * (mu_xx + mu_zz))
+    imp[:, 2] = q_v
+    e[:, 3] = ((-u * u_x) + (-w * u_z)) + (-dpdx / rho_t) + (K * (u_xx + u_zz))
+    e[:, 4] = ((-u * w_x) + (-w * w_z)) + (((-gravity * rho_p) - dpdz) / rho_t) + (K * (w_xx + w_zz))
+    imp[:, 4] = -(Pxi_bar * xi_z)
+    if rain:
+        e[:, 5] = ((-u * mu_c_x) + (-w * mu_c_z)) + (dmudq(mu_c, q_c) * (q_cond - q_auto - q_coll)) + (K * (mu_c_xx + mu_c_zz))
+        e[:, 6] = ((-u * mu_r_x) + (-w * mu_r_z)) + (dmudq(mu_r, q_r) * (q_auto + q_coll - q_evap - Vt_flux)) \
+            + (K * (mu_r_xx + mu_r_zz))
+        e[:, 7] = ((-u * qss_x) + (-w * qss_z)) + qss_cond
+        imp[:, 7] = qss
+    else:
+        e[:, 5] = ((-u * mu_l_x) + (-w * (mu_l_z + mu_lbar_z))) + (q_cond * dmudq(mu_l, q_l)) + (K * (mu_l_xx + mu_l_zz))
+        e[:, 6] = ((-u * qss_x) + (-w * qss_z)) + qss_cond
+        imp[:, 6] = qss
+    explicit_timestep(mtile, t)
+    if mtile.model.options.get("semiimplicit", False):
+        semiimplicit_adjustment(mtile, t)
+    condensation_adjustment(mtile, t)
+
+
+def BF02_test(mtile, t):  # src/testModels.jl:217-385
+    _moist_test(mtile, t, rain=False)
+
+
+def rainfall_test(mtile, t):  # src/testModels.jl:387-586
+    _moist_test(mtile, t, rain=True)
+
+
 EQUATION_SETS = {f.__name__: f for f in (
     LinearAdvection1D, LinearAdvectionRZ, LinearAdvectionRL, LinearAdvectionRLZ,
     LinearShallowWater1D, LinearShallowWaterRL, Oneway_ShallowWater_Slab, Twoway_ShallowWater_Slab,
-    Oneway_ShallowWater_HeightResolvedBL, Euler_test)}
+    Oneway_ShallowWater_HeightResolvedBL, Euler_test, BF02_test, rainfall_test)}
 
 
 def physical_model(mtile, t):  # src/semiimplicit.jl:357-363

@@ -10,3 +10,4 @@ from .api import (Chebyshev, Chebyshev1D, ChebyshevParameters, CubicBSpline, Dom
                   spectralTransform, splineTransform, tileTransform, tile_grid_params, write_grid)
 from .modelfile import ModelFileError, load_model_file, parse_model_text  # noqa: F401,E402
 from .ncio import read_physical_grid_netcdf, write_grid_netcdf  # noqa: F401,E402
+from .reference_state import exact_reference_state, interpolate_reference_file, transform_reference_state  # noqa: F401,E402

@@ -38,7 +38,8 @@ class sb_model_params(C.Structure):
                 ("equation_set", C.c_char_p), ("grid", C.POINTER(sb_grid_params)),
                 ("var_names", C.POINTER(C.c_char_p)), ("n_physical_params", C.c_int32),
                 ("param_names", C.POINTER(C.c_char_p)), ("param_values", c_f64p), ("semiimplicit", C.c_int32),
-                ("ref_sbar", c_f64p), ("ref_xibar", c_f64p), ("ref_mubar", c_f64p), ("Pxi_bar", C.c_double)]
+                ("ref_sbar", c_f64p), ("ref_xibar", c_f64p), ("ref_mubar", c_f64p), ("Pxi_bar", C.c_double),
+                ("ref_mu_lbar", c_f64p)]
 
 
 class sb_cheb_params(C.Structure):

@@ -489,10 +489,20 @@ class Model:
                                   output_interval=model.output_interval, equation_set=model.equation_set.encode(),
                                   grid=C.pointer(cgp), var_names=cnames, n_physical_params=len(pk), param_names=pnames,
                                   param_values=pvals, semiimplicit=int(semi))
+        if ref_state is None and model.ref_state_file and gp.geometry in ("RZ", "RLZ"):
+            # createModelTile (src/semiimplicit.jl:62-73): the reference state comes from model.ref_state_file, evaluated on
+            # the model levels (the reference reads them from tilepoints[1:zDim, 2], i.e. the RZ layout: SURVEY App. E.6)
+            from . import reference_state as _rs
+            zcol = Chebyshev1D(ChebyshevParameters(zmin=gp.zmin, zmax=gp.zmax, zDim=gp.zDim, bDim=gp.b_zDim), lib=self.lib)
+            ref_state = _rs.reference_state_for(model, zcol.mishPoints, lib=self.lib)
+        self.ref_state = ref_state
         if ref_state is not None:
             self._ref = [np.asfortranarray(np.asarray(a, dtype=np.float64)) for a in
                          (ref_state.sbar, ref_state.xibar, ref_state.mubar)]
             mp.ref_sbar, mp.ref_xibar, mp.ref_mubar = (_ptr(a) for a in self._ref)
+            if ref_state.mu_lbar is not None:
+                self._ref.append(np.asfortranarray(np.asarray(ref_state.mu_lbar, dtype=np.float64)))
+                mp.ref_mu_lbar = _ptr(self._ref[-1])
             mp.Pxi_bar = float(ref_state.Pxi_bar)
         h = _lib.model_t()
         self.lib.check(self.lib.sb_model_create(C.byref(mp), num_tiles, tile_first, tile_count, device, None, C.byref(h)))

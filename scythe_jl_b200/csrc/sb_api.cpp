@@ -785,7 +785,7 @@ struct sb_model {
   double* d_colfrag = nullptr;
   double* d_refstate = nullptr;
   double* d_sicols = nullptr;
-  std::vector<double> ref_host;  // [3][3][zDim]
+  std::vector<double> ref_host;  // [4][3][zDim]: sbar, xibar, mubar, mu_lbar
   void* comm = nullptr;
   double* d_barrier = nullptr;
   int rank = 0, nranks = 1;
@@ -860,6 +860,8 @@ static void model_check_equation_set(sb_model* M) {
     case EQ_Twoway_ShallowWater_Slab: need(SB_GEOM_RL, 6, {"g", "K", "Cd", "Hfree", "Hb", "f", "S1"}); break;
     case EQ_Oneway_ShallowWater_HeightResolvedBL: need(SB_GEOM_RLZ, 6, {"g", "Kh", "Cd", "Hfree", "f", "Um", "Vm"}); break;
     case EQ_Euler_test: need(SB_GEOM_RZ, 5, {"K"}); break;
+    case EQ_BF02_test: need(SB_GEOM_RZ, 7, {"K"}); break;
+    case EQ_rainfall_test: need(SB_GEOM_RZ, 8, {"K"}); break;
     default: throw Unsupported("equation set is not built as a CUDA kernel (no CPU fallback)");
   }
   EqParams& e = M->ep;
@@ -872,6 +874,21 @@ static void model_check_equation_set(sb_model* M) {
   if (M->eq == EQ_Euler_test) {
     if (M->ref_host.empty()) throw std::invalid_argument("Euler_test needs a reference state");
     if (M->semiimplicit && (e.iw != 4 || e.ixi != 1)) throw std::invalid_argument("Euler_test expects vars s,xi,mu,u,w = 1..5");
+  }
+  if (M->eq == EQ_BF02_test || M->eq == EQ_rainfall_test) {
+    const char* name = M->eq == EQ_BF02_test ? "BF02_test" : "rainfall_test";
+    if (M->ref_host.empty()) throw std::invalid_argument(std::string(name) + " needs a reference state");
+    // condensation_adjustment (src/microphysics.jl:141-165) looks these up by NAME in grid_params.vars and throws a
+    // KeyError when one is missing -- which is what the reference's BF02_test does on its first step with a variable list
+    // that calls column 6 "mu_l".  Same error, raised when the model is created.
+    for (const char* k : {"s", "xi", "mu", "mu_c", "mu_r", "qss"})
+      if (var_index(M, k) < 0) throw std::invalid_argument(std::string("KeyError: key \"") + k + "\" not found (condensation_adjustment, src/microphysics.jl:141-165)");
+    const bool rain = M->eq == EQ_rainfall_test;
+    const char* order[2][8] = {{"s", "xi", "mu", "u", "w", "mu_c", "qss", "mu_r"}, {"s", "xi", "mu", "u", "w", "mu_c", "mu_r", "qss"}};
+    for (int v = 0; v < 8; ++v)
+      if (var_index(M, order[rain][v]) != v)
+        throw std::invalid_argument(std::string(name) + (rain ? " expects vars s,xi,mu,u,w,mu_c,mu_r,qss = 1..8"
+                                                              : " expects vars s,xi,mu,u,w,mu_c,qss,mu_r = 1..8 (column 6 is the equation set's mu_l)"));
   }
 }
 
@@ -915,12 +932,18 @@ static void build_column_ops(sb_model* M) {
       M->d_colfrag = dev_upload(frag); M->owned.push_back(M->d_colfrag);
     }
   }
-  if (M->eq == EQ_Euler_test) {
+  if (M->eq == EQ_Euler_test || M->eq == EQ_BF02_test || M->eq == EQ_rainfall_test) {
     M->d_refstate = dev_upload(M->ref_host); M->owned.push_back(M->d_refstate);
+    std::vector<double> ops(7 * nn, 0.0);
+    if (M->eq == EQ_rainfall_test) {   // CB -> CA -> CIx of the "mu_r" column (src/testModels.jl:525-529)
+      const int imr = var_index(M, "mu_r");
+      std::vector<double> IGr = cheb_bc_matrix(ct, P->bcb[imr], P->bct[imr]), Dr;
+      composite(ct.T1, IGr, Dr); transpose_into(Dr, ops.data() + 6 * nn);
+    }
     if (M->semiimplicit) {
       const int ixi = M->ep.ixi;
       std::vector<double> IG = cheb_bc_matrix(ct, P->bcb[ixi], P->bct[ixi]);
-      std::vector<double> ops(6 * nn), F, Dz;
+      std::vector<double> F, Dz;
       composite(ct.T0, IG, F); transpose_into(F, ops.data());
       composite(ct.T1, IG, Dz); transpose_into(Dz, ops.data() + nn);
       // Helmholtz (src/semiimplicit.jl:768-781): rows 0,1 = tau^2 Pxi dct[0,:], dct[nz-1,:]; rows 2.. = (tau^2 Pxi dct2 - dct)[1..nz-2]
@@ -945,8 +968,8 @@ static void build_column_ops(sb_model* M) {
         transpose_into(W, ops.data() + (2 + 2 * k) * nn);
         transpose_into(X, ops.data() + (3 + 2 * k) * nn);
       }
-      M->d_sicols = dev_upload(ops); M->owned.push_back(M->d_sicols);
     }
+    if (M->semiimplicit || M->eq == EQ_rainfall_test) { M->d_sicols = dev_upload(ops); M->owned.push_back(M->d_sicols); }
   }
 }
 
@@ -979,10 +1002,11 @@ static sb_model* model_new(const sb_model_params* mp, int ntiles, int tile_first
   const bool has_z = (M->gp.geometry == SB_GEOM_RZ || M->gp.geometry == SB_GEOM_RLZ);
   if (mp->ref_sbar && mp->ref_xibar && mp->ref_mubar && has_z) {
     const size_t n3 = (size_t)3 * M->gp.zDim;
-    M->ref_host.resize(3 * n3);
+    M->ref_host.assign(4 * n3, 0.0);
     std::copy(mp->ref_sbar, mp->ref_sbar + n3, M->ref_host.begin());
     std::copy(mp->ref_xibar, mp->ref_xibar + n3, M->ref_host.begin() + n3);
     std::copy(mp->ref_mubar, mp->ref_mubar + n3, M->ref_host.begin() + 2 * n3);
+    if (mp->ref_mu_lbar) std::copy(mp->ref_mu_lbar, mp->ref_mu_lbar + n3, M->ref_host.begin() + 3 * n3);
   }
   M->ep.Pxi_bar = mp->Pxi_bar;
   model_check_equation_set(M.get());

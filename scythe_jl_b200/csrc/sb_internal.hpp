@@ -248,7 +248,8 @@ void launch_nan_scan(const LaunchCtx& c, const double* phys, long long N, int V,
 enum EquationSet {
   EQ_LinearAdvection1D = 0, EQ_LinearAdvectionRZ, EQ_LinearAdvectionRL, EQ_LinearAdvectionRLZ,
   EQ_LinearShallowWater1D, EQ_LinearShallowWaterRL, EQ_Oneway_ShallowWater_Slab,
-  EQ_Twoway_ShallowWater_Slab, EQ_Oneway_ShallowWater_HeightResolvedBL, EQ_Euler_test, EQ_COUNT
+  EQ_Twoway_ShallowWater_Slab, EQ_Oneway_ShallowWater_HeightResolvedBL, EQ_Euler_test,
+  EQ_BF02_test, EQ_rainfall_test, EQ_COUNT
 };
 int equation_set_from_name(const char* name);
 struct EqParams {
@@ -268,9 +269,10 @@ struct ModelArrays {
   double* imp_nm2;
   const double* colops;   // [4][zDim][zDim]: CB->CA->{CI, CIx, CIInt} of "h", (spare)
   const double* colfrag;  // DMMA B fragments of colops 2 (CIInt) and 1 (CIx): [2][zDim/8][zDim/4][32]; null if zDim % 8
-  const double* refstate; // [3 profiles][3][zDim] sbar, xibar, mubar (value, dz, dzz)
+  const double* refstate; // [4 profiles][3][zDim] sbar, xibar, mubar, mu_lbar (value, dz, dzz)
   const double* helm;     // [2][zDim][zDim] inverse Helmholtz matrices (tau=0.5 ts, 1.25 ts)
-  const double* sicols;   // [2 vars (xi,w)][3][zDim][zDim] composite column operators for semi-implicit
+  const double* sicols;   // [7][zDim][zDim] composite column operators: 0..5 semi-implicit (F, Dz of xi; W, X for tau = 0.5 ts,
+                          // 1.25 ts), 6 = CB->CA->CIx of "mu_r" (rainfall_test's sedimentation flux divergence)
 };
 void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* need /*[V]: slots the kernel reads*/);
 void build_colop_fragments(int nz, const double* Mt /*[k][z]*/, std::vector<double>& out);

@@ -7,6 +7,7 @@
 // writes var_np1 and expdot_n; the history rotation (:689-695) is a pointer rotation on the host.
 #include "sb_internal.hpp"
 #include "sb_eqcore.hpp"
+#include "sb_thermo.hpp"
 
 #include <cmath>
 #include <cstdlib>
@@ -18,7 +19,7 @@ namespace sb {
 static const char* kEqNames[EQ_COUNT] = {
     "LinearAdvection1D", "LinearAdvectionRZ", "LinearAdvectionRL", "LinearAdvectionRLZ",
     "LinearShallowWater1D", "LinearShallowWaterRL", "Oneway_ShallowWater_Slab", "Twoway_ShallowWater_Slab",
-    "Oneway_ShallowWater_HeightResolvedBL", "Euler_test"};
+    "Oneway_ShallowWater_HeightResolvedBL", "Euler_test", "BF02_test", "rainfall_test"};
 
 int equation_set_from_name(const char* name) {
   for (int i = 0; i < EQ_COUNT; ++i)
@@ -59,6 +60,12 @@ void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* n
       break;
     case EQ_Euler_test:                                // RZ: s, mu, u, w all five ; xi: r, z
       set(1, F | R | S3);
+      break;
+    case EQ_BF02_test:                                 // s, mu, u, w, mu_l all five ; xi, qss: r, z ; var 8 (mu_r): value
+      set(1, F | R | S3); set(6, F | R | S3); set(7, F);
+      break;
+    case EQ_rainfall_test:                             // s, mu, u, w, mu_c, mu_r all five ; xi, qss: r, z
+      set(1, F | R | S3); set(7, F | R | S3);
       break;
     default: break;
   }
@@ -353,51 +360,48 @@ void build_colop_fragments(int nz, const double* Mt, std::vector<double>& out) {
         out[((size_t)nt * nkt + kt) * 32 + lane] = Mt[(size_t)(kt * 4 + lane % 4) * nz + nt * 8 + lane / 4];
 }
 
-// ---- thermodynamic closure for Euler_test (src/thermodynamics.jl:2-17,31-32,67-80,184-269) ----
-#define TH_Rd 287.04
-#define TH_Rv 461.50
-#define TH_Cvd 716.96
-#define TH_Cvv 1410.0
-#define TH_Cl 4186.0
-#define TH_g 9.81
-#define TH_Lv0 2.501e6
-#define TH_T0 273.16
-#define TH_p0 1000.0
-#define TH_q0 1.0e-7
-
-struct Thermo { double rho_d0, rho_v0, Lv_T0; };
-static Thermo make_thermo() {
-  Thermo th;
-  th.rho_d0 = 100.0 * TH_p0 / (TH_T0 * TH_Rd);
-  double Tc = TH_T0 - 273.15;
-  double es = 6.112 * std::exp(17.67 * Tc / (Tc + 243.5));
-  th.rho_v0 = 100.0 * es / (TH_T0 * TH_Rv);
-  th.Lv_T0 = TH_Lv0 + (((TH_Cvv + TH_Rv) - TH_Cl) * (TH_T0 - TH_T0));
-  return th;
-}
-__device__ __forceinline__ double th_ahyp(double mu) {
-  return (mu < 0.0) ? 0.0 : sqrt(mu * mu + TH_q0 * TH_q0) + mu - TH_q0;
-}
-__device__ __forceinline__ double th_dmudq(double mu, double q_v) { return ((q_v + TH_q0) - mu) / (q_v + TH_q0); }
-__device__ __forceinline__ double th_P_s(double Tk, double rho_d, double q_v) {
-  return Tk * ((rho_d * TH_Rd) + (q_v * rho_d * TH_Rv)) / (TH_Cvd + (q_v * TH_Cvv));
-}
-__device__ __forceinline__ double th_pgrad(const Thermo& th, double Tk, double rho_d, double q_v, double s_x,
-                                           double xi_x, double qv_x) {
-  double Ps = th_P_s(Tk, rho_d, q_v);
-  double Pxi = (TH_Rd + (q_v * rho_d * TH_Rv)) * ((rho_d * Tk) + Ps);
-  double Pqv = 0.0;
-  if (q_v != 0.0) {
-    double rho_v = q_v * rho_d;
-    double qf = TH_Rv * (1 + log(rho_v / th.rho_v0)) - (TH_Cvv * log(Tk / TH_T0)) - th.Lv_T0 / TH_T0;
-    Pqv = (rho_d * TH_Rv * Tk) + qf * Ps;
+// semiimplicit_adjustment (src/semiimplicit.jl:521-597) for one level of a column; every thread of the column calls it
+// (two barriers inside).  xi uses impdot[:, xi] = "wdot", w uses impdot[:, w] = "xidot"; o1 / o4 = offsets of this point
+// in the xi / w columns of the [V][N] state arrays; s0, s1 = the column's two shared vectors.
+// sicols (transposed [k][z'][z]): 0 = F (CB->CA->CI of xi), 1 = Dz (CB->CA->CIx of xi),
+//   2,3 = W,X for tau = 0.5 ts ; 4,5 = W,X for tau = 1.25 ts   (W = dct H^-1 Shift, X = dct1 H^-1 Shift)
+__device__ __forceinline__ void semi_adjust(const ModelArrays& a, const EqParams& p, int t, int nz, int z, long long o1,
+                                            long long o4, double imp1, double imp4, double* s0, double* s1, double& xi_np1,
+                                            double& w_np1) {
+  const double ts = p.ts;
+  double wdot_n = imp1, xidot_n = imp4;
+  double wdot_nm1 = (t >= 2) ? a.imp_nm1[o1] : 0.0, wdot_nm2 = (t >= 3) ? a.imp_nm2[o1] : 0.0;
+  double xidot_nm1 = (t >= 2) ? a.imp_nm1[o4] : 0.0, xidot_nm2 = (t >= 3) ? a.imp_nm2[o4] : 0.0;
+  double tau, w_ns, xi_ns;
+  if (t == 1) {
+    tau = 0.5 * ts;
+    w_ns = w_np1 - (ts * xidot_n) + (ts * 0.5 * xidot_n);
+    xi_ns = xi_np1 - (ts * wdot_n) + (ts * 0.5 * wdot_n);
+  } else if (t == 2) {
+    tau = 1.25 * ts;
+    w_ns = w_np1 - (0.5 * ts) * ((3.0 * xidot_n) - xidot_nm1) - (ts * xidot_n) + (ts * 0.75 * xidot_nm1);
+    xi_ns = xi_np1 - (0.5 * ts) * ((3.0 * wdot_n) - wdot_nm1) - (ts * wdot_n) + (ts * 0.75 * wdot_nm1);
+  } else {
+    tau = 1.25 * ts;
+    w_ns = w_np1 - ((ts / 12.0) * ((23.0 * xidot_n) - (16.0 * xidot_nm1) + (5.0 * xidot_nm2))) - (ts * xidot_n) +
+           (ts * 0.75 * xidot_nm1);
+    xi_ns = xi_np1 - ((ts / 12.0) * ((23.0 * wdot_n) - (16.0 * wdot_nm1) + (5.0 * wdot_nm2))) - (ts * wdot_n) +
+            (ts * 0.75 * wdot_nm1);
   }
-  return (Ps * s_x) + (Pxi * xi_x) + (Pqv * qv_x);
+  const size_t nn = (size_t)nz * nz;
+  s0[z] = xi_ns;
+  __syncthreads();
+  double xi_f = col_matvec(a.sicols, s0, nz, z);
+  double xi_fz = col_matvec(a.sicols + nn, s0, nz, z);
+  s1[z] = tau * p.Pxi_bar * xi_fz - w_ns;   // g before the BC-row shift (folded into W, X)
+  __syncthreads();
+  const double* Wm = a.sicols + ((t == 1) ? 2 : 4) * nn;
+  const double* Xm = Wm + nn;
+  w_np1 = col_matvec(Wm, s1, nz, z);
+  xi_np1 = xi_f - tau * col_matvec(Xm, s1, nz, z);
 }
 
 // Euler_test + semiimplicit_adjustment, src/testModels.jl:100-215, src/semiimplicit.jl:521-597
-// sicols (transposed [k][z'][z]): 0 = F (CB->CA->CI of xi), 1 = Dz (CB->CA->CIx of xi),
-//   2,3 = W,X for tau = 0.5 ts ; 4,5 = W,X for tau = 1.25 ts   (W = dct H^-1 Shift, X = dct1 H^-1 Shift)
 __global__ void k_euler_test(DevGrid g, EqParams p, ModelArrays a, Thermo th, int semi, int t) {
   SB_DYN_SMEM(double, sm);
   const int nz = g.zDim, z = threadIdx.x, cl = threadIdx.y;
@@ -453,40 +457,161 @@ __global__ void k_euler_test(DevGrid g, EqParams p, ModelArrays a, Thermo th, in
     if (live) { a.var_np1[o1] = xi_np1; a.var_np1[o4] = w_np1; }
     return;
   }
-  // ---- semi-implicit adjustment (xi uses impdot[:,xi] = "wdot", w uses impdot[:,w] = "xidot")
-  double wdot_n = imp1, xidot_n = imp4;
-  double wdot_nm1 = (t >= 2) ? a.imp_nm1[o1] : 0.0, wdot_nm2 = (t >= 3) ? a.imp_nm2[o1] : 0.0;
-  double xidot_nm1 = (t >= 2) ? a.imp_nm1[o4] : 0.0, xidot_nm2 = (t >= 3) ? a.imp_nm2[o4] : 0.0;
-  double tau, w_ns, xi_ns;
-  if (t == 1) {
-    tau = 0.5 * ts;
-    w_ns = w_np1 - (ts * xidot_n) + (ts * 0.5 * xidot_n);
-    xi_ns = xi_np1 - (ts * wdot_n) + (ts * 0.5 * wdot_n);
-  } else if (t == 2) {
-    tau = 1.25 * ts;
-    w_ns = w_np1 - (0.5 * ts) * ((3.0 * xidot_n) - xidot_nm1) - (ts * xidot_n) + (ts * 0.75 * xidot_nm1);
-    xi_ns = xi_np1 - (0.5 * ts) * ((3.0 * wdot_n) - wdot_nm1) - (ts * wdot_n) + (ts * 0.75 * wdot_nm1);
-  } else {
-    tau = 1.25 * ts;
-    w_ns = w_np1 - ((ts / 12.0) * ((23.0 * xidot_n) - (16.0 * xidot_nm1) + (5.0 * xidot_nm2))) - (ts * xidot_n) +
-           (ts * 0.75 * xidot_nm1);
-    xi_ns = xi_np1 - ((ts / 12.0) * ((23.0 * wdot_n) - (16.0 * wdot_nm1) + (5.0 * wdot_nm2))) - (ts * wdot_n) +
-            (ts * 0.75 * wdot_nm1);
-  }
-  const size_t nn = (size_t)nz * nz;
-  s0[z] = xi_ns;
-  __syncthreads();
-  double xi_f = col_matvec(a.sicols, s0, nz, z);
-  double xi_fz = col_matvec(a.sicols + nn, s0, nz, z);
-  s1[z] = tau * p.Pxi_bar * xi_fz - w_ns;   // g before the BC-row shift (folded into W, X)
-  __syncthreads();
-  const double* Wm = a.sicols + ((t == 1) ? 2 : 4) * nn;
-  const double* Xm = Wm + nn;
-  double w_new = col_matvec(Wm, s1, nz, z);
-  double xi_new = xi_f - tau * col_matvec(Xm, s1, nz, z);
+  semi_adjust(a, p, t, nz, z, o1, o4, imp1, imp4, s0, s1, xi_np1, w_np1);
   if (live) {
-    a.var_np1[o4] = w_new;
-    a.var_np1[o1] = xi_new;
+    a.var_np1[o4] = w_np1;
+    a.var_np1[o1] = xi_np1;
+  }
+}
+
+// lexicographic isless(A, B) of two column vectors in shared memory (Julia: isless(::AbstractVector, ::AbstractVector) =
+// cmp(A, B) < 0, first !isequal pair decides): what the un-dotted min / max of condensation_adjustment reduce to
+__device__ __forceinline__ bool column_lex_less(const double* A, const double* B, int nz) {
+  for (int k = 0; k < nz; ++k)
+    if (!th_isequal(A[k], B[k])) return th_isless(A[k], B[k]);
+  return false;
+}
+
+// BF02_test (RAIN = false, src/testModels.jl:217-385) and rainfall_test (RAIN = true, :387-586): moist compressible
+// RZ test sets with bulk condensation (+ warm-rain microphysics), then explicit_timestep (src/semiimplicit.jl:672-698),
+// semiimplicit_adjustment (:521-597) and condensation_adjustment (src/microphysics.jl:141-195) on var_np1.
+// Variables by column: s, xi, mu, u, w, then BF02: mu_l (named mu_c), qss, mu_r (no tendency) | rainfall: mu_c, mu_r, qss.
+// Reference quirks kept as written: the un-dotted vector min / max of condensation_adjustment (lexicographic, whole
+// column), sedimentation's clamp that leaves Vt = 0, dmudq(mu_l, q_l) with the perturbation mu_l and the total q_l.
+// impdot[:, mu] = q_v and impdot[:, qss] = qss (:354,:364 / :551,:573) are placeholders nothing reads: not stored.
+template <bool RAIN>
+__global__ void k_moist_test(DevGrid g, EqParams p, ModelArrays a, Thermo th, int semi, int t) {
+  SB_DYN_SMEM(double, sm);
+  const int nz = g.zDim, z = threadIdx.x, cl = threadIdx.y;
+  const long long col = (long long)blockIdx.x * blockDim.y + cl;
+  const bool live = col < g.hpoints;
+  double* s0 = sm + (size_t)cl * 2 * nz;
+  double* s1 = s0 + nz;
+  const long long i = live ? col * nz + z : 0;
+  PointCtx c{g, a, i};
+  const double ts = p.ts, K = p.K;
+  const double* rs = a.refstate;  // [profile][deriv][z]
+  const double sbar = rs[z], sbar_z = rs[nz + z];
+  const double xibar = rs[3 * nz + z], xibar_z = rs[4 * nz + z];
+  const double mubar = rs[6 * nz + z], mubar_z = rs[7 * nz + z];
+  const int IQ = RAIN ? 7 : 6;                       // column of qss
+  double s = c.P(0, 0), s_x = c.P(0, 1), s_xx = c.P(0, 2), s_z = c.P(0, 3), s_zz = c.P(0, 4);
+  double xi = c.P(1, 0), xi_x = c.P(1, 1), xi_z = c.P(1, 3);
+  double mu = c.P(2, 0), mu_x = c.P(2, 1), mu_xx = c.P(2, 2), mu_z = c.P(2, 3), mu_zz = c.P(2, 4);
+  double u = c.P(3, 0), u_x = c.P(3, 1), u_xx = c.P(3, 2), u_z = c.P(3, 3), u_zz = c.P(3, 4);
+  double w = c.P(4, 0), w_x = c.P(4, 1), w_xx = c.P(4, 2), w_z = c.P(4, 3), w_zz = c.P(4, 4);
+  double m5 = c.P(5, 0), m5_x = c.P(5, 1), m5_xx = c.P(5, 2), m5_z = c.P(5, 3), m5_zz = c.P(5, 4);   // mu_l | mu_c
+  double qss = c.P(IQ, 0), qss_x = c.P(IQ, 1), qss_z = c.P(IQ, 3);
+  const double mu_total = mu + mubar;
+  const ThermoPoint tp = th_tuple(th, s + sbar, xi + xibar, mu_total);
+  const double q_v = tp.q_v, rho_d = tp.rho_d, Tk = tp.Tk, pr = tp.p;
+  double q_c = 0.0, q_r = 0.0, q_l, rho_t;
+  double m6 = 0.0, m6_x = 0.0, m6_xx = 0.0, m6_z = 0.0, m6_zz = 0.0;     // rainfall: mu_r
+  if (RAIN) {
+    m6 = c.P(6, 0); m6_x = c.P(6, 1); m6_xx = c.P(6, 2); m6_z = c.P(6, 3); m6_zz = c.P(6, 4);
+    q_c = th_ahyp(m5);
+    q_r = th_ahyp(m6);
+    q_l = q_c + q_r;
+    rho_t = rho_d * (1.0 + (q_v + q_l));
+  } else {
+    q_l = th_ahyp(m5 + rs[9 * nz + z]);
+    rho_t = rho_d * (1.0 + q_v + q_l);
+  }
+  const double mu_factor = th_dmudq(mu_total, q_v);
+  const double qvp_x = mu_x / mu_factor, qvp_z = mu_z / mu_factor;
+  const double rhobar = (th.rho_d0 * exp(xibar)) * (1.0 + th_ahyp(mubar));
+  const double rho_p = rho_t - rhobar;
+  const double dpdx = th_pgrad(th, Tk, rho_d, q_v, s_x, xi_x, qvp_x);
+  const double dpdz = th_pgrad(th, Tk, rho_d, q_v, s_z, xi_z, qvp_z);
+  const double Cm = (q_l * TH_Cl) / (TH_Cvd + (q_v * TH_Cvv) + (q_l * TH_Cl));
+  const double s_div = Cm * (TH_Rd + q_v * TH_Rv) * (u_x + w_z);
+  const double N_c = RAIN ? 100.0 : 500.0, r_c = 10.0;
+  const SatPoint sp = th_sat(Tk, pr);
+  const double cloudtau = th_invtau(Tk, pr, N_c, r_c);
+  double q_cond = qss / (1.0 + th_Q_s(sp, Tk, q_v, q_l));        // q_condensation, src/microphysics.jl:84-93
+  q_cond = fmin(q_v, q_cond);
+  q_cond = fmax(-q_l, q_cond);
+  q_cond = q_cond * cloudtau;
+  const double s_cond = th_s_condensation(sp, q_cond, Tk, q_v, q_l, pr);
+  const double lift = (u * dpdx) + (w * (dpdz - rhobar * TH_g));
+  const double dq = th_dqsdp(sp, pr, rho_d, q_v, q_l);
+  double qss_cond, q_evap = 0.0, q_auto = 0.0, q_coll = 0.0, Vt_flux = 0.0;
+  if (RAIN) {
+    const double rho_r = q_r * rho_d, fice = th_f_ice(Tk);
+    double f_vent = 1.6 + 30.39 * pow(rho_r, 0.2046) * pow(fice, 1.5);
+    if (f_vent < 0.0) f_vent = 0.0;
+    const double rho_vs = sp.e_s / (TH_Rv * Tk);
+    double raintau = (f_vent * pow(rho_r, 0.525)) / (1.0e4 * ((2.03 * rho_vs) + (3.337 / Tk)));
+    if (raintau < 0.0) raintau = 0.0;
+    q_evap = -qss * raintau;
+    qss_cond = dq * lift - qss * (cloudtau + raintau);
+    q_auto = 0.001 * (q_c - 0.001);
+    if (q_auto < 0.0) q_auto = 0.0;
+    q_coll = 2.20 * q_c * pow(q_r, 0.875) * fice;
+    if (q_coll < 0.0) q_coll = 0.0;
+    double Vt = -14.164 * pow(rho_r, 0.1364) * pow(th.rho_d0 / rho_d, 0.5) * fice;
+    if (Vt < 0.0) Vt = 0.0;
+    s0[z] = q_r * Vt;                                             // col.uMish (:526), CB -> CA -> CIx of the mu_r column
+    __syncthreads();
+    Vt_flux = col_matvec(a.sicols + (size_t)6 * nz * nz, s0, nz, z) / rho_d;
+    __syncthreads();
+  } else {
+    qss_cond = dq * lift - qss * cloudtau;
+  }
+  const double e0 = ((-u * s_x) + (-w * (s_z + sbar_z))) + (s_cond + s_div) + (K * (s_xx + s_zz));
+  const double e1 = ((-u * xi_x) + (-w * (xi_z + xibar_z))) + (-u_x - w_z);
+  const double e2 = ((-u * mu_x) + (-w * (mu_z + mubar_z))) + (RAIN ? (mu_factor * (q_evap - q_cond)) : (-q_cond * mu_factor)) +
+                    (K * (mu_xx + mu_zz));
+  const double e3 = ((-u * u_x) + (-w * u_z)) + (-dpdx / rho_t) + (K * (u_xx + u_zz));
+  const double e4 = ((-u * w_x) + (-w * w_z)) + (((-TH_g * rho_p) - dpdz) / rho_t) + (K * (w_xx + w_zz));
+  double e5, e6 = 0.0;
+  if (RAIN) {
+    e5 = ((-u * m5_x) + (-w * m5_z)) + (th_dmudq(m5, q_c) * (q_cond - q_auto - q_coll)) + (K * (m5_xx + m5_zz));
+    e6 = ((-u * m6_x) + (-w * m6_z)) + (th_dmudq(m6, q_r) * (q_auto + q_coll - q_evap - Vt_flux)) + (K * (m6_xx + m6_zz));
+  } else {
+    e5 = ((-u * m5_x) + (-w * (m5_z + rs[10 * nz + z]))) + (q_cond * th_dmudq(m5, q_l)) + (K * (m5_xx + m5_zz));
+  }
+  const double eq = ((-u * qss_x) + (-w * qss_z)) + qss_cond;
+  auto step = [&](int v, double u0, double fn) {                  // explicit_timestep of one variable; var_np1 stays in a register
+    const long long o = (long long)v * g.N + i;
+    const double f1 = (t >= 2) ? a.exp_nm1[o] : 0.0;
+    const double f2 = (t >= 3) ? a.exp_nm2[o] : 0.0;
+    if (live) a.exp_n[o] = fn;
+    return ab_step(t, ts, u0, fn, f1, f2);
+  };
+  double s_np1 = step(0, s, e0), xi_np1 = step(1, xi, e1), mu_np1 = step(2, mu, e2), u_np1 = step(3, u, e3);
+  double w_np1 = step(4, w, e4), m5_np1 = step(5, m5, e5), qss_np1 = step(IQ, qss, eq);
+  double mur_np1 = RAIN ? step(6, m6, e6) : step(7, c.P(7, 0), 0.0);
+  const long long o1 = (long long)1 * g.N + i, o4 = (long long)4 * g.N + i;
+  const double imp1 = -w_z, imp4 = -(p.Pxi_bar * xi_z);
+  if (live && a.imp_n) { a.imp_n[o1] = imp1; a.imp_n[o4] = imp4; }
+  if (semi) semi_adjust(a, p, t, nz, z, o1, o4, imp1, imp4, s0, s1, xi_np1, w_np1);
+  // ---- condensation_adjustment (src/microphysics.jl:141-195) on the advanced state; mu_c = column 5, mu_r = column 6 | 7
+  {
+    const double mu_total2 = mu_np1 + mubar;
+    const ThermoPoint t2 = th_tuple(th, s_np1 + sbar, xi_np1 + xibar, mu_total2);
+    const double qc2 = th_ahyp(m5_np1), qr2 = th_ahyp(mur_np1), ql2 = qc2 + qr2;
+    const SatPoint sp2 = th_sat(t2.Tk, t2.p);
+    const double Qs2 = th_Q_s(sp2, t2.Tk, t2.q_v, ql2);
+    double qcond2 = (t2.q_v - sp2.q_sat - qss_np1) / (1.0 + Qs2);
+    __syncthreads();
+    s0[z] = qcond2; s1[z] = t2.q_v;
+    __syncthreads();
+    if (!column_lex_less(s0, s1, nz)) qcond2 = t2.q_v;            // min(q_v, q_cond) on the column vectors (:185)
+    __syncthreads();
+    s0[z] = qcond2; s1[z] = -qc2;
+    __syncthreads();
+    if (column_lex_less(s0, s1, nz)) qcond2 = -qc2;               // max(-q_c, q_cond) (:187)
+    const double tau_r = 0.25;
+    mu_np1 = mu_np1 - tau_r * th_dmudq(mu_total2, t2.q_v) * qcond2;
+    m5_np1 = m5_np1 + tau_r * th_dmudq(m5_np1, qc2) * qcond2;
+    s_np1 = s_np1 + tau_r * th_s_condensation(sp2, qcond2, t2.Tk, t2.q_v, ql2, t2.p);
+  }
+  if (live) {
+    const long long N = g.N;
+    a.var_np1[i] = s_np1; a.var_np1[N + i] = xi_np1; a.var_np1[2 * N + i] = mu_np1; a.var_np1[3 * N + i] = u_np1;
+    a.var_np1[4 * N + i] = w_np1; a.var_np1[5 * N + i] = m5_np1; a.var_np1[(long long)IQ * N + i] = qss_np1;
+    a.var_np1[(long long)(RAIN ? 6 : 7) * N + i] = mur_np1;
   }
 }
 
@@ -529,6 +654,19 @@ void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqP
       size_t smem = (size_t)cpb * 2 * g.zDim * sizeof(double);
       SB_LAUNCH(k_euler_test, dim3((unsigned)blocks), dim3(g.zDim, cpb), smem, c.stream, g, p, a, make_thermo(),
                 a.imp_n ? 1 : 0, tstep);
+      break;
+    }
+    case EQ_BF02_test:
+    case EQ_rainfall_test: {
+      int cpb = 128 / g.zDim; if (cpb < 1) cpb = 1;
+      long long blocks = (g.hpoints + cpb - 1) / cpb;
+      size_t smem = (size_t)cpb * 2 * g.zDim * sizeof(double);
+      if (eq == EQ_rainfall_test)
+        SB_LAUNCH(k_moist_test<true>, dim3((unsigned)blocks), dim3(g.zDim, cpb), smem, c.stream, g, p, a, make_thermo(),
+                  a.imp_n ? 1 : 0, tstep);
+      else
+        SB_LAUNCH(k_moist_test<false>, dim3((unsigned)blocks), dim3(g.zDim, cpb), smem, c.stream, g, p, a, make_thermo(),
+                  a.imp_n ? 1 : 0, tstep);
       break;
     }
     default: throw std::runtime_error("equation set has no CUDA kernel");

@@ -78,6 +78,7 @@ struct ModelParamsC                   # sb_model_params
     ref_xibar::Ptr{Float64}
     ref_mubar::Ptr{Float64}
     Pxi_bar::Float64
+    ref_mu_lbar::Ptr{Float64}
 end
 
 const GEOM = Dict("R" => 0, "RZ" => 1, "RL" => 2, "RLZ" => 3)
@@ -258,7 +259,8 @@ function GPUModel(model; num_tiles::Integer = 1, tile_first::Integer = 0, tile_c
     sbar = ref_state === nothing ? Float64[] : Array{Float64}(ref_state.sbar)     # [zDim, 3] value, d/dz, d2/dz2
     xibar = ref_state === nothing ? Float64[] : Array{Float64}(ref_state.xibar)
     mubar = ref_state === nothing ? Float64[] : Array{Float64}(ref_state.mubar)
-    GC.@preserve keep names pnames pvals eq sbar xibar mubar begin
+    mu_lbar = ref_state === nothing ? Float64[] : Array{Float64}(ref_state.mu_lbar)   # BF02_test (src/testModels.jl:291-293)
+    GC.@preserve keep names pnames pvals eq sbar xibar mubar mu_lbar begin
         cnames = Cstring[Base.unsafe_convert(Cstring, n) for n in names]
         cpn = isempty(pnames) ? Cstring[Base.unsafe_convert(Cstring, "")] : Cstring[Base.unsafe_convert(Cstring, n) for n in pnames]
         gref = Ref(keep.c)
@@ -267,7 +269,8 @@ function GPUModel(model; num_tiles::Integer = 1, tile_first::Integer = 0, tile_c
                               Base.unsafe_convert(Ptr{GridParamsC}, gref), pointer(cnames), length(pnames), pointer(cpn),
                               isempty(pvals) ? C_NULL : pointer(pvals), semi,
                               isempty(sbar) ? C_NULL : pointer(sbar), isempty(xibar) ? C_NULL : pointer(xibar),
-                              isempty(mubar) ? C_NULL : pointer(mubar), ref_state === nothing ? 0.0 : Float64(ref_state.Pxi_bar))
+                              isempty(mubar) ? C_NULL : pointer(mubar), ref_state === nothing ? 0.0 : Float64(ref_state.Pxi_bar),
+                              length(mu_lbar) == length(sbar) && !isempty(mu_lbar) ? pointer(mu_lbar) : C_NULL)
             check(ccall(sym(:sb_model_create), Cint,
                         (Ref{ModelParamsC}, Int32, Int32, Int32, Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
                         mp, num_tiles, tile_first, tile_count, device, C_NULL, h))

@@ -236,10 +236,55 @@ def model_cases(small=True):
     ic[:, 0] = 2.0 * np.exp(-((x) ** 2 + (z - 3e3) ** 2) / 2e3 ** 2)
     ic[:, 2] = 1e-4 * np.exp(-((x - 2e3) ** 2 + (z - 2e3) ** 2) / 2e3 ** 2)
     ic[:, 3] = 1.0 * np.sin(z / 2e3)
+    # moist test sets (src/testModels.jl:217-586): a hydrostatic moist sounding as the reference state, a warm moist bubble,
+    # cloud and rain blobs, and a supersaturation field whose sign changes along the bottom level.  Of the two whole-column
+    # (lexicographic) selections of condensation_adjustment, max(-q_c, q_cond) goes both ways across the columns;
+    # min(q_v, q_cond) always picks q_cond here (its other outcome sets q_cond = q_v in the whole column, which the
+    # reference's own formulas amplify to overflow within two steps; tests/test_oracle_golden.py covers the selection rule)
+    gpm = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=8, zmin=0, zmax=1e4, zDim=16,
+                           vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5, "mu_c": 6, "mu_r": 7, "qss": 8})
+    refm, icm = moist_case(gpm, rain=True)
+    cases["rainfall_test_explicit"] = dict(gp=gpm, eq="rainfall_test", prm={"K": 50.0}, ts=0.05, n=3, ic=icm, tiles=(1,), ref=refm)
+    cases["rainfall_test_semiimplicit"] = dict(gp=gpm, eq="rainfall_test", prm={"K": 50.0}, ts=0.5, n=3, ic=icm, tiles=(1, 2),
+                                               ref=refm, opts={"semiimplicit": True, "exact_reference_state": True})
+    gpb = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=8, zmin=0, zmax=1e4, zDim=16,
+                           vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5, "mu_c": 6, "qss": 7, "mu_r": 8})
+    refb, icb = moist_case(gpb, rain=False)
+    cases["BF02_test_semiimplicit"] = dict(gp=gpb, eq="BF02_test", prm={"K": 50.0}, ts=0.5, n=3, ic=icb, tiles=(1, 2),
+                                           ref=refb, opts={"semiimplicit": True, "exact_reference_state": True})
     cases["Euler_test_explicit"] = dict(gp=gp, eq="Euler_test", prm={"K": 50.0}, ts=0.05, n=3, ic=ic, tiles=(1,), ref=ref)
     cases["Euler_test_semiimplicit"] = dict(gp=gp, eq="Euler_test", prm={"K": 50.0}, ts=1.0, n=4, ic=ic, tiles=(1, 2),
                                             ref=ref, opts={"semiimplicit": True, "exact_reference_state": True})
     return cases
+
+
+def moist_case(gp, rain: bool):
+    """Reference state + initial condition for BF02_test / rainfall_test on `gp` (8 variables)."""
+    zc = ch.mish_points(ch.ChebyshevParameters(gp.zmin, gp.zmax, gp.zDim, gp.b_zDim))
+    Tk = 300.0 - 6.5e-3 * zc
+    p = 1000.0 * (Tk / 300.0) ** (M.gravity / (M.Rd * 6.5e-3))
+    q_v = 0.95 * float(M.q_sat_liquid(np.float64(300.0), np.float64(1000.0))) * np.exp(-zc / 2500.0)   # 95 % RH at the surface
+    e = M.vapor_pressure(p, q_v)
+    rho_d = 100.0 * (p - e) / (M.Rd * Tk)
+    sbar = M.entropy(Tk, rho_d, q_v)
+    xibar = np.log(rho_d / M.rho_d0)
+    mubar = M.bhyp(q_v)
+    mu_lbar = M.bhyp(1e-4 * np.exp(-((zc - 3e3) / 1e3) ** 2))
+    ref = M.exact_reference_state_from_profiles(gp, sbar, xibar, mubar, mu_lbar)
+    x, z = G.createGrid(gp).getGridpoints().T
+    v = {k: i - 1 for k, i in gp.vars.items()}
+    ic = np.zeros((x.size, 8))
+    ic[:, v["s"]] = 2.0 * np.exp(-((x) ** 2 + (z - 3e3) ** 2) / 2e3 ** 2)
+    # a moist and a dry blob near the surface: max(-q_c, q_cond) of condensation_adjustment picks -q_c in the dry columns
+    ic[:, v["mu"]] = 2e-3 * np.exp(-((x - 4e3) / 3e3) ** 2 - (z / 3e3) ** 2) - 3.5e-3 * np.exp(-((x + 5e3) / 2.5e3) ** 2 - (z / 2e3) ** 2)
+    ic[:, v["u"]] = 2.0 * np.sin(z / 2e3)
+    ic[:, v["w"]] = 0.5 * np.exp(-((x + 1e3) ** 2 + (z - 4e3) ** 2) / 2.5e3 ** 2)
+    # haze everywhere (mu_c, mu_r > 0: where they go negative the reference's dmudq = 1 + |mu| / q0 makes its own tendencies
+    # explosive), q_c above and below the 1 g/kg autoconversion threshold
+    ic[:, v["mu_c"]] = 8e-4 + 1.5e-3 * np.exp(-((x - 1e3) ** 2 + (z - 3.5e3) ** 2) / 3e3 ** 2)
+    ic[:, v["mu_r"]] = 2e-4 + 1.0e-3 * np.exp(-((x + 3e3) ** 2 + (z - 2.5e3) ** 2) / 3e3 ** 2)
+    ic[:, v["qss"]] = 2e-4 * np.sin(x / 2.5e3) * np.exp(-z / 4e3)
+    return ref, ic
 
 
 def benchmarked_shape_cases():
@@ -296,6 +341,18 @@ def benchmarked_shape_cases():
     ic[:, 0] = 2.0 * np.exp(-((x) ** 2 + (z - 3e3) ** 2) / 2e3 ** 2)
     ic[:, 2] = 1e-4 * np.exp(-((x - 2e3) ** 2 + (z - 2e3) ** 2) / 2e3 ** 2)
     ic[:, 3] = 1.0 * np.sin(z / 2e3)
+    # the moist sets at the C3 level count (64 levels: four warps per column in k_moist_test, 64 x 64 column operators)
+    gpm = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=100, zmin=0, zmax=1e4, zDim=64,
+                           vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5, "mu_c": 6, "mu_r": 7, "qss": 8})
+    refm, icm = moist_case(gpm, rain=True)
+    cases["rainfall_test_semiimplicit_100cells_z64"] = dict(gp=gpm, eq="rainfall_test", prm={"K": 50.0}, ts=0.5, n=3, ic=icm,
+                                                            tiles=(1, 2), ref=refm,
+                                                            opts={"semiimplicit": True, "exact_reference_state": True})
+    gpb = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=100, zmin=0, zmax=1e4, zDim=64,
+                           vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5, "mu_c": 6, "qss": 7, "mu_r": 8})
+    refb, icb = moist_case(gpb, rain=False)
+    cases["BF02_test_semiimplicit_100cells_z64"] = dict(gp=gpb, eq="BF02_test", prm={"K": 50.0}, ts=0.5, n=3, ic=icb, tiles=(1, 2),
+                                                        ref=refb, opts={"semiimplicit": True, "exact_reference_state": True})
     cases["Euler_test_semiimplicit_C3_334cells_z64"] = dict(gp=gp, eq="Euler_test", prm={"K": 50.0}, ts=1.0, n=4, ic=ic,
                                                             tiles=(1, 2), ref=ref,
                                                             opts={"semiimplicit": True, "exact_reference_state": True})

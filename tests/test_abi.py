@@ -139,4 +139,4 @@ def test_julia_shim_binds_only_exported_symbols(lib):
         return sum(len(stmt.split(",")) for stmt in body.split(";") if stmt.strip())
     assert julia_fields("GridParamsC") == c_fields("sb_grid_params") == 16
     assert julia_fields("GridInfoC") == c_fields("sb_grid_info") == 13
-    assert julia_fields("ModelParamsC") == c_fields("sb_model_params") == 14
+    assert julia_fields("ModelParamsC") == c_fields("sb_model_params") == 15

@@ -435,3 +435,13 @@ def test_launcher_on_device(gpu_lib, tmp_path, monkeypatch):
     from test_driver_io import check_launcher, check_netcdf_round_trip
     check_netcdf_round_trip(gpu_lib, tmp_path)
     check_launcher(gpu_lib, tmp_path, monkeypatch, nsteps=40)
+
+
+def test_moist_error_behaviour(gpu_lib):
+    from test_kernels_emulated import check_moist_error_behaviour
+    check_moist_error_behaviour(S, gpu_lib)
+
+
+def test_reference_state_files(gpu_lib, tmp_path):
+    from test_kernels_emulated import check_reference_state_files
+    check_reference_state_files(S, gpu_lib, tmp_path)

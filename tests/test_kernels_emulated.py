@@ -203,3 +203,94 @@ def test_overlapped_step_is_bit_identical(emu_lib, monkeypatch):
     from helpers import check_overlapped_step
     check_overlapped_step(M_CASES["LinearAdvectionRLZ_z16_fused"], emu_lib, 1, monkeypatch, batches=(3,))
     check_overlapped_step(M_CASES["LinearAdvectionRLZ_z16_fused"], emu_lib, 2, monkeypatch, batches=(2,), exchange="columns")
+
+
+def check_moist_error_behaviour(S, lib):
+    """BF02_test / rainfall_test: the names condensation_adjustment looks up (src/microphysics.jl:141-165) must exist --
+    the reference throws KeyError on the first step, here the model is refused when it is created -- and the columns must
+    be in the order the equation sets index by position (src/testModels.jl:233-271, :403-447)."""
+    from helpers import moist_case, to_pkg
+    from oracle import grids as G
+    def gp(names):
+        return G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=4, zmin=0, zmax=1e4, zDim=8,
+                                vars={n: i + 1 for i, n in enumerate(names)})
+    good = gp(["s", "xi", "mu", "u", "w", "mu_c", "qss", "mu_r"])
+    ref, _ = moist_case(good, rain=False)
+    sref = S.ReferenceState(ref.sbar, ref.xibar, ref.mubar, ref.mu_lbar, ref.Pxi_bar)
+    def make(eq, g, r=sref):
+        return S.Model(S.ModelParameters(ts=0.1, equation_set=eq, grid_params=to_pkg(g), physical_params={"K": 1.0}), ref_state=r, lib=lib)
+    make("BF02_test", good).close()
+    with pytest.raises(S.ScytheError, match='KeyError: key "mu_c" not found'):
+        make("BF02_test", gp(["s", "xi", "mu", "u", "w", "mu_l", "qss"]))
+    with pytest.raises(S.ScytheError, match="expects vars"):
+        make("rainfall_test", good)                       # BF02 order handed to rainfall_test
+    with pytest.raises(S.ScytheError, match="needs a reference state"):
+        make("rainfall_test", gp(["s", "xi", "mu", "u", "w", "mu_c", "mu_r", "qss"]), r=None)
+
+
+def test_moist_error_behaviour(emu_lib):
+    import scythe_jl_b200 as S
+    check_moist_error_behaviour(S, emu_lib)
+
+
+def check_reference_state_files(S, lib, tmp_path):
+    """createModelTile's reference-state set-up (src/semiimplicit.jl:62-73) through the product: a sounding file through
+    interpolate_reference_file (src/reference_state.jl:17-136) and an exact file through exact_reference_state (:159-199),
+    against the oracle's restatement; then a model created from `ref_state_file` alone steps like one handed the object."""
+    import numpy as np
+    from helpers import model_cases, pkg_model, to_pkg, rel_err
+    from oracle import chebyshev as och
+    from oracle import model as OM
+    case = model_cases()["rainfall_test_semiimplicit"]
+    ogp = case["gp"]
+    gp = to_pkg(ogp)
+    z = och.mish_points(och.ChebyshevParameters(ogp.zmin, ogp.zmax, ogp.zDim, ogp.b_zDim))
+    # a sounding on its own levels: surface line, then altitude / theta / q_v[g/kg]; one model level coincides with a sounding level
+    alts = np.concatenate([np.linspace(250.0, 12000.0, 48), [float(z[3])]])
+    alts.sort()
+    lines = ["1005.0 299.5 16.0"] + [f"{float(a)!r} {float(299.5 + 4.2e-3 * a)!r} {float(16.0 * np.exp(-a / 2600.0))!r}" for a in alts]
+    snd = tmp_path / "sounding.txt"
+    snd.write_text("\n".join(lines) + "\n\n999 1 1\n")          # anything after the first blank line is not read
+    mp = S.ModelParameters(ts=0.5, equation_set="rainfall_test", grid_params=gp, physical_params={"K": 50.0},
+                           ref_state_file=str(snd), options={"semiimplicit": True, "exact_reference_state": False})
+    got = S.interpolate_reference_file(mp, z, lib=lib)
+    want = OM.interpolate_reference_file(ogp, snd.read_text(), z)
+    for k in ("sbar", "xibar", "mubar", "mu_lbar"):
+        assert rel_err(getattr(got, k), getattr(want, k)) <= 1e-12, k
+    assert abs(got.Pxi_bar / want.Pxi_bar - 1) <= 1e-12
+    # exact file: z sbar xibar mubar mu_lbar per level
+    ref = case["ref"]
+    # levels as the library computes them: the file is matched against them number for number (the reference compares text)
+    zc = S.Chebyshev1D(S.ChebyshevParameters(zmin=gp.zmin, zmax=gp.zmax, zDim=gp.zDim, bDim=gp.b_zDim), lib=lib).mishPoints.copy()
+    assert np.abs(zc - och.mish_points(och.ChebyshevParameters(ogp.zmin, ogp.zmax, ogp.zDim, ogp.b_zDim))).max() <= 1e-11 * ogp.zmax
+    Tk = 300.0 - 6.5e-3 * zc
+    raw = np.stack([zc, OM.entropy(Tk, 1.1 * np.exp(-zc / 8e3), 0.01 * np.exp(-zc / 2500)), np.log(1.1 * np.exp(-zc / 8e3) / OM.rho_d0),
+                    OM.bhyp(0.01 * np.exp(-zc / 2500)), OM.bhyp(1e-4 * np.exp(-((zc - 3e3) / 1e3) ** 2))], 1)
+    ex = tmp_path / "exact.txt"
+    ex.write_text("\n".join(" ".join(repr(float(v)) for v in row) for row in raw) + "\n")
+    mp.ref_state_file, mp.options = str(ex), {"semiimplicit": True, "exact_reference_state": True}
+    got = S.exact_reference_state(mp, zc, lib=lib)
+    want = OM.exact_reference_state_from_profiles(ogp, raw[:, 1], raw[:, 2], raw[:, 3], raw[:, 4])
+    for k in ("sbar", "xibar", "mubar", "mu_lbar"):
+        assert rel_err(getattr(got, k), getattr(want, k)) <= 1e-12, k
+    assert abs(got.Pxi_bar / want.Pxi_bar - 1) <= 1e-12
+    bad = tmp_path / "bad.txt"
+    bad.write_text(ex.read_text().replace(repr(float(zc[2])), repr(float(zc[2]) + 1.0), 1))
+    mp.ref_state_file = str(bad)
+    with pytest.raises(S.DomainError, match="Model level does not match reference level"):
+        S.exact_reference_state(mp, zc, lib=lib)
+    # a model built from the file alone == a model handed the ReferenceState object
+    mp.ref_state_file = str(ex)
+    mp.ts = case["ts"]
+    a = S.Model(mp, num_tiles=1, lib=lib)
+    b = S.Model(mp, num_tiles=1, ref_state=got, lib=lib)
+    for m in (a, b):
+        m.initialize(case["ic"])
+        m.run(2)
+    assert np.array_equal(a.state(0, "var_np1"), b.state(0, "var_np1"))
+    a.close(); b.close()
+
+
+def test_reference_state_files(emu_lib, tmp_path):
+    import scythe_jl_b200 as S
+    check_reference_state_files(S, emu_lib, tmp_path)

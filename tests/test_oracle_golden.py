@@ -138,3 +138,42 @@ def test_tile_sum_identity_and_halo_maps():
         shared[hrow] += tile.spectral[htrow]
     assert start == patch.N
     assert np.abs(shared - patch.spectral).max() < 1e-13 * np.abs(patch.spectral).max()
+
+
+def test_moist_closure_identities_and_whole_column_selection():
+    """The moist closure of BF02_test / rainfall_test (src/thermodynamics.jl, src/microphysics.jl) has no golden vector in
+    the reference tree; what can be pinned is its internal consistency and the selection rule of the un-dotted
+    min / max in condensation_adjustment (src/microphysics.jl:185-187: Julia's generic min(x, y) = ifelse(isless(y, x), y, x),
+    isless lexicographic for vectors, isequal / isless for the elements: NaN above everything, -0.0 < 0.0)."""
+    Tk, p = np.float64(288.0), np.float64(900.0)
+    h = 1e-4
+    d = (M.sat_pressure_liquid_buck(Tk + h, p) - M.sat_pressure_liquid_buck(Tk - h, p)) / (2 * h)
+    assert abs(M.sat_pressure_liquid_buck_dT(Tk, p) / d - 1) < 1e-8                  # analytic dT == finite difference
+    es = M.sat_pressure_liquid_buck(Tk, p)
+    assert abs(M.vapor_pressure(p, M.q_sat_liquid(Tk, p)) / es - 1) < 1e-14         # q_sat <-> vapour pressure inverse pair
+    q = np.array([0.0, 1e-9, 1e-4, 2e-2])
+    assert np.allclose(M.ahyp(M.bhyp(q)), q, rtol=1e-12, atol=1e-20)                # hyperbolic water variable round trip
+    rho_d, q_v = np.float64(1.05), np.float64(0.012)
+    s = M.entropy(Tk, rho_d, q_v)
+    assert abs(M.temperature(s, rho_d, q_v) / Tk - 1) < 1e-13                        # entropy <-> temperature
+    assert M.sedimentation(np.float64(1e-3), rho_d, Tk) == 0.0                       # the clamp leaves no fall speed (quirk)
+    A = np.array([[1.0, 5.0, 0.0], [1.0, 2.0, 9.0], [0.0, 1.0, 1.0], [-0.0, 7.0, 7.0], [np.nan, 0.0, 0.0], [2.0, 2.0, 2.0]])
+    B = np.array([[1.0, 6.0, -9.0], [1.0, 2.0, 3.0], [-0.0, 9.0, 9.0], [0.0, 0.0, 0.0], [5.0, 9.0, 9.0], [2.0, 2.0, 2.0]])
+    #            first unequal pair decides | later pair | 0.0 vs -0.0      | -0.0 < 0.0      | NaN is largest  | equal
+    assert list(M._lex_less(A, B)) == [True, False, False, True, False, False]
+    assert list(M._lex_less(B, A)) == [False, True, True, False, True, False]
+
+
+def test_moist_sets_fail_like_the_reference_without_the_named_variables():
+    """condensation_adjustment looks up "mu_c", "mu_r", "qss" by name: BF02_test with a variable list that calls column 6
+    "mu_l" dies with a KeyError on its first step in the reference (src/microphysics.jl:158-165)."""
+    gp = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=4, zmin=0, zmax=1e4, zDim=8,
+                          vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5, "mu_l": 6, "qss": 7})
+    from helpers import moist_case
+    gp8 = G.GridParameters(geometry="RZ", xmin=-1e4, xmax=1e4, num_cells=4, zmin=0, zmax=1e4, zDim=8,
+                           vars={"s": 1, "xi": 2, "mu": 3, "u": 4, "w": 5, "mu_c": 6, "qss": 7, "mu_r": 8})
+    ref, ic = moist_case(gp8, rain=False)
+    mp = M.ModelParameters(ts=0.1, equation_set="BF02_test", grid_params=gp, physical_params={"K": 1.0})
+    run = M.ModelRun(mp, 1, ic[:, :7], ref)
+    with pytest.raises(KeyError, match="mu_c"):
+        run.step()
