@@ -242,6 +242,12 @@ static void build_grid(sb_grid* G) {
   d.ring_n = G->up(G->ring_n);
   d.ring_ri = G->up(G->ring_ri);
   d.ring_hoff = G->up(G->hoff);
+  {   // ring offsets with every ring padded to whole 16-point blocks (blocked SZ layout, sb_internal.hpp RowDst)
+    std::vector<long long> hoffp(G->hoff.size(), 0);
+    for (size_t r = 0; r + 1 < G->hoff.size(); ++r) hoffp[r + 1] = hoffp[r] + ((G->hoff[r + 1] - G->hoff[r] + 15) / 16) * 16;
+    d.hpointsp = hoffp.back();
+    d.ring_hoffp = G->up(hoffp);
+  }
   d.ring_woff = G->up(G->woff);
   d.rad = G->up(G->rad);
   d.h2r = G->up(G->h2r);
@@ -760,6 +766,7 @@ struct TileState {
   double* var_np1 = nullptr;
   double* expd[3] = {nullptr, nullptr, nullptr};  // n, nm1, nm2 (rotating)
   double* impd[3] = {nullptr, nullptr, nullptr};
+  bool hist_untouched = true;   // nothing but the equation-set kernels has written expd[] since it was allocated (zeros)
   HostPipe pipe;
 };
 
@@ -840,6 +847,12 @@ static double param_req(const sb_model* M, const char* k) {
   auto it = M->params.find(k);
   if (it == M->params.end()) throw std::invalid_argument(std::string("physical_params is missing :") + k);
   return it->second;
+}
+
+// variables whose expdot history the fused kernels may leave alone (ModelArrays::passive); SB_PASSIVE=0: A/B switch
+static unsigned passive_mask(const sb_model* M) {
+  static const bool off = std::getenv("SB_PASSIVE") != nullptr && std::atoi(std::getenv("SB_PASSIVE")) == 0;
+  return off ? 0u : equation_set_passive(M->eq, M->gp.nvars);
 }
 
 static void model_check_equation_set(sb_model* M) {
@@ -1101,7 +1114,11 @@ static bool fused_advection_ok(const sb_model* M, const sb_grid* G) {
 static void grid_inverse_advection_fused(sb_grid* P, sb_grid* T, const EqParams& ep, const ModelArrays& a, int tq) {
   DevGrid& t = T->dg;
   DevGrid& p = P->dg;
-  const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
+  // SZ in the blocked layout (two bulk copies per field and tile in the synthesis kernel instead of one per z-mode) when
+  // that kernel runs; the ring-row layout otherwise
+  const bool blocked = inv_z_advection_blocked(t);
+  const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * (blocked ? t.hpointsp : t.hpoints);
+  const int sz_kind = blocked ? 2 : 0;
   const long long sz_off = (3 * slN + 15) & ~15LL;
   T->ensure_scratch_doubles(sz_off + 7 * szN + 16);
   double* SL = T->scratch;                  // [3][slN]   one variable at a time
@@ -1112,12 +1129,12 @@ static void grid_inverse_advection_fused(sb_grid* P, sb_grid* T, const EqParams&
   c.need = k3_need_from_slots(t, 31u);
   launch_inv_r(c, t, p, 1, P->spectralA, p.S, SL, slN, slN, 0, 0);
   launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, 1, SL, slN,
-               slN, SZ, szN, szN, 0, 0, &T->iwork2, T->d_iwork2.data());
+               slN, SZ, szN, szN, sz_kind, 0, &T->iwork2, T->d_iwork2.data());
   c.need = k3_need_from_slots(t, 1u);
   launch_inv_r(c, t, p, 2, P->spectralA + p.S, p.S, SL, 2 * slN, slN, 0, 1);          // SL[0] = u spectrum, SL[1] = v spectrum
   launch_inv_l(c, t, T->iwork, T->d_iwork.data(), T->classes, T->d_tw.data(), T->d_twp.data(), T->d_plans, T->d_blob, 2, SL,
-               2 * slN, slN, SZ + 5 * szN, szN, szN, 0, 1, &T->iwork2, T->d_iwork2.data());
-  launch_inv_z_advection(c, t, T->d_ztiles, T->nztiles, SZ, szN, T->d_parB, ep, a, tq);
+               2 * slN, slN, SZ + 5 * szN, szN, szN, sz_kind, 1, &T->iwork2, T->d_iwork2.data());
+  launch_inv_z_advection(c, t, T->d_ztiles, T->nztiles, SZ, szN, T->d_parB, ep, a, tq, blocked);
 }
 
 // first half of advanceTimestep: tileTransform! + equation set + explicit/semi-implicit step
@@ -1134,6 +1151,7 @@ static void tiles_physics(sb_model* M, int64_t t) {
     a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
     a.imp_n = T.impd[0]; a.imp_nm1 = T.impd[1]; a.imp_nm2 = T.impd[2];
     a.colops = M->d_colops; a.colfrag = M->d_colfrag; a.refstate = M->d_refstate; a.sicols = M->d_sicols;
+    a.passive = T.hist_untouched ? passive_mask(M) : 0u;
     const int tq = (int)std::min<int64_t>(t, 3);
     if (M->k3_slots == 0 && fused_advection_ok(M, G)) {   // K3's last stage and K4 in one kernel: no slot reaches HBM
       grid_inverse_advection_fused(M->cs.on ? G : P, G, M->ep, a, tq);
@@ -1250,6 +1268,7 @@ static void tile_step_overlapped(sb_model* M, TileState& T, int tq) {
   ModelArrays a{};
   a.var_np1 = T.var_np1;
   a.exp_n = T.expd[0]; a.exp_nm1 = T.expd[1]; a.exp_nm2 = T.expd[2];
+  a.passive = T.hist_untouched ? passive_mask(M) : 0u;
   G->slot0_src = nullptr;
   LaunchCtx cm = G->ctx(), cf = G->ctx();
   cm.stream = ov.s_mem;
@@ -2003,6 +2022,14 @@ int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* 
     if (!dst) throw std::invalid_argument("state array not allocated (semi-implicit off)");
     CU(cudaMemcpyAsync(dst, host, (size_t)T.grid->dg.N * T.grid->dg.V * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     CU(cudaStreamSynchronize(m->stream));
+    if (which == 2 || which == 3) {     // a tendency history from outside: variables without a tendency keep the all-zeros
+      const unsigned pm = passive_mask(m);   // guarantee only if what was stored for them is all zeros too (a restart file)
+      const long long N = T.grid->dg.N;
+      for (int v = 0; v < T.grid->dg.V && T.hist_untouched; ++v)
+        if ((pm >> v) & 1u)
+          for (long long i = 0; i < N; ++i)
+            if (host[(long long)v * N + i] != 0.0) { T.hist_untouched = false; break; }
+    }
   });
 }
 static void pipe_open(sb_model* m, TileState& T) {

@@ -382,18 +382,28 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection(DevGrid g, const ZTi
 //     warp) are bank-conflict free.
 // Arithmetic, DMMA order and store pattern are those of the kernel above: bit-identical results.
 // -------------------------------------------------------------------------------------------------------------------
+// BLK: the input is in the blocked SZ layout (sb_internal.hpp RowDst): a tile's 16 points x bz modes of a field are one
+// contiguous run, even modes first, so the tile arrives with TWO bulk copies per field (14 per tile, 2.7 KB each) instead
+// of one 128-byte copy per (field, mode) row (301 per tile).  The copy engine serves a request in some tens of cycles
+// whatever its size (B300_MICROARCH "TMA service/SM"): at 301 + 96 requests per tile the kernel was bound by the REQUEST
+// rate -- 13.5 GB moved in 3.8 ms, and dropping 6.2 GB of history traffic bought only 6 % -- not by HBM or the DMMAs.
+// Rows are 16 doubles, the point index XOR-swizzled by the mode (conflict-free fragment loads without padding); the
+// history blocks arrive as one 8 KB run per array (columns 64 doubles apart; the epilogue's four double2 reads per thread
+// are then 2-way bank conflicts, which is noise).
 #define ZB_HS 72                // column stride (doubles) of a history block in shared memory
+template <bool BLK>
 __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, const ZTile* __restrict__ tiles, int ntiles,
                                                                  const double* __restrict__ in, long long in_fs,
                                                                  const double* __restrict__ parB, EqParams p, ModelArrays arr, int t) {
   SB_DYN_SMEM(double, a);       // [ZF_NF][2 parities][ZM_KK][ZM_CS] | history [2][3][16][ZB_HS] | row table | 2 mbarriers
-  constexpr int COLS = 16, ZM_CS = COLS + 4, ZM_THREADS = COLS * 16, SPLIT = 32 / COLS;
+  constexpr int COLS = 16, ZM_CS = BLK ? COLS : COLS + 4, ZM_THREADS = COLS * 16, SPLIT = 32 / COLS;
+  constexpr int HS = BLK ? 64 : ZB_HS;               // column stride of a history block (BLK: as in HBM, zDim == 64)
   const int zDim = g.zDim, bz = g.bz, zh = zDim >> 1, nzt = zh >> 3, ncg = (ZM_THREADS / 32) / nzt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = lane & 3, i = lane >> 2;
   const int zt = warp % nzt, cg = warp / nzt;
   constexpr int bufsz = ZF_NF * 2 * ZM_KK * ZM_CS;
-  constexpr int histsz = 6 * COLS * ZB_HS;
+  constexpr int histsz = 6 * COLS * HS;
   double* const hist = a + bufsz;
   int4* const rowtab = reinterpret_cast<int4*>(hist + histsz);
   const int nrow = ZF_NF * bz;
@@ -428,6 +438,17 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
   auto issue_in = [&](const ZTile& ztile) {
     const int nc = ztile.ncols > 0 ? ztile.ncols : 0;
     sb_fence_proxy_async();
+    if (BLK) {       // two runs per field: the even modes, then the odd modes, of the tile's 16-point block
+      if (tid == 0) sb_mbar_expect_tx(full_in, nc > 0 ? (unsigned)(ZF_NF * bz * COLS * 8) : 0u);
+      if (nc > 0 && tid < 2 * ZF_NF) {
+        const int f = tid >> 1, par = tid & 1, k0 = (bz + 1) >> 1;
+        const int ring = g.h2r[ztile.hcol0];
+        const long long blk = (long long)bz * (g.ring_hoffp[ring] + (ztile.hcol0 - g.ring_hoff[ring]));
+        sb_bulk_g2s(a + (f * 2 + par) * ZM_KK * ZM_CS, in + (long long)f * in_fs + blk + (par ? k0 * COLS : 0),
+                    (unsigned)((par ? bz - k0 : k0) * COLS * 8), full_in);
+      }
+      return;
+    }
     if (tid == 0) sb_mbar_expect_tx(full_in, (unsigned)(nrow * nc * 8));
     if (nc > 0) {
       const double* src = in + ztile.out_base;
@@ -438,15 +459,28 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
     }
   };
   // history: one 8 zDim-byte run per (array, variable, column)
+  // u and v carry no tendency (src/testModels.jl:93 writes expdot[:, 1] only): while their history arrays still hold the
+  // zeros they were allocated with (arr.passive, cleared by the host when somebody stores into them) they are neither
+  // fetched nor is exp_n = 0 written back -- 6 of the kernel's 16 array passes.  The AB step below runs on zeros either way.
+  const bool uv_live = (arr.passive & 6u) != 6u;
+  const int nvh = uv_live ? 3 : 1;                     // variables whose history is fetched: h | h, u, v
   auto issue_hist = [&](const ZTile& ztile) {
     const int nc = ztile.ncols > 0 ? ztile.ncols : 0;
     sb_fence_proxy_async();
-    if (tid == 0) sb_mbar_expect_tx(full_hist, (unsigned)(nh * 3 * nc * zDim * 8));
-    const int total = nh * 3 * nc;
+    if (tid == 0) sb_mbar_expect_tx(full_hist, (unsigned)(nh * nvh * nc * zDim * 8));
+    if (BLK) {       // the nc columns of a tile are one contiguous run of every [V][N] array
+      if (nc > 0 && tid < nh * nvh) {
+        const int v = tid % nvh, hk = tid / nvh;
+        const double* src = (hk ? arr.exp_nm2 : arr.exp_nm1) + (long long)v * N + (long long)ztile.hcol0 * zDim;
+        sb_bulk_g2s(hist + (hk * 3 + v) * COLS * HS, src, (unsigned)(nc * zDim * 8), full_hist);
+      }
+      return;
+    }
+    const int total = nh * nvh * nc;
     for (int j = tid; j < total; j += ZM_THREADS) {
-      const int c = j % nc, hv = j / nc, v = hv % 3, hk = hv / 3;        // hk = 0: exp_nm1, 1: exp_nm2
+      const int c = j % nc, hv = j / nc, v = hv % nvh, hk = hv / nvh;    // hk = 0: exp_nm1, 1: exp_nm2
       const double* src = (hk ? arr.exp_nm2 : arr.exp_nm1) + (long long)v * N + ((long long)ztile.hcol0 + c) * zDim;
-      sb_bulk_g2s(hist + ((hk * 3 + v) * COLS + c) * ZB_HS, src, (unsigned)(zDim * 8), full_hist);
+      sb_bulk_g2s(hist + ((hk * 3 + v) * COLS + c) * HS, src, (unsigned)(zDim * 8), full_hist);
     }
   };
   const double ts = p.ts, K = p.K;
@@ -472,7 +506,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
     const bool live = c < ztile.ncols && cg < COLS / 8;
     double f[ZF_NF][4];         // f[s][0..3]: field row s at levels z0, z0+1, zDim-2-z0, zDim-1-z0
     {
-      const double* ap = a + q * ZM_CS + (cg < COLS / 8 ? c : i);
+      const double* ap = a + q * ZM_CS + (BLK ? ((cg < COLS / 8 ? c : i) ^ (q << 2)) : (cg < COLS / 8 ? c : i));
 #pragma unroll
       for (int s = 0; s < ZF_NF; ++s) {
         const double* af = ap + (size_t)s * 2 * ZM_KK * ZM_CS;
@@ -498,8 +532,9 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
         double2 h1[3], h2[3];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-          h1[v] = t >= 2 ? *reinterpret_cast<const double2*>(hist + (v * COLS + c) * ZB_HS + zl) : make_double2(0.0, 0.0);
-          h2[v] = t >= 3 ? *reinterpret_cast<const double2*>(hist + ((3 + v) * COLS + c) * ZB_HS + zl) : make_double2(0.0, 0.0);
+          const bool hv = v == 0 || uv_live;
+          h1[v] = (t >= 2 && hv) ? *reinterpret_cast<const double2*>(hist + (v * COLS + c) * HS + zl) : make_double2(0.0, 0.0);
+          h2[v] = (t >= 3 && hv) ? *reinterpret_cast<const double2*>(hist + ((3 + v) * COLS + c) * HS + zl) : make_double2(0.0, 0.0);
         }
         double e[2];
 #pragma unroll
@@ -513,7 +548,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
           const int s = v == 0 ? 0 : 4 + v;
           const double2 f1 = h1[v], f2 = h2[v];
           const double fn0 = v == 0 ? e[0] : 0.0, fn1 = v == 0 ? e[1] : 0.0;
-          *reinterpret_cast<double2*>(arr.exp_n + o) = make_double2(fn0, fn1);
+          if (v == 0 || uv_live) *reinterpret_cast<double2*>(arr.exp_n + o) = make_double2(fn0, fn1);
           *reinterpret_cast<double2*>(arr.var_np1 + o) =
               make_double2(ab_step(t, ts, f[s][2 * hm], fn0, f1.x, f2.x), ab_step(t, ts, f[s][2 * hm + 1], fn1, f1.y, f2.y));
         }
@@ -533,8 +568,15 @@ bool inv_z_advection_ok(const DevGrid& g) {
   return g.has_l && g.has_z && g.V == 3 && (g.zDim == 16 || g.zDim == 32 || g.zDim == 64) && g.bz <= 2 * ZM_KK && g.N % 2 == 0;
 }
 
+// blocked SZ layout: the bulk-copy kernel at 64 levels (history blocks as in HBM); SB_SZ_BLOCKED=0: A/B switch
+bool inv_z_advection_blocked(const DevGrid& g) {
+  static const char* e = std::getenv("SB_SZ_BLOCKED");
+  return inv_z_advection_ok(g) && inv_z_bulk_enabled() && g.zDim == 64 && !(e && std::atoi(e) == 0);
+}
+
 void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, const double* in,
-                            long long in_fstride, const double* parB, const EqParams& p, const ModelArrays& arr, int t) {
+                            long long in_fstride, const double* parB, const EqParams& p, const ModelArrays& arr, int t,
+                            bool blocked) {
   ProfScope prof_scope_(c, "inv_z_k4");
   const bool al16 = ((uintptr_t)in % 16 == 0) && in_fstride % 2 == 0;
   const size_t smem = (size_t)2 * ZF_NF * 2 * ZM_KK * (16 + 4) * sizeof(double) + (size_t)ZF_NF * g.bz * 16;
@@ -543,12 +585,18 @@ void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* t
   const int gx = nwork < sms * 2 ? nwork : sms * 2;
   cudaError_t e;
   // bulk copies need 16-byte aligned rows (in, in_fs even, ring rows are multiples of 4 doubles) and whole history columns
-  if (al16 && inv_z_bulk_enabled() && g.zDim <= ZB_HS - 8) {
+  if (blocked) {
+    if (!al16 || !inv_z_advection_blocked(g)) throw std::runtime_error("blocked SZ layout handed to a grid / buffer that cannot use it");
+    const size_t smem_b = (size_t)(ZF_NF * 2 * ZM_KK * 16 + 6 * 16 * 64) * sizeof(double) + (size_t)((ZF_NF * g.bz + 1) & ~1) * 16 + 32;
+    e = cudaFuncSetAttribute(k_inv_z_advection_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
+    SB_LAUNCH(k_inv_z_advection_bulk<true>, dim3(gx), dim3(256), smem_b, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
+  } else if (al16 && inv_z_bulk_enabled() && g.zDim <= ZB_HS - 8) {
     const size_t smem_b = (size_t)(ZF_NF * 2 * ZM_KK * (16 + 4) + 6 * 16 * ZB_HS) * sizeof(double) +
                           (size_t)((ZF_NF * g.bz + 1) & ~1) * 16 + 32;
-    e = cudaFuncSetAttribute(k_inv_z_advection_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    e = cudaFuncSetAttribute(k_inv_z_advection_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
     if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
-    SB_LAUNCH(k_inv_z_advection_bulk, dim3(gx), dim3(256), smem_b, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
+    SB_LAUNCH(k_inv_z_advection_bulk<false>, dim3(gx), dim3(256), smem_b, c.stream, g, tiles, ntiles, in, in_fstride, parB, p, arr, t);
   } else if (al16) {
     e = cudaFuncSetAttribute(k_inv_z_advection<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));

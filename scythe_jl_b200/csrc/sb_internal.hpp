@@ -78,6 +78,8 @@ struct DevGrid {
   const int* ring_n;           // [rDim]
   const int* ring_ri;          // [rDim]
   const long long* ring_hoff;  // [rDim+1] horizontal point prefix
+  const long long* ring_hoffp; // [rDim+1] the same prefix with every ring padded to a multiple of 16 points (blocked SZ layout)
+  long long hpointsp;          // ring_hoffp[rDim]
   const long long* ring_woff;  // [rDim+1] retained-coefficient prefix (1+2ri per ring, or 1)
   const double* rad;           // [rDim]
   const double* zlev;          // [zDim]
@@ -90,6 +92,44 @@ struct DevGrid {
 int sb_sm_count();
 
 struct ZTile { int hcol0; int ncols; long long out_base; int out_stride; int pad; };
+
+// Where the inverse ring transform puts the rows of one (field, variable, z-mode) of a ring.  out_is_phys selects
+//   1: the physical array [D][V][N] (grids without levels);
+//   0: the post-L scratch SZ, one contiguous row of n points per z-mode:  bz * hoff[r] + zb * n + j;
+//   2: SZ in the BLOCKED layout the fused synthesis kernel (k_inv_z_advection_bulk) fetches with two bulk copies per field
+//      and tile instead of one per z-mode: the ring is cut into blocks of 16 points (rings padded to a multiple of 16),
+//      a block holds all bz modes of its 16 points contiguously, even modes first (the parity split of the synthesis),
+//      and inside a 16-point row the point index is XORed with 4 (k & 3), k = zb >> 1 -- the DMMA fragment loads
+//      (4 modes x 8 points per warp) then hit 16 different banks without padding the rows:
+//        bz * (hoffp[r] + 16 (j >> 4)) + 16 ((zb & 1) * ceil(bz / 2) + k) + ((j & 15) ^ 4 (k & 3))
+struct RowDst {
+  double* base;
+  long long blk;
+  int swz;
+  __device__ __forceinline__ double* at(int j) const {      // j even: a double2 (points j, j + 1) is stored here
+    return blk ? base + (long long)(j >> 4) * blk + ((j & 15) ^ swz) : base + j;
+  }
+  // at(j + 4 T n) == at(j) + n * step(T) for T % 4 == 0: the team kernels store their eight outputs a = n T + tl with one
+  // address computation and a constant stride in either layout
+  __device__ __forceinline__ long long step(int T) const { return blk ? (long long)(T >> 2) * blk : 4LL * T; }
+};
+__device__ __forceinline__ RowDst row_dst(const DevGrid& g, double* out, long long out_fs, long long out_vs, int out_is_phys,
+                                          int f, int v, int var0, int r, long long hoff, int n, int zb) {
+  RowDst d;
+  d.blk = 0; d.swz = 0;
+  if (out_is_phys == 1) {
+    d.base = out + ((long long)f * g.V + var0 + v) * g.N + hoff;
+  } else if (out_is_phys == 0) {
+    d.base = out + (long long)f * out_fs + (long long)v * out_vs + (long long)g.bz * hoff + (long long)zb * n;
+  } else {
+    const int k = zb >> 1;
+    d.base = out + (long long)f * out_fs + (long long)v * out_vs + (long long)g.bz * g.ring_hoffp[r] +
+             16 * ((zb & 1) * ((g.bz + 1) >> 1) + k);
+    d.blk = 16LL * g.bz;
+    d.swz = (k & 3) << 2;
+  }
+  return d;
+}
 struct LWork { int r; int row0; int nrows; int pad; };
 
 // ---------------------------------------------------------------- kernel launchers (sb_transforms.cu)
@@ -267,6 +307,9 @@ struct ModelArrays {
   double* imp_n;       // semi-implicit only
   double* imp_nm1;
   double* imp_nm2;
+  unsigned passive;       // bit v: variable v has no tendency in this equation set AND its expdot history is known to be all
+                          // zeros (never written since allocation): a kernel may skip reading exp_nm1/exp_nm2[v] and writing
+                          // exp_n[v] (= 0); var_np1[v] comes out of the same ab_step arithmetic fed with zeros.  0 = general path
   const double* colops;   // [4][zDim][zDim]: CB->CA->{CI, CIx, CIInt} of "h", (spare)
   const double* colfrag;  // DMMA B fragments of colops 2 (CIInt) and 1 (CIx): [2][zDim/8][zDim/4][32]; null if zDim % 8
   const double* refstate; // [4 profiles][3][zDim] sbar, xibar, mubar, mu_lbar (value, dz, dzz)
@@ -275,11 +318,14 @@ struct ModelArrays {
                           // 1.25 ts), 6 = CB->CA->CIx of "mu_r" (rainfall_test's sedimentation flux divergence)
 };
 void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* need /*[V]: slots the kernel reads*/);
+unsigned equation_set_passive(int eq, int V);   // bit v: the equation set never writes expdot[:, v] (src/testModels.jl:40,68,93: only h)
 void build_colop_fragments(int nz, const double* Mt /*[k][z]*/, std::vector<double>& out);
 // K3 last stage + K4 fused for LinearAdvectionRLZ (sb_chebmma.cu): in = [7 field rows: h value,r,rr,l,ll | u | v][bz][ring rows]
 bool inv_z_advection_ok(const DevGrid& g);
+bool inv_z_advection_blocked(const DevGrid& g);   // the kernel that reads the blocked SZ layout (RowDst) will run for this grid
 void launch_inv_z_advection(const LaunchCtx& c, const DevGrid& g, const ZTile* tiles, int ntiles, const double* in,
-                            long long in_fstride, const double* parB, const EqParams& p, const ModelArrays& arr, int t);
+                            long long in_fstride, const double* parB, const EqParams& p, const ModelArrays& arr, int t,
+                            bool blocked = false);
 void launch_equation_set(const LaunchCtx& c, int eq, const DevGrid& g, const EqParams& p,
                          const ModelArrays& a, int tstep);
 

@@ -72,6 +72,18 @@ void equation_set_needs(int eq, const EqParams& p, const DevGrid& g, unsigned* n
 }
 
 
+// Variables whose tendency column the equation set never writes: expdot_n[:, v] keeps the zeros it was allocated with
+// (LinearAdvectionRZ/RL/RLZ set expdot[:, 1] only, src/testModels.jl:40,68,93), so explicit_timestep adds
+// ts/12 (23*0 - 16*0 + 5*0) to them.  The fused K3+K4 kernel uses this to leave those history arrays alone.
+unsigned equation_set_passive(int eq, int V) {
+  switch (eq) {
+    case EQ_LinearAdvectionRZ:
+    case EQ_LinearAdvectionRL:
+    case EQ_LinearAdvectionRLZ: return V >= 32 ? ~1u : (((1u << V) - 1u) & ~1u);
+    default: return 0u;
+  }
+}
+
 struct PointCtx {
   const DevGrid& g;
   const ModelArrays& a;

@@ -254,17 +254,13 @@ __global__ void __launch_bounds__(512) k_inv_l_fast(DevGrid g, const LWork* __re
     }
     team_conv(v, buf, fc, FHt, tl, active);
     if (active) {
-      double* orow;
-      if (out_is_phys)
-        orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
-      else
-        orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+      const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const int a = n1 * M + tl;
         if (a < m) {
           const double2 Y = cm(v[n1], chirp[a]);
-          *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+          *reinterpret_cast<double2*>(orow.at(4 * a + 2 * half)) = make_double2(Y.x, -Y.y);
         }
       }
     }

@@ -284,17 +284,15 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
       }
       conv2<LOG2L, true, true>(v, buf, tw0, twr, FHt, tl, team, active);
       if (active) {
-        double* orow;
-        if (out_is_phys)
-          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
-        else
-          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
+        double* const o0 = orow.at(4 * tl + 2 * half);
+        const long long ostep = orow.step(T);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
           const int a = n1 * T + tl;
           if (a < m) {
             const double2 Y = cm(v[n1], chirp[a]);
-            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+            *reinterpret_cast<double2*>(o0 + n1 * ostep) = make_double2(Y.x, -Y.y);
           }
         }
       }
@@ -593,18 +591,14 @@ __global__ void __launch_bounds__(R3Cfg<LOG2L2>::NT, 1) k_inv_l3(DevGrid g, cons
       group_sync<T>(grp);            // x is complete
       conv3<LOG2L2, true>(cx, gb, FHt, r, grp, team, tl, active);
       if (active) {
-        double* orow;
-        if (out_is_phys)
-          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
-        else
-          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
           const int i = (r == 1 ? L2 / 2 : 0) + n1 * T + tl;
           const int a = (r == 2 ? L2 : 0) + i;
           if (a < m) {
             const double2 Y = cm(combine3<LOG2L2>(gb, r, i), cx.s_ch[a]);
-            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+            *reinterpret_cast<double2*>(orow.at(4 * a + 2 * half)) = make_double2(Y.x, -Y.y);
           }
         }
       }

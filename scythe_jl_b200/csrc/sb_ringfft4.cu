@@ -200,7 +200,9 @@ __device__ __forceinline__ void conv4(double2 (&v)[16], double2* buf, uint32_t t
 // =====================================================================================
 // inverse: spectra (value, d/dr, d2/dr2) -> 5 real rows; rows of a ring are rho = zb*5 + f
 // =====================================================================================
-template <int LOG2L>
+// BLK: rows go to the blocked SZ layout (sb_internal.hpp RowDst, out_is_phys == 2) -- a separate instantiation, so that the
+// ring-row / physical destinations keep their compile-time store stride
+template <int LOG2L, bool BLK>
 __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __restrict__ work, int nwork, int nvars,
                                                    const double2* __restrict__ twp, const RingPlan* __restrict__ plans,
                                                    const double* __restrict__ blob, const double* __restrict__ in,
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
       sb_tmem_fence_after_sync();
       cur_ring = wk.r;
     }
-    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const long long woff = g.ring_woff[wk.r], hoff = BLK ? g.ring_hoffp[wk.r] : g.ring_hoff[wk.r];
     const int nseq = 2 * wk.nrows;
     // spectrum row of sequence s (rows f = 0, 3, 4 read the value spectrum)
     auto row_of = [&](int s) -> const double* {
@@ -402,11 +404,18 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
         if (tl == 0 && s_next < nseq) request(s_next);     // lands while this convolution runs
       });
       if (active) {
-        double* orow;
-        if (out_is_phys)
-          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
-        else
-          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+        double* orow;                 // destination of this thread's first output a = tl; the others follow at a constant stride
+        long long ostep = 4 * T;
+        if (BLK) {
+          const int k = zb >> 1, j0 = 4 * tl + 2 * half;
+          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + 16 * ((zb & 1) * ((g.bz + 1) >> 1) + k) +
+                 (long long)(j0 >> 4) * (16 * g.bz) + ((j0 & 15) ^ ((k & 3) << 2));
+          ostep = (long long)(4 * T) * g.bz;
+        } else if (out_is_phys) {
+          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half + 4 * tl;
+        } else {
+          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half + 4 * tl;
+        }
         uint32_t r0[16], r1[16];
         sb_tmem_ld16(tb + C::C_CH, r0);
         sb_tmem_ld16(tb + C::C_CH + 16, r1);
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l4(DevGrid g, const LWork* __res
           const double2 ch = n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3);
           if (a < m) {
             const double2 Y = cm(v[n1], ch);
-            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+            *reinterpret_cast<double2*>(orow + (BLK ? n1 * ostep : (long long)(4 * T * n1))) = make_double2(Y.x, -Y.y);
           }
         }
       }
@@ -939,16 +948,15 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, cons
       __syncwarp();
       conv5<LOG2L2>(gb, tb, ctab, r, grp, team, tl);
       {
-        double* orow;
-        if (out_is_phys)
-          orow = out + ((long long)f * g.V + var0 + v_) * g.N + hoff + 2 * half;
-        else
-          orow = out + (long long)f * out_fs + (long long)v_ * out_vs + (long long)g.bz * hoff + (long long)zb * n + 2 * half;
+        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
         uint32_t r0[16], r1[16];
         sb_tmem_ld16(tb + C::C_CH3 + 32 * r, r0);
         sb_tmem_ld16(tb + C::C_CH3 + 32 * r + 16, r1);
         sb_tmem_wait_ld16(r0);
         sb_tmem_wait_ld16(r1);
+#pragma unroll
+        double* const o0 = orow.at(4 * ((r == 2 ? L2 : 0) + (r == 1 ? L2 / 2 : 0) + tl) + 2 * half);
+        const long long ostep = orow.step(T);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
           const int i = (r == 1 ? L2 / 2 : 0) + n1 * T + tl;
@@ -956,7 +964,7 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, cons
           const double2 ch = n1 < 4 ? tm_c(r0, n1 & 3) : tm_c(r1, n1 & 3);
           if (a < m) {
             const double2 Y = cm(combine5(gb, r, i), ch);
-            *reinterpret_cast<double2*>(orow + 4 * a) = make_double2(Y.x, -Y.y);
+            *reinterpret_cast<double2*>(o0 + n1 * ostep) = make_double2(Y.x, -Y.y);
           }
         }
       }
@@ -1143,11 +1151,12 @@ static void launch_inv4(const LaunchCtx& c, const DevGrid& g, const LWork* work,
                         const RingPlan* plans, const double* blob, int nvars, const double* in, long long in_fs,
                         long long in_vs, double* out, long long out_fs, long long out_vs, int out_is_phys, int var0) {
   const size_t smem = R4Cfg<LOG2L>::SMEM;
-  cudaError_t e = cudaFuncSetAttribute(k_inv_l4<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = out_is_phys == 2 ? k_inv_l4<LOG2L, true> : k_inv_l4<LOG2L, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) throw std::runtime_error(std::string("smem opt-in: ") + cudaGetErrorString(e));
   const int total = nwork * nvars, cap = fft_grid_cap(c), gx = total < cap ? total : cap;
   int* counter = take_counter(c);     // non-null: the launch shares the chip with another stream's kernels
-  SB_LAUNCH(k_inv_l4<LOG2L>, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
+  SB_LAUNCH(kern, dim3(gx), dim3(512), smem, c.stream, g, work, nwork, nvars,
             reinterpret_cast<const double2*>(twp), plans, blob, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0,
             c.need.lmask, counter, c.fft_chunk);
   e = cudaGetLastError();

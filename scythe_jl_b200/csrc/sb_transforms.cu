@@ -671,13 +671,9 @@ __global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restric
     const double2* b1 = b0 + L;
     const double2 c = chirp[a];
     double2 Y0 = cmul(b0[a], c), Y1 = cmul(b1[a], c);
-    double* o;
-    if (out_is_phys)
-      o = out + ((long long)f * g.V + var0 + v) * g.N + hoff + 4 * a;
-    else
-      o = out + (long long)f * out_fs + (long long)v * out_vs + (long long)g.bz * hoff + (long long)zb * n + 4 * a;
-    *reinterpret_cast<double2*>(o) = make_double2(Y0.x, -Y0.y);
-    *reinterpret_cast<double2*>(o + 2) = make_double2(Y1.x, -Y1.y);
+    const RowDst o = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v, var0, wk.r, hoff, n, zb);
+    *reinterpret_cast<double2*>(o.at(4 * a)) = make_double2(Y0.x, -Y0.y);
+    *reinterpret_cast<double2*>(o.at(4 * a + 2)) = make_double2(Y1.x, -Y1.y);
   }
 }
 

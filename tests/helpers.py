@@ -136,9 +136,9 @@ def _slab_case(nc=6):
     return gp, ic, prm
 
 
-def fused_advection_case(num_cells, tiles=(1, 2)):
-    """16 levels, no vertical BCs: the fused synthesis + tendency + AB3 kernel (k_inv_z_advection)"""
-    gpf = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=num_cells, zmin=0, zmax=1e3, zDim=16,
+def fused_advection_case(num_cells, tiles=(1, 2), zDim=16):
+    """no vertical BCs: the fused synthesis + tendency + AB3 kernel (k_inv_z_advection); 64 levels: its blocked-SZ form"""
+    gpf = G.GridParameters(geometry="RLZ", xmin=0, xmax=1e5, num_cells=num_cells, zmin=0, zmax=1e3, zDim=zDim,
                            vars={"h": 1, "u": 2, "v": 3})
     r, l, z = G.createGrid(gpf).getGridpoints().T
     icf = np.zeros((r.size, 3))
@@ -182,6 +182,8 @@ def model_cases(small=True):
     ic[:, 2] = -5 * np.sin(l) * np.exp(-z / 900.0)
     cases["LinearAdvectionRLZ"] = dict(gp=gp, eq="LinearAdvectionRLZ", prm={"K": 100.0}, ts=50.0, n=3, ic=ic, tiles=(1, 2))
     cases["LinearAdvectionRLZ_z16_fused"] = fused_advection_case(6)
+    # 64 levels: k_inv_z_advection_bulk<true> on the blocked SZ layout (rings of 8 ... 64 points: whole, partial and empty 16-point blocks)
+    cases["LinearAdvectionRLZ_z64_blocked"] = fused_advection_case(6, zDim=64)
     gp = G.GridParameters(geometry="RZ", xmin=0, xmax=1e5, num_cells=12, zmin=0, zmax=1e4, zDim=12,
                           vars={"h": 1, "u": 2, "x": 3, "w": 4})
     r, z = G.createGrid(gp).getGridpoints().T

@@ -445,3 +445,9 @@ def test_moist_error_behaviour(gpu_lib):
 def test_reference_state_files(gpu_lib, tmp_path):
     from test_kernels_emulated import check_reference_state_files
     check_reference_state_files(S, gpu_lib, tmp_path)
+
+
+@pytest.mark.parametrize("ntiles", [1, 2])
+def test_passive_history_of_tendency_free_variables(ntiles, gpu_lib):
+    from test_kernels_emulated import check_passive_history
+    check_passive_history(S, gpu_lib, B_CASES["LinearAdvectionRLZ_z64_24cells_fused"], ntiles)

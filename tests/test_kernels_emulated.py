@@ -294,3 +294,43 @@ def check_reference_state_files(S, lib, tmp_path):
 def test_reference_state_files(emu_lib, tmp_path):
     import scythe_jl_b200 as S
     check_reference_state_files(S, emu_lib, tmp_path)
+
+
+def check_passive_history(S, lib, case, ntiles=1):
+    """LinearAdvectionRLZ writes a tendency for h only (src/testModels.jl:93): the fused K3+K4 kernel leaves the u / v
+    history arrays alone while they still hold their initial zeros.  (1) the state equals the all-slots path bit for bit,
+    history arrays included; (2) once somebody stores a non-zero history for u (sb_model_set_state), the kernel must
+    read it again: still bit-identical to the all-slots path, which always does; (3) storing zeros keeps the fast path."""
+    import numpy as np
+    from helpers import pkg_model
+    runs = {}
+    for mode in ("all", "fused"):
+        m = pkg_model(case, ntiles, lib)
+        m.set_k3_slots(mode)
+        m.initialize(case["ic"])
+        m.run(3)
+        snap = [[m.state(i, k).copy() for k in ("var_np1", "expdot_nm1", "expdot_nm2")] for i in range(ntiles)]
+        for i in range(ntiles):
+            h = m.state(i, "expdot_nm1")
+            assert not h[:, 1:].any()                       # u, v: zeros
+            m.lib.check(m.lib.sb_model_set_state(m.handle, i, 2, S.api._ptr(np.asfortranarray(h))))   # zeros for u, v: fast path kept
+        m.run(1)
+        snap2 = [[m.state(i, k).copy() for k in ("var_np1", "expdot_nm1", "expdot_nm2")] for i in range(ntiles)]
+        for i in range(ntiles):
+            h = m.state(i, "expdot_nm1")
+            h[:, 1] = 1e-3 * np.cos(np.arange(h.shape[0]))  # a history for u from outside
+            m.lib.check(m.lib.sb_model_set_state(m.handle, i, 2, S.api._ptr(np.asfortranarray(h))))
+        m.run(3)
+        snap3 = [[m.state(i, k).copy() for k in ("var_np1", "expdot_nm1", "expdot_nm2")] for i in range(ntiles)]
+        runs[mode] = (snap, snap2, snap3)
+        m.close()
+    for a, b in zip(runs["all"], runs["fused"]):
+        for ta, tb in zip(a, b):
+            for x, y in zip(ta, tb):
+                assert np.array_equal(x, y)
+    assert np.abs(runs["fused"][2][0][0][:, 1] - runs["fused"][1][0][0][:, 1]).max() > 1e-4     # the injected history acted on u
+
+
+def test_passive_history_of_tendency_free_variables(emu_lib):
+    import scythe_jl_b200 as S
+    check_passive_history(S, emu_lib, M_CASES["LinearAdvectionRLZ_z16_fused"])
