@@ -1094,7 +1094,7 @@ __global__ void k_spline_solve(DevSplineFactor f, int ncols, int qc, const doubl
 // (A is read back: 4S instead of 2S of traffic, but 10x more columns in flight per SM than the
 // whole-column kernel above, whose 172 KB of shared memory allowed 64 columns per SM).
 #define SSQ 128
-__global__ void __launch_bounds__(SSQ) k_spline_solve2(const DevSplineFactor* __restrict__ fs, int ncols, int chol_in_smem,
+__global__ void __launch_bounds__(SSQ, 4) k_spline_solve2(const DevSplineFactor* __restrict__ fs, int ncols, int chol_in_smem,
                                                        const double* __restrict__ B, double* __restrict__ A, long long vstride) {
   __shared__ double tile[SSQ][33];
   SB_DYN_SMEM(double, s_chol);
@@ -1120,24 +1120,35 @@ __global__ void __launch_bounds__(SSQ) k_spline_solve2(const DevSplineFactor* __
     if (M >= 2) bM2 = B[(c0 + tid) * M + M - 2];
   }
   // ---------------- fold + forward substitution  L y = Gamma b
+  // Software pipeline: the warp's 32 columns of the NEXT tile are requested into registers (32 loads in flight per thread)
+  // before the substitution of the current tile starts, so HBM works while the dependent FMA chains run (ncu: 2.8 TB/s with
+  // load, substitution and store phases taking turns).
+  constexpr int NPW = SSQ / (SSQ / 32);          // columns per warp (qq = warp + u * SSQ/32)
+  double xr[NPW];
+  auto fetch = [&](const double* __restrict__ src, int t) {
+    const int m0 = t * 32, cnt = (M - m0 < 32) ? M - m0 : 32;
+#pragma unroll
+    for (int u = 0; u < NPW; ++u) {
+      const int qq = warp + u * (SSQ / 32);
+      xr[u] = (qq < nq && lane < cnt) ? src[(c0 + qq) * M + m0 + lane] : 0.0;
+    }
+  };
+  auto park = [&](int t) {
+    const int m0 = t * 32, cnt = (M - m0 < 32) ? M - m0 : 32;
+#pragma unroll
+    for (int u = 0; u < NPW; ++u) {
+      const int qq = warp + u * (SSQ / 32);
+      if (qq < nq && lane < cnt) tile[qq][lane] = xr[u];
+    }
+  };
   double y1 = 0, y2 = 0, y3 = 0;
+  fetch(B, 0);
   for (int t = 0; t < ntile; ++t) {
     const int m0 = t * 32, cnt = (M - m0 < 32) ? M - m0 : 32;
     __syncthreads();
-    for (int qq0 = warp; qq0 < SSQ; qq0 += 8 * (SSQ / 32)) {     // eight columns per round: eight loads in flight per warp
-      double x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int qq = qq0 + u * (SSQ / 32);
-        x[u] = (qq < nq && lane < cnt) ? B[(c0 + qq) * M + m0 + lane] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int qq = qq0 + u * (SSQ / 32);
-        if (qq < nq && lane < cnt) tile[qq][lane] = x[u];
-      }
-    }
+    park(t);
     __syncthreads();
+    if (t + 1 < ntile) fetch(B, t + 1);
     if (valid) {
       for (int j = 0; j < cnt; ++j) {
         const int i = m0 + j;
@@ -1162,23 +1173,16 @@ __global__ void __launch_bounds__(SSQ) k_spline_solve2(const DevSplineFactor* __
   }
   // ---------------- back substitution  L^T x = y, unfold a = Gamma^T x
   double x1 = 0, x2 = 0, x3 = 0, xa = 0, xb = 0;      // xa = x[n-1], xb = x[n-2]
+  // (the forward sweep's last tile is still in shared memory: the first fetch of the way down re-reads what this block
+  //  itself has just stored -- program order per thread, same addresses)
+  __syncthreads();
+  fetch(A, ntile - 1);
   for (int t = ntile - 1; t >= 0; --t) {
     const int m0 = t * 32, cnt = (M - m0 < 32) ? M - m0 : 32;
     __syncthreads();
-    for (int qq0 = warp; qq0 < SSQ; qq0 += 8 * (SSQ / 32)) {
-      double x[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int qq = qq0 + u * (SSQ / 32);
-        x[u] = (qq < nq && lane < cnt) ? A[(c0 + qq) * M + m0 + lane] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int qq = qq0 + u * (SSQ / 32);
-        if (qq < nq && lane < cnt) tile[qq][lane] = x[u];
-      }
-    }
+    park(t);
     __syncthreads();
+    if (t > 0) fetch(A, t - 1);
     if (valid) {
       for (int j = cnt - 1; j >= 0; --j) {
         const int i = m0 + j;
