@@ -179,8 +179,11 @@ struct sb_grid {
     long long per_v = std::max(fwd_need(), inv_need());
     const char* env = std::getenv("SB_VCHUNK");
     vchunk = dg.V;
+    // as many variables per pass as fit a 16 GiB scratch (C4: all three -- one launch per stage instead of one per
+    // variable: fwd_l 2.89 -> 2.67 ms; the TC boundary-layer set: three of six), SB_SCRATCH_GB / SB_VCHUNK override
+    const long long budget = (std::getenv("SB_SCRATCH_GB") ? std::atoll(std::getenv("SB_SCRATCH_GB")) : 16LL) << 30;
     if (env && std::atoi(env) > 0) vchunk = std::min(dg.V, std::atoi(env));
-    else if (per_v * dg.V * 8 > (4LL << 30)) vchunk = 1;
+    else if (per_v * dg.V * 8 > budget) vchunk = (int)std::max<long long>(1, std::min<long long>(dg.V, budget / std::max<long long>(per_v * 8, 1)));
     scratch_doubles = std::max<long long>(per_v * vchunk, 1) + 16;   // + alignment slack of the SZ region
     CU(cudaMalloc((void**)&scratch, (size_t)scratch_doubles * sizeof(double)));
   }

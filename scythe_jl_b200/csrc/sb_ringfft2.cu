@@ -753,7 +753,7 @@ void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
     launch_inv2<LG>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); \
     break;
   switch (L) {
-    SB_INV2(8) SB_INV2(9) SB_INV2(10) SB_INV2(11) SB_INV2(12) SB_INV2(13)
+    SB_INV2(5) SB_INV2(6) SB_INV2(7) SB_INV2(8) SB_INV2(9) SB_INV2(10) SB_INV2(11) SB_INV2(12) SB_INV2(13)
     default: throw std::runtime_error("launch_inv_l2: unsupported convolution length");
   }
 #undef SB_INV2
@@ -782,7 +782,7 @@ void launch_fwd_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
     launch_fwd2<LG>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs);     \
     break;
   switch (L) {
-    SB_FWD2(8) SB_FWD2(9) SB_FWD2(10) SB_FWD2(11) SB_FWD2(12)
+    SB_FWD2(5) SB_FWD2(6) SB_FWD2(7) SB_FWD2(8) SB_FWD2(9) SB_FWD2(10) SB_FWD2(11) SB_FWD2(12)
     default: throw std::runtime_error("launch_fwd_l2: unsupported convolution length");
   }
 #undef SB_FWD2
