@@ -528,9 +528,13 @@ static void grid_inverse(sb_grid* P, sb_grid* T, const unsigned* need = nullptr,
   }
   T->ensure_scratch();
   const long long slN = (long long)t.bz * t.W, szN = (long long)t.bz * t.hpoints;
-  for (int v0 = 0; v0 < t.V; v0 += T->vchunk) {
-    const int nv = std::min(T->vchunk, t.V - v0);
-    const unsigned slots = chunk_slots(v0, nv);
+  // a pass takes consecutive variables that need the SAME slots (up to vchunk of them): the stage masks are per launch, and
+  // a union over unlike variables would transform rows nobody reads (the boundary-layer set: ub, vb need five ring rows,
+  // the diagnostic wb none)
+  for (int v0 = 0, nv = 1; v0 < t.V; v0 += nv) {
+    const unsigned slots = chunk_slots(v0, 1);
+    nv = 1;
+    while (nv < T->vchunk && v0 + nv < t.V && chunk_slots(v0 + nv, 1) == slots) ++nv;
     if (!slots) continue;                             // nothing of these variables is read (diagnostic outputs)
     c.need = k3_need_from_slots(t, slots);
     double* SL = T->scratch;                          // [3][vchunk][slN]

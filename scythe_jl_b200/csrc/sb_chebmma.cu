@@ -435,15 +435,19 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
   const long long N = g.N;
   const int nh = (t >= 3 ? 2 : (t >= 2 ? 1 : 0));     // history arrays the AB step reads: exp_nm1 (t >= 2), exp_nm2 (t >= 3)
   // rows of the tile: every thread asks for its rows (<= 2), thread 0 arms the barrier with the byte count of the tile
-  auto issue_in = [&](const ZTile& ztile) {
+  // offset of a tile's block in a field row of the blocked layout (fetched one tile ahead, like the radius)
+  auto block_of = [&](const ZTile& z) -> long long {
+    if (!BLK || z.ncols <= 0) return 0;
+    const int ring = g.h2r[z.hcol0];
+    return (long long)bz * (g.ring_hoffp[ring] + (z.hcol0 - g.ring_hoff[ring]));
+  };
+  auto issue_in = [&](const ZTile& ztile, long long blk) {
     const int nc = ztile.ncols > 0 ? ztile.ncols : 0;
     sb_fence_proxy_async();
     if (BLK) {       // two runs per field: the even modes, then the odd modes, of the tile's 16-point block
       if (tid == 0) sb_mbar_expect_tx(full_in, nc > 0 ? (unsigned)(ZF_NF * bz * COLS * 8) : 0u);
       if (nc > 0 && tid < 2 * ZF_NF) {
         const int f = tid >> 1, par = tid & 1, k0 = (bz + 1) >> 1;
-        const int ring = g.h2r[ztile.hcol0];
-        const long long blk = (long long)bz * (g.ring_hoffp[ring] + (ztile.hcol0 - g.ring_hoff[ring]));
         sb_bulk_g2s(a + (f * 2 + par) * ZM_KK * ZM_CS, in + (long long)f * in_fs + blk + (par ? k0 * COLS : 0),
                     (unsigned)((par ? bz - k0 : k0) * COLS * 8), full_in);
       }
@@ -490,11 +494,13 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
   ZTile zt0 = desc(w < nwork ? w : 0), zt1;
   auto radius = [&](const ZTile& z) { return z.ncols > 0 ? g.rad[g.h2r[z.hcol0]] : 1.0; };
   double r0 = radius(zt0), r1;
-  if (w < nwork) { issue_in(zt0); issue_hist(zt0); }
+  long long b1 = 0;
+  if (w < nwork) { issue_in(zt0, block_of(zt0)); issue_hist(zt0); }
   for (; w < nwork; w += G) {
     const bool more = w + G < nwork;
     zt1 = desc(more ? w + G : w);
     r1 = radius(zt1);
+    b1 = block_of(zt1);
     const ZTile ztile = zt0;
     zt0 = zt1;
     const double ri = 1.0 / r0, ri2 = ri * ri;
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
       }
     }
     __syncthreads();            // every warp has drained the tile buffer
-    if (more) issue_in(zt1);    // lands during the epilogue
+    if (more) issue_in(zt1, b1);    // lands during the epilogue
     sb_mbar_wait(full_hist, ph_h);
     ph_h ^= 1u;
     if (live) {

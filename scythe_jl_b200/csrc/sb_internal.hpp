@@ -113,8 +113,9 @@ struct RowDst {
   // address computation and a constant stride in either layout
   __device__ __forceinline__ long long step(int T) const { return blk ? (long long)(T >> 2) * blk : 4LL * T; }
 };
+// hoff: the ring's point offset -- g.ring_hoff[r], or g.ring_hoffp[r] (padded rings) for the blocked layout
 __device__ __forceinline__ RowDst row_dst(const DevGrid& g, double* out, long long out_fs, long long out_vs, int out_is_phys,
-                                          int f, int v, int var0, int r, long long hoff, int n, int zb) {
+                                          int f, int v, int var0, long long hoff, int n, int zb) {
   RowDst d;
   d.blk = 0; d.swz = 0;
   if (out_is_phys == 1) {
@@ -123,8 +124,7 @@ __device__ __forceinline__ RowDst row_dst(const DevGrid& g, double* out, long lo
     d.base = out + (long long)f * out_fs + (long long)v * out_vs + (long long)g.bz * hoff + (long long)zb * n;
   } else {
     const int k = zb >> 1;
-    d.base = out + (long long)f * out_fs + (long long)v * out_vs + (long long)g.bz * g.ring_hoffp[r] +
-             16 * ((zb & 1) * ((g.bz + 1) >> 1) + k);
+    d.base = out + (long long)f * out_fs + (long long)v * out_vs + (long long)g.bz * hoff + 16 * ((zb & 1) * ((g.bz + 1) >> 1) + k);
     d.blk = 16LL * g.bz;
     d.swz = (k & 3) << 2;
   }

@@ -80,6 +80,10 @@ unsigned equation_set_passive(int eq, int V) {
     case EQ_LinearAdvectionRZ:
     case EQ_LinearAdvectionRL:
     case EQ_LinearAdvectionRLZ: return V >= 32 ? ~1u : (((1u << V) - 1u) & ~1u);
+    // the slab / boundary-layer sets diagnose w (column 6) and step it with a zero tendency (src/shallowWaterModels.jl:66-69,108)
+    case EQ_Oneway_ShallowWater_Slab:
+    case EQ_Twoway_ShallowWater_Slab:
+    case EQ_Oneway_ShallowWater_HeightResolvedBL: return V >= 6 ? (1u << 5) : 0u;
     default: return 0u;
   }
 }
@@ -92,6 +96,10 @@ struct PointCtx {
   __device__ __forceinline__ void setP(int v, int d, double x) const { a.phys[((long long)d * g.V + v) * g.N + i] = x; }
   __device__ __forceinline__ void advance(int v, int t, double ts, double u, double fn) const {
     const long long o = (long long)v * g.N + i;
+    if ((a.passive >> v) & 1u) {          // no tendency and an all-zero history (ModelArrays::passive): same arithmetic on zeros,
+      a.var_np1[o] = ab_step(t, ts, u, 0.0, 0.0, 0.0);   // the three history passes over this variable are left out
+      return;
+    }
     double f1 = (t >= 2) ? a.exp_nm1[o] : 0.0;
     double f2 = (t >= 3) ? a.exp_nm2[o] : 0.0;
     a.exp_n[o] = fn;

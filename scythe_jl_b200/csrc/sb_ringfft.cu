@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(512) k_inv_l_fast(DevGrid g, const LWork* __re
   const double2* FHt = ph + m;
   const int team = tid / T, tl = tid - team * T;
   double2* buf = sm + (size_t)team * Lp;
-  const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+  const long long woff = g.ring_woff[wk.r], hoff = (out_is_phys == 2 ? g.ring_hoffp : g.ring_hoff)[wk.r];
   const int nseq = 2 * wk.nrows;
   for (int it = 0; it < fc.iters; ++it) {
     const int s = it * fc.nteams + team;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(512) k_inv_l_fast(DevGrid g, const LWork* __re
     }
     team_conv(v, buf, fc, FHt, tl, active);
     if (active) {
-      const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
+      const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, hoff, n, zb);
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const int a = n1 * M + tl;

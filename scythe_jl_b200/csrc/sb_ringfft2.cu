@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
     }
     const double2* FHt = C::FH_SMEM ? s_FH : FH_g;
     const double2* chirp = C::CH_SMEM ? s_ch : chirp_g;
-    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const long long woff = g.ring_woff[wk.r], hoff = (out_is_phys == 2 ? g.ring_hoffp : g.ring_hoff)[wk.r];
     const int nseq = 2 * wk.nrows;
     for (int s = team; s - team < nseq; s += C::NTEAMS) {
       const bool active = s < nseq;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
       }
       conv2<LOG2L, true, true>(v, buf, tw0, twr, FHt, tl, team, active);
       if (active) {
-        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
+        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, hoff, n, zb);
         double* const o0 = orow.at(4 * tl + 2 * half);
         const long long ostep = orow.step(T);
 #pragma unroll
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(R3Cfg<LOG2L2>::NT, 1) k_inv_l3(DevGrid g, cons
       cur_ring = wk.r;
     }
     const double2* FHt = C::FH_SMEM ? cx.s_FH : FH_g;
-    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const long long woff = g.ring_woff[wk.r], hoff = (out_is_phys == 2 ? g.ring_hoffp : g.ring_hoff)[wk.r];
     const int nseq = 2 * wk.nrows;
     for (int s = grp; s - grp < nseq; s += C::NGROUPS) {
       const bool active = s < nseq;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(R3Cfg<LOG2L2>::NT, 1) k_inv_l3(DevGrid g, cons
       group_sync<T>(grp);            // x is complete
       conv3<LOG2L2, true>(cx, gb, FHt, r, grp, team, tl, active);
       if (active) {
-        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
+        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, hoff, n, zb);
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
           const int i = (r == 1 ? L2 / 2 : 0) + n1 * T + tl;

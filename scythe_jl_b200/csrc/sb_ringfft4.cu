@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, cons
       sb_tmem_fence_after_sync();
       cur_ring = wk.r;
     }
-    const long long woff = g.ring_woff[wk.r], hoff = g.ring_hoff[wk.r];
+    const long long woff = g.ring_woff[wk.r], hoff = (out_is_phys == 2 ? g.ring_hoffp : g.ring_hoff)[wk.r];
     const int nseq = 2 * wk.nrows;
     auto row_of = [&](int s) -> const double* {
       const int rho = wk.row0 + (s >> 1), zb = rho / 5, f = rho - zb * 5;
@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(R5Cfg<LOG2L2>::NT, 1) k_inv_l5(DevGrid g, cons
       __syncwarp();
       conv5<LOG2L2>(gb, tb, ctab, r, grp, team, tl);
       {
-        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, wk.r, hoff, n, zb);
+        const RowDst orow = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v_, var0, hoff, n, zb);
         uint32_t r0[16], r1[16];
         sb_tmem_ld16(tb + C::C_CH3 + 32 * r, r0);
         sb_tmem_ld16(tb + C::C_CH3 + 32 * r + 16, r1);

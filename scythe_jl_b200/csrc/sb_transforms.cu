@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restric
   __syncthreads();
   bluestein_conv(buf, log2L, ndft, tw, FH, tid, nthr);
   // 3. un-chirp; conj(Y) = x_{4a} + i x_{4a+1} (first DFT), x_{4a+2} + i x_{4a+3} (second)
-  const long long hoff = g.ring_hoff[wk.r];
+  const long long hoff = (out_is_phys == 2 ? g.ring_hoffp : g.ring_hoff)[wk.r];
   for (int i = tid; i < wk.nrows * m; i += nthr) {
     int row = i / m, a = i - row * m;
     const int rho = wk.row0 + row;
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(512) k_inv_l(DevGrid g, const LWork* __restric
     const double2* b1 = b0 + L;
     const double2 c = chirp[a];
     double2 Y0 = cmul(b0[a], c), Y1 = cmul(b1[a], c);
-    const RowDst o = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v, var0, wk.r, hoff, n, zb);
+    const RowDst o = row_dst(g, out, out_fs, out_vs, out_is_phys, f, v, var0, hoff, n, zb);
     *reinterpret_cast<double2*>(o.at(4 * a)) = make_double2(Y0.x, -Y0.y);
     *reinterpret_cast<double2*>(o.at(4 * a + 2)) = make_double2(Y1.x, -Y1.y);
   }
