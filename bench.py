@@ -556,7 +556,7 @@ def run_ours(args):
         if fused:     # read A and 2 history arrays, write var_np1 + expdot_n: nothing else is algorithmically required
             del groups["K3 tileTransform! (inv_r+inv_l+inv_z)"], groups[f"K4 equation set + AB3 ({args.equation_set})"]
             groups[f"K3+K4 tileTransform! + {args.equation_set} + AB3 (inv_r+inv_l+inv_z_k4, fused)"] = (
-                ["inv_r", "inv_l", "inv_z_k4"], 8.0 * (vr * Sg + N * k4_hist))
+                ["inv_r", "inv_l", "inv_z_k4"], 8.0 * (vr * Sg + N * k4_hist))      # every variable with its history
         det = {}
         for name, (ks, nbytes) in groups.items():
             ms = sum(prof_.get(k, {"ms": 0.0})["ms"] for k in ks) / steps_
@@ -617,6 +617,11 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": top, "achieved": detail[top]["achieved_GBps"], "peak": peak, "unit": "GB/s",
             "frac": detail[top]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": detail[top]["algorithmic_GB"] * 1e9,
+            "algorithmic_bytes_note": "SURVEY 8(d) figure: read A and two history arrays, write var_np1 and expdot_n for EVERY variable "
+                                      "(8 (V S + 4 V N)).  Since round 2 the fused kernel leaves the history arrays of u and v alone "
+                                      "while they hold their initial zeros (LinearAdvectionRLZ gives them no tendency, "
+                                      "src/testModels.jl:93): what it must touch is 8 (V S + 6 N) = "
+                                      f"{8.0 * (V * Sg + 6 * N) / 1e9:.2f} GB; `achieved` / `frac` keep the SURVEY figure" if is_fused and not tcbl else None,
             "share_of_step": detail[top]["ms_per_step"] / ms_step, "ncu": ncu_note, "ring_fft_fp64": fp64_roof}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -635,6 +640,10 @@ def run_ours(args):
             "all": f"all: every one of the {V * D} (variable, slot) pairs is produced"}[args.k3_slots]
     if args.k3_slots != "all":
         what += "; state bit-identical to the all-slots step (tests/test_gpu_parity.py::test_needed_slots_*), which is timed in 'materialised'"
+    line["config"]["zero_history"] = ("variables the equation set gives no tendency (LinearAdvectionRLZ: u, v; boundary-layer set: the diagnostic "
+                                      "wb) keep the all-zero expdot history they were allocated with; the step kernels neither read it nor "
+                                      "write zeros back (same AB3 arithmetic on zeros, state and history bit-identical to the general path: "
+                                      "tests test_passive_history_*; SB_PASSIVE=0 restores the reads and writes)")
     line["config"]["k3_slots"] = what
     if mat:
         mdet, mkern, mbytes = tables(mat["prof"], mat["steps"], V * D, V)
