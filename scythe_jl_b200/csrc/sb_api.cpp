@@ -245,12 +245,11 @@ static void build_grid(sb_grid* G) {
   d.ring_n = G->up(G->ring_n);
   d.ring_ri = G->up(G->ring_ri);
   d.ring_hoff = G->up(G->hoff);
-  {   // ring offsets with every ring padded to whole 16-point blocks (blocked SZ layout, sb_internal.hpp RowDst)
-    std::vector<long long> hoffp(G->hoff.size(), 0);
-    for (size_t r = 0; r + 1 < G->hoff.size(); ++r) hoffp[r + 1] = hoffp[r] + ((G->hoff[r + 1] - G->hoff[r] + 15) / 16) * 16;
-    d.hpointsp = hoffp.back();
-    d.ring_hoffp = G->up(hoffp);
-  }
+  // ring offsets with every ring padded to whole 16-point blocks (blocked SZ layout, sb_internal.hpp RowDst)
+  std::vector<long long> hoffp(G->hoff.size(), 0);
+  for (size_t r = 0; r + 1 < G->hoff.size(); ++r) hoffp[r + 1] = hoffp[r] + ((G->hoff[r + 1] - G->hoff[r] + 15) / 16) * 16;
+  d.hpointsp = hoffp.back();
+  d.ring_hoffp = G->up(hoffp);
   d.ring_woff = G->up(G->woff);
   d.rad = G->up(G->rad);
   d.h2r = G->up(G->h2r);
@@ -331,6 +330,9 @@ static void build_grid(sb_grid* G) {
           t.ncols = std::min(32, G->ring_n[r] - j0);
           t.out_base = (long long)d.bz * G->hoff[r] + j0;
           t.out_stride = G->ring_n[r];
+          t.ring = r;
+          t.rad = G->rad[r];
+          t.blk = (long long)d.bz * (hoffp[r] + j0);
           zt.push_back(t);
         }
       }

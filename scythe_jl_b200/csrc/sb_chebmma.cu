@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection(DevGrid g, const ZTi
   ZTile zt0 = desc(w < nwork ? w : 0), zt1;
   // the tile's radius (a ZTile lies inside one ring) is fetched with the descriptor, one tile ahead: h2r -> rad is a
   // dependent pair of global loads that used to sit right behind the barrier (12 % of the stall samples)
-  auto radius = [&](const ZTile& z) { return z.ncols > 0 ? g.rad[g.h2r[z.hcol0]] : 1.0; };
+  auto radius = [&](const ZTile& z) { return z.ncols > 0 ? z.rad : 1.0; };     // (rides in the descriptor: no dependent lookups)
   double r0 = radius(zt0), r1;
   if (w < nwork) issue(zt0, a);
   for (; w < nwork; w += G) {
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
   auto desc = [&](int w) {       // COLS-column sub-tile of a 32-column ZTile
     ZTile tl = tiles[w / SPLIT];
     const int off = (w % SPLIT) * COLS;
-    tl.hcol0 += off; tl.out_base += off;
+    tl.hcol0 += off; tl.out_base += off; tl.blk += (long long)off * bz;
     tl.ncols = tl.ncols - off < COLS ? tl.ncols - off : COLS;   // may be <= 0: empty sub-tile
     return tl;
   };
@@ -436,11 +436,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
   const int nh = (t >= 3 ? 2 : (t >= 2 ? 1 : 0));     // history arrays the AB step reads: exp_nm1 (t >= 2), exp_nm2 (t >= 3)
   // rows of the tile: every thread asks for its rows (<= 2), thread 0 arms the barrier with the byte count of the tile
   // offset of a tile's block in a field row of the blocked layout (fetched one tile ahead, like the radius)
-  auto block_of = [&](const ZTile& z) -> long long {
-    if (!BLK || z.ncols <= 0) return 0;
-    const int ring = g.h2r[z.hcol0];
-    return (long long)bz * (g.ring_hoffp[ring] + (z.hcol0 - g.ring_hoff[ring]));
-  };
+  auto block_of = [&](const ZTile& z) -> long long { return z.blk; };
   auto issue_in = [&](const ZTile& ztile, long long blk) {
     const int nc = ztile.ncols > 0 ? ztile.ncols : 0;
     sb_fence_proxy_async();
@@ -492,7 +488,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
   int w = blockIdx.x;
   unsigned ph_in = 0, ph_h = 0;
   ZTile zt0 = desc(w < nwork ? w : 0), zt1;
-  auto radius = [&](const ZTile& z) { return z.ncols > 0 ? g.rad[g.h2r[z.hcol0]] : 1.0; };
+  auto radius = [&](const ZTile& z) { return z.ncols > 0 ? z.rad : 1.0; };     // (rides in the descriptor: no dependent lookups)
   double r0 = radius(zt0), r1;
   long long b1 = 0;
   if (w < nwork) { issue_in(zt0, block_of(zt0)); issue_hist(zt0); }
@@ -513,16 +509,25 @@ __global__ void __launch_bounds__(256, 2) k_inv_z_advection_bulk(DevGrid g, cons
     double f[ZF_NF][4];         // f[s][0..3]: field row s at levels z0, z0+1, zDim-2-z0, zDim-1-z0
     {
       const double* ap = a + q * ZM_CS + (BLK ? ((cg < COLS / 8 ? c : i) ^ (q << 2)) : (cg < COLS / 8 ? c : i));
+      // k-tile outermost: the 14 accumulator pairs (7 fields x 2 parities) are independent chains, so consecutive DMMAs
+      // never wait for each other (field-outermost left two chains in flight: 40 % of the DMMA phase's stall samples were
+      // fixed-latency waits, profiles/r2za_ncu_full_k_inv_z_advection_bulk_blocked.txt).  Each chain still accumulates its
+      // k-tiles in ascending order: the values are bit-identical.
+      double E[ZF_NF][2], O[ZF_NF][2];
+#pragma unroll
+      for (int s = 0; s < ZF_NF; ++s) { E[s][0] = 0.0; E[s][1] = 0.0; O[s][0] = 0.0; O[s][1] = 0.0; }
+#pragma unroll
+      for (int kt = 0; kt < ZM_KT; ++kt) {
+#pragma unroll
+        for (int s = 0; s < ZF_NF; ++s) {
+          const double* af = ap + (size_t)s * 2 * ZM_KK * ZM_CS;
+          sb_dmma(E[s][0], E[s][1], af[(kt * 4) * ZM_CS], B[0][kt]);
+          sb_dmma(O[s][0], O[s][1], af[(ZM_KK + kt * 4) * ZM_CS], B[1][kt]);
+        }
+      }
 #pragma unroll
       for (int s = 0; s < ZF_NF; ++s) {
-        const double* af = ap + (size_t)s * 2 * ZM_KK * ZM_CS;
-        double E[2] = {0, 0}, O[2] = {0, 0};
-#pragma unroll
-        for (int kt = 0; kt < ZM_KT; ++kt) {
-          sb_dmma(E[0], E[1], af[(kt * 4) * ZM_CS], B[0][kt]);
-          sb_dmma(O[0], O[1], af[(ZM_KK + kt * 4) * ZM_CS], B[1][kt]);
-        }
-        f[s][0] = E[0] + O[0]; f[s][1] = E[1] + O[1]; f[s][2] = E[1] - O[1]; f[s][3] = E[0] - O[0];
+        f[s][0] = E[s][0] + O[s][0]; f[s][1] = E[s][1] + O[s][1]; f[s][2] = E[s][1] - O[s][1]; f[s][3] = E[s][0] - O[s][0];
       }
     }
     __syncthreads();            // every warp has drained the tile buffer

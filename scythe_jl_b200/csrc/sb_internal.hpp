@@ -91,7 +91,10 @@ struct DevGrid {
 // number of SMs of the current device (148 on B200), queried once per device; grids of the persistent kernels are sized from it
 int sb_sm_count();
 
-struct ZTile { int hcol0; int ncols; long long out_base; int out_stride; int pad; };
+// a <= 32-column tile of one ring for the Chebyshev kernels.  ring / rad / blk ride along so that the fused kernel needs no
+// dependent lookups (h2r -> rad, h2r -> ring offsets) behind the descriptor load: blk = bz * (hoffp[ring] + j0), the tile's
+// block in a field row of the blocked SZ layout
+struct ZTile { int hcol0; int ncols; long long out_base; int out_stride; int ring; double rad; long long blk; };
 
 // Where the inverse ring transform puts the rows of one (field, variable, z-mode) of a ring.  out_is_phys selects
 //   1: the physical array [D][V][N] (grids without levels);
