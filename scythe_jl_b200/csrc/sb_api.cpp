@@ -19,7 +19,7 @@
 
 using namespace sb;
 
-namespace sb { int sb_rows_per_cta(int L); }
+namespace sb { int sb_rows_per_cta(int L, bool fast); }
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -355,13 +355,13 @@ static void build_grid(sb_grid* G) {
   if (d.has_l) {
     std::vector<RingPlan> plans;
     std::vector<double> blob;
-    build_ring_plans(G->ring_ri, G->classes, plans, blob);
+    build_ring_plans(d.has_z ? 32 : 256, G->ring_ri, G->classes, plans, blob);
     G->d_plans = G->up(plans);
     G->d_blob = G->up(blob);
     G->fwork.assign(G->classes.size(), {});
     G->iwork.assign(G->classes.size(), {});
     for (int r = d.rDim - 1; r >= 0; --r) {
-      int nr = sb_rows_per_cta(plans[r].L);
+      int nr = sb_rows_per_cta(plans[r].L, G->classes[plans[r].cls].fast);
       for (int row0 = 0; row0 < d.bz; row0 += nr) G->fwork[plans[r].cls].push_back(LWork{r, row0, std::min(nr, d.bz - row0), 0});
       for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork[plans[r].cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
     }
@@ -388,7 +388,7 @@ static void build_grid(sb_grid* G) {
         if (cl.fast || cl.R == 3) continue;
         iw.insert(iw.end(), G->iwork[ci].begin(), G->iwork[ci].end());
         fw.insert(fw.end(), G->fwork[ci].begin(), G->fwork[ci].end());
-        smem = std::max(smem, (size_t)2 * sb_rows_per_cta(cl.L) * cl.L * 16);
+        smem = std::max(smem, (size_t)2 * sb_rows_per_cta(cl.L, false) * cl.L * 16);
       }
       G->small.niwork = (int)iw.size();
       G->small.nfwork = (int)fw.size();

@@ -61,7 +61,10 @@ struct RingPlan {            // Bluestein plan of one ring (sub-DFT length m = n
 // blob layout per ring: chirp[2m] | wk[2m] | ph[2m] | FHp[2L] | P0,Q0,P1,Q1[2m each] | A0..A3[2m each]  (interleaved re,im)
 //   inverse prologue:  u[k] = conj(c_k D_k) P_h[k] + (c_{m-k} D_{m-k}) Q_h[k]          (sequence half h = 0,1)
 //   forward epilogue:  X[k] = b0[k] A0[k] + conj(b0[m-k]) A1[k] + b1[k] A2[k] + conj(b1[m-k]) A3[k]
-void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& classes,
+// min_fast_L: shortest convolution length served by the register-resident team kernels on this grid (the rest goes to the
+// generic kernel, all classes in one launch): 32 on grids with levels (hundreds of sequences per ring), 256 on RL grids
+// (ten sequences per ring and variable: launch-bound, fewer launches win)
+void build_ring_plans(int min_fast_L, const std::vector<int>& ring_ri, std::vector<FftClass>& classes,
                       std::vector<RingPlan>& plans, std::vector<double>& blob);
 // host reference of the device FFT (used to build FHp and by self-tests)
 void host_fft_dif(double* x, int L, const double* tw);   // natural -> digit-reversed

@@ -285,8 +285,8 @@ void fast_class_config(int L, int* log2L, int* nfull, int* rf, int* T, int* ntea
 
 bool fast_class_supported(int L) {
   static const bool generic_only = std::getenv("SB_FFT_GENERIC") != nullptr;   // A/B switch for tests/profiling
-  // L = 32 .. 128 (rings of 36 .. 256 points): the v2 kernels with sub-warp teams of 2 .. 8 threads (one strided radix-16 pass +
-  // a register-local radix 2 / 4 / 8 pass); below that the generic shared-memory kernel.  SB_FFT_FAST_MINL: A/B switch
+  // L = 32 .. 128 (rings of 36 .. 256 points): the v1 register kernel with sub-warp teams of 2 .. 8 threads (one strided
+  // radix-16 pass + a register-local radix 2 / 4 / 8 pass); below that the generic shared-memory kernel.  SB_FFT_FAST_MINL: A/B switch
   static const int minL = std::getenv("SB_FFT_FAST_MINL") ? std::atoi(std::getenv("SB_FFT_FAST_MINL")) : 32;
   return !generic_only && L >= minL && L >= 32 && L <= 8192;
 }

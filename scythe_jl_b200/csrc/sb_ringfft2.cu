@@ -224,11 +224,15 @@ __global__ void __launch_bounds__(512, 1) k_inv_l2(DevGrid g, const LWork* __res
     const long long woff = g.ring_woff[wk.r], hoff = (out_is_phys == 2 ? g.ring_hoffp : g.ring_hoff)[wk.r];
     const int nseq = 2 * wk.nrows;
     for (int s = team; s - team < nseq; s += C::NTEAMS) {
-      const bool active = s < nseq;
       const int row = s >> 1, half = s & 1;
       const int rho = wk.row0 + row;
       const int zb = rho / 5, f = rho - zb * 5;
-      if (!((lmask >> f) & 1)) continue;   // row not read by the equation set (team-uniform: no barrier is skipped by part of a team)
+      // a row the equation set does not read is skipped.  Teams of >= 16 threads: the two teams of a warp work on the two
+      // halves of ONE row, so the decision is warp-uniform and the trip is left before any barrier.  Smaller teams (L <= 128)
+      // share a warp with teams on OTHER rows: they stay in step (the barriers below are __syncwarp) and merely go inactive.
+      const bool wanted = ((lmask >> f) & 1) != 0;
+      if (T >= 16 && !wanted) continue;
+      const bool active = s < nseq && wanted;
       double2 v[16];
       team_sync<T>(team);            // the team's previous sequence has finished reading buf
       if (SB_FFT_L2PF && s + C::NTEAMS < nseq) {   // the team's next spectrum row: (2m-1) doubles <= T lines of 128 B
@@ -711,6 +715,8 @@ bool fft2_supported(int L, bool forward) {
   static const char* env = std::getenv("SB_FFT");
   if (env && std::string(env) == "v1") return false;   // A/B switch
   if (L % 3 == 0) return L == 1536 || L == 3072 || L == 6144;
+  // (L = 32 .. 128 run in the v1 register kernel k_*_l_fast; routing them through these kernels with sub-warp teams of 2 .. 8
+  //  threads gave wrong results in the emulated tests and was not pursued)
   return L >= 256 && L <= (forward ? 4096 : 8192);
 }
 
@@ -753,7 +759,7 @@ void launch_inv_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
     launch_inv2<LG>(c, g, work, nwork, twp, plans, blob, nvars, in, in_fs, in_vs, out, out_fs, out_vs, out_is_phys, var0); \
     break;
   switch (L) {
-    SB_INV2(5) SB_INV2(6) SB_INV2(7) SB_INV2(8) SB_INV2(9) SB_INV2(10) SB_INV2(11) SB_INV2(12) SB_INV2(13)
+    SB_INV2(8) SB_INV2(9) SB_INV2(10) SB_INV2(11) SB_INV2(12) SB_INV2(13)
     default: throw std::runtime_error("launch_inv_l2: unsupported convolution length");
   }
 #undef SB_INV2
@@ -782,7 +788,7 @@ void launch_fwd_l2(const LaunchCtx& c, const DevGrid& g, const LWork* work, int 
     launch_fwd2<LG>(c, g, work, nwork, twp, plans, blob, nvars, in, in_vs, mirror, mirror_vs, out, out_vs);     \
     break;
   switch (L) {
-    SB_FWD2(5) SB_FWD2(6) SB_FWD2(7) SB_FWD2(8) SB_FWD2(9) SB_FWD2(10) SB_FWD2(11) SB_FWD2(12)
+    SB_FWD2(8) SB_FWD2(9) SB_FWD2(10) SB_FWD2(11) SB_FWD2(12)
     default: throw std::runtime_error("launch_fwd_l2: unsupported convolution length");
   }
 #undef SB_FWD2

@@ -379,7 +379,7 @@ void host_fft_dit(double* x, int L, const double* tw) {
   }
 }
 
-void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& classes,
+void build_ring_plans(int min_fast_L, const std::vector<int>& ring_ri, std::vector<FftClass>& classes,
                       std::vector<RingPlan>& plans, std::vector<double>& blob) {
   classes.clear();
   plans.assign(ring_ri.size(), RingPlan());
@@ -407,7 +407,7 @@ void build_ring_plans(const std::vector<int>& ring_ri, std::vector<FftClass>& cl
       c.tw[2 * t] = (double)cosl(-2.0L * kPiL * t / L);
       c.tw[2 * t + 1] = (double)sinl(-2.0L * kPiL * t / L);
     }
-    c.fast = fast_class_supported(L);
+    c.fast = fast_class_supported(L) && L >= min_fast_L;
     if (c.fast) fast_class_twiddles(L, c.twp, c.twoff);
     classes.push_back(std::move(c));
     return (int)classes.size() - 1;

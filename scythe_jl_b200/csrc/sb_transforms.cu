@@ -507,8 +507,8 @@ __global__ void __launch_bounds__(512) k_fwd_l(DevGrid g, const LWork* __restric
   }
 }
 
-int sb_rows_per_cta(int L) {
-  if (fast_class_supported(L)) {
+int sb_rows_per_cta(int L, bool fast) {
+  if (fast) {
     int log2L, nfull, rf, T, nteams, iters, nrows;
     fast_class_config(L, &log2L, &nfull, &rf, &T, &nteams, &iters, &nrows);
     return nrows;
@@ -575,7 +575,7 @@ void launch_fwd_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                         mirror_vstride, out, out_vstride);
       continue;
     }
-    int nr = sb_rows_per_cta(L);
+    int nr = sb_rows_per_cta(L, false);
     size_t smem = (size_t)2 * nr * L * 16;
     opt_in_smem(k_fwd_l, smem);
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
@@ -718,7 +718,7 @@ void launch_inv_l(const LaunchCtx& c, const DevGrid& g, const std::vector<std::v
                         in_vstride, out, out_fstride, out_vstride, out_is_phys, var0);
       continue;
     }
-    int nr = sb_rows_per_cta(L);
+    int nr = sb_rows_per_cta(L, false);
     size_t smem = (size_t)2 * nr * L * 16;
     opt_in_smem(k_inv_l, smem);
     int threads = (nr * L / 2 >= 512) ? 512 : ((nr * L / 2 >= 256) ? 256 : 128);
