@@ -660,25 +660,22 @@ __global__ void __launch_bounds__(FZ_THREADS, 3) k_fwd_z_mma(DevGrid g, const ZT
     sb_cp_commit();
   };
   // three-stage ring of tiles: two tiles are always in flight behind the one being transformed
+  // (tried: fetching the descriptor of the tile to be issued one iteration earlier, because 13 % of the kernel's stall samples
+  //  sit on that dependent load -- 1.21 -> 1.28 ms: the two extra 40-byte descriptor loads per tile cost more than the wait)
   const int G = gridDim.x;
   auto desc = [&](int w) { return w < nwork ? tiles[w % ntiles] : ZTile{}; };
-  auto issue_d = [&](int w, const ZTile& dz, int stage) {   // always commits a group (possibly empty): uniform group counting
-    if (w < nwork) issue(w, dz, u + stage * 32 * FZ_US);
+  auto issue_w = [&](int w, int stage) {          // always commits a group (possibly empty): uniform group counting
+    if (w < nwork) issue(w, desc(w), u + stage * 32 * FZ_US);
     else sb_cp_commit();
   };
   int w = blockIdx.x, cur = 0;
-  issue_d(w, desc(w), 0);
-  issue_d(w + G, desc(w + G), 1);
-  // the descriptor of the tile issued in an iteration is fetched one iteration earlier: its load has a whole tile's work to
-  // land instead of stalling the copy requests behind it (ncu: 13 % of the kernel's samples sat on that dependent load)
-  ZTile dn = desc(w + 2 * G);
+  issue_w(w, 0);
+  issue_w(w + G, 1);
   for (; w < nwork; w += G) {
     const ZTile zt = desc(w);     // (cached: it was fetched when the tile was issued) -- overlaps the wait below
-    const ZTile dnn = desc(w + 3 * G);
     sb_cp_wait<1>();              // everything but the newest group has landed: tile w is in stage `cur`
     __syncthreads();              // ... for every thread, and everybody has left the stage tile w-G used
-    issue_d(w + 2 * G, dn, cur == 0 ? 2 : cur - 1);
-    dn = dnn;
+    issue_w(w + 2 * G, cur == 0 ? 2 : cur - 1);
     const int v = w / ntiles;
     const double* ub = u + cur * 32 * FZ_US;
     if (mirror) {
