@@ -451,3 +451,52 @@ def test_reference_state_files(gpu_lib, tmp_path):
 def test_passive_history_of_tendency_free_variables(ntiles, gpu_lib):
     from test_kernels_emulated import check_passive_history
     check_passive_history(S, gpu_lib, B_CASES["LinearAdvectionRLZ_z64_24cells_fused"], ntiles)
+
+
+def test_launcher_two_gpus(gpu_lib, tmp_path):
+    """python -m scythe_jl_b200.run --gpus 2 model.jl (one radial tile per GPU under torchrun / NCCL, rank 0 writes): same
+    final CSV, to round-off, as the 2-tile run on one GPU; checkpoint files are per rank.  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    if gpu_lib.sb_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = Path(__file__).resolve().parent.parent
+    gp = S.GridParameters(geometry="RL", xmin=0.0, xmax=24.0, num_cells=24, BCL={"h": S.CubicBSpline.R1T1, "u": S.CubicBSpline.R1T0,
+                          "v": S.CubicBSpline.R1T0}, BCR={"h": S.CubicBSpline.R0, "u": S.CubicBSpline.R0, "v": S.CubicBSpline.R0},
+                          vars={"h": 1, "u": 2, "v": 3})
+    g = S.createGrid(gp, lib=gpu_lib)
+    pts = S.getGridpoints(g).reshape(g.N, -1)
+    g.close()
+    r, l = pts[:, 0], pts[:, 1]
+    ic = np.stack([r, l, np.exp(-((r * np.cos(l) - 8.0) ** 2 + (r * np.sin(l)) ** 2) / 16.0), 0.5 * np.cos(l), -0.5 * np.sin(l)], 1)
+    np.savetxt(tmp_path / "ic.csv", ic, delimiter=",", header="r,l,h,u,v", comments="", fmt="%.17g")
+
+    def model_text(out):
+        return f'''model = ModelParameters(
+            ts = 0.05, integration_time = 1.0, output_interval = 0.5, equation_set = "LinearAdvectionRL",
+            initial_conditions = "{tmp_path / "ic.csv"}", output_dir = "{out}/",
+            grid_params = GridParameters(geometry = "RL", xmin = 0.0, xmax = 24.0, num_cells = 24,
+                BCL = Dict("h" => CubicBSpline.R1T1, "u" => CubicBSpline.R1T0, "v" => CubicBSpline.R1T0),
+                BCR = Dict("h" => CubicBSpline.R0, "u" => CubicBSpline.R0, "v" => CubicBSpline.R0),
+                vars = Dict("h" => 1, "u" => 2, "v" => 3)),
+            physical_params = Dict(:K => 0.01))'''
+    env = dict(os.environ, PYTHONPATH=str(root) + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    (tmp_path / "one.jl").write_text(model_text(tmp_path / "one"))
+    (tmp_path / "two.jl").write_text(model_text(tmp_path / "two"))
+    a = subprocess.run([sys.executable, "-m", "scythe_jl_b200.run", "-w", "2", str(tmp_path / "one.jl")], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert a.returncode == 0, a.stdout[-2000:] + a.stderr[-2000:]
+    b = subprocess.run([sys.executable, "-m", "scythe_jl_b200.run", "--gpus", "2", "--master-port", str(29500 + os.getpid() % 2000),
+                        "--checkpoint", str(tmp_path / "ck.npz"), str(tmp_path / "two.jl")], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert b.returncode == 0, b.stdout[-3000:] + b.stderr[-3000:]
+    assert "Model complete!" in b.stdout
+    names = sorted(p.name for p in (tmp_path / "two").iterdir())
+    assert names == ["physical_out_0.0.csv", "physical_out_0.5.csv", "physical_out_1.0.csv"]
+    one = np.loadtxt(tmp_path / "one" / "physical_out_1.0.csv", delimiter=",", skiprows=1)
+    two = np.loadtxt(tmp_path / "two" / "physical_out_1.0.csv", delimiter=",", skiprows=1)
+    assert np.array_equal(one[:, :2], two[:, :2])
+    assert rel_err(two[:, 2:], one[:, 2:]) <= 1e-12
+    assert sorted(p.name for p in tmp_path.glob("ck.tiles*.npz")) == ["ck.tiles0-0.npz", "ck.tiles1-1.npz"]
