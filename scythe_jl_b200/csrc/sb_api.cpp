@@ -370,12 +370,14 @@ static void build_grid(sb_grid* G) {
     for (int r = d.rDim - 1; r >= 0; --r) {
       const int L = plans[r].L, cls = plans[r].cls;
       if (!G->classes[cls].fast) continue;
+      // items of (nearly) equal size: ceil(total / k) rows for the k items the target size asks for
+      auto even = [](int total, int nr) { const int k = (total + nr - 1) / nr; return (total + k - 1) / k; };
       if (fft2_supported(L, true)) {
-        const int nr = fft2_rows_per_item(L, true);
+        const int nr = even(d.bz, fft2_rows_per_item(L, true));
         for (int row0 = 0; row0 < d.bz; row0 += nr) G->fwork2[cls].push_back(LWork{r, row0, std::min(nr, d.bz - row0), 0});
       }
       if (fft2_supported(L, false)) {
-        const int nr = fft2_rows_per_item(L, false);
+        const int nr = even(5 * d.bz, fft2_rows_per_item(L, false));
         for (int row0 = 0; row0 < 5 * d.bz; row0 += nr) G->iwork2[cls].push_back(LWork{r, row0, std::min(nr, 5 * d.bz - row0), 0});
       }
     }
