@@ -734,10 +734,11 @@ int fft2_rows_per_item(int L, bool forward) {
   }
   const int T = L / 16, nteams = 512 / T;
   const int wave = forward ? (nteams / 2) : (nteams > 1 ? nteams / 2 : 1);   // rows in flight per CTA
-  // rows per item: 11 / 27 per wave of rows in flight -- at L = 2048 two items of 22 rows per ring forward and four of 54
+  // rows per item: 11 / 27 per wave of rows in flight, at most 22 / 54 -- at L <= 2048 two items of 22 rows per ring forward and four of 54
   // inverse (43 z-modes x 1 | 5 rows); measured at C4 against 16 / 32 (three / seven uneven items): fwd_l 2.66 -> 2.62 ms,
   // inv_l 6.56 -> 6.48 ms; 11 / 108 rows are slower again.  The caller evens the items of a ring out (sb_api.cpp).
-  return (forward ? 11 : 27) * (wave < 1 ? 1 : wave);
+  const int w = wave < 1 ? 1 : (wave > 2 ? 2 : wave);      // (the sweep ran 22 / 54 rows for EVERY class: the shorter classes like them too)
+  return (forward ? 11 : 27) * w;
 }
 
 template <int LOG2L>
