@@ -535,10 +535,19 @@ static void grid_inverse(sb_grid* P, sb_grid* T, const unsigned* need = nullptr,
   // a pass takes consecutive variables that need the SAME slots (up to vchunk of them): the stage masks are per launch, and
   // a union over unlike variables would transform rows nobody reads (the boundary-layer set: ub, vb need five ring rows,
   // the diagnostic wb none)
+  // (launch-bound grids -- C2: 181,800 points, every kernel ~15 us -- take all variables in one pass with the union of their
+  //  masks instead: fewer launches beat fewer rows there)
+  const char* bm = std::getenv("SB_K3_BY_MASK");        // tests: 1 forces the per-mask passes on small grids, 0 the union
+  const bool by_mask = bm ? std::atoi(bm) != 0 : t.N * t.V >= (1LL << 25);
   for (int v0 = 0, nv = 1; v0 < t.V; v0 += nv) {
-    const unsigned slots = chunk_slots(v0, 1);
+    unsigned slots = chunk_slots(v0, 1);
     nv = 1;
-    while (nv < T->vchunk && v0 + nv < t.V && chunk_slots(v0 + nv, 1) == slots) ++nv;
+    if (by_mask) {
+      while (nv < T->vchunk && v0 + nv < t.V && chunk_slots(v0 + nv, 1) == slots) ++nv;
+    } else {
+      nv = std::min(T->vchunk, t.V - v0);
+      slots = chunk_slots(v0, nv);
+    }
     if (!slots) continue;                             // nothing of these variables is read (diagnostic outputs)
     c.need = k3_need_from_slots(t, slots);
     double* SL = T->scratch;                          // [3][vchunk][slN]

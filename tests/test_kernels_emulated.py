@@ -334,3 +334,13 @@ def check_passive_history(S, lib, case, ntiles=1):
 def test_passive_history_of_tendency_free_variables(emu_lib):
     import scythe_jl_b200 as S
     check_passive_history(S, emu_lib, M_CASES["LinearAdvectionRLZ_z16_fused"])
+
+
+@pytest.mark.parametrize("by_mask", ["0", "1"])
+def test_k3_passes_by_mask_and_by_union_leave_the_same_state(by_mask, emu_lib, monkeypatch):
+    """In-step tileTransform! passes either group consecutive variables with identical slot masks (large grids) or take all
+    variables with the union of their masks (launch-bound grids): the boundary-layer set (three different masks, one of them
+    empty) must leave the all-slots state bit for bit either way, with the unread slots poisoned."""
+    from helpers import check_needed_slots
+    monkeypatch.setenv("SB_K3_BY_MASK", by_mask)
+    check_needed_slots(M_CASES["Oneway_ShallowWater_HeightResolvedBL_z16"], emu_lib)
