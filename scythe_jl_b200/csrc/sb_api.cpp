@@ -2053,6 +2053,11 @@ int sb_model_set_state(sb_model_t m, int32_t tile, int32_t which, const double* 
         if ((pm >> v) & 1u)
           for (long long i = 0; i < N; ++i)
             if (host[(long long)v * N + i] != 0.0) { T.hist_untouched = false; break; }
+#ifndef SB_EMU
+      if (!T.hist_untouched)      // step graphs captured so far have the zero-history form of the kernels baked in
+        for (int k = 0; k < 3; ++k)
+          if (m->graph.exec[k]) { cudaGraphExecDestroy(m->graph.exec[k]); m->graph.exec[k] = nullptr; }
+#endif
     }
   });
 }
