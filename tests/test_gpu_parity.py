@@ -450,7 +450,7 @@ def test_reference_state_files(gpu_lib, tmp_path):
 @pytest.mark.parametrize("ntiles", [1, 2])
 def test_passive_history_of_tendency_free_variables(ntiles, gpu_lib):
     from test_kernels_emulated import check_passive_history
-    check_passive_history(S, gpu_lib, B_CASES["LinearAdvectionRLZ_z64_24cells_fused"], ntiles)
+    check_passive_history(S, gpu_lib, B_CASES["LinearAdvectionRLZ_z64_24cells_fused"], ntiles, n0=9, n2=6)
 
 
 def test_launcher_two_gpus(gpu_lib, tmp_path):

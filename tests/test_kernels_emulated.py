@@ -296,7 +296,7 @@ def test_reference_state_files(emu_lib, tmp_path):
     check_reference_state_files(S, emu_lib, tmp_path)
 
 
-def check_passive_history(S, lib, case, ntiles=1):
+def check_passive_history(S, lib, case, ntiles=1, n0=3, n2=3):
     """LinearAdvectionRLZ writes a tendency for h only (src/testModels.jl:93): the fused K3+K4 kernel leaves the u / v
     history arrays alone while they still hold their initial zeros.  (1) the state equals the all-slots path bit for bit,
     history arrays included; (2) once somebody stores a non-zero history for u (sb_model_set_state), the kernel must
@@ -308,7 +308,7 @@ def check_passive_history(S, lib, case, ntiles=1):
         m = pkg_model(case, ntiles, lib)
         m.set_k3_slots(mode)
         m.initialize(case["ic"])
-        m.run(9)      # on the device the last six steps replay CUDA graphs of the step: they must not outlive the guarantee
+        m.run(n0)     # on the device (n0 = 9) the last six steps replay CUDA graphs of the step: they must not outlive the guarantee
         snap = [[m.state(i, k).copy() for k in ("var_np1", "expdot_nm1", "expdot_nm2")] for i in range(ntiles)]
         for i in range(ntiles):
             h = m.state(i, "expdot_nm1")
@@ -320,7 +320,7 @@ def check_passive_history(S, lib, case, ntiles=1):
             h = m.state(i, "expdot_nm1")
             h[:, 1] = 1e-3 * np.cos(np.arange(h.shape[0]))  # a history for u from outside
             m.lib.check(m.lib.sb_model_set_state(m.handle, i, 2, S.api._ptr(np.asfortranarray(h))))
-        m.run(6)
+        m.run(n2)
         snap3 = [[m.state(i, k).copy() for k in ("var_np1", "expdot_nm1", "expdot_nm2")] for i in range(ntiles)]
         runs[mode] = (snap, snap2, snap3)
         m.close()
