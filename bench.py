@@ -365,7 +365,9 @@ def run_ours(args):
     else:
         m = S.Model(mp, num_tiles=ntiles, device=local_rank, distributed=distributed)
     cfg_exchange = m.exchange
-    Sp = m.patch.S
+    # spline coefficients this rank SOLVES per variable: the whole patch when the solve is replicated (one tile, or the
+    # reference's all-reduce scheme), its share of the z-mode planes when the columns are dealt over the ranks
+    Sp = m.patch.S / world if (m.columns and world > 1) else m.patch.S
     tp = m.tile_params
     tcells, tsil = int(tp[2, m.tile_first]), int(tp[3, m.tile_first])
     ic = (synthetic_state_tcbl if tcbl else synthetic_state)(tp[0, m.tile_first], DX, tcells, (tsil - 1) * 3, ZDIM, ZMAX)
